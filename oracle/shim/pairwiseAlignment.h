@@ -1,0 +1,43 @@
+/*
+ * oracle/shim/pairwiseAlignment.h -- TEST INFRASTRUCTURE ONLY (see sonLib.h in this directory).
+ * Shape of sonLib's cigar structs as the reference's convertPairwiseForwardStrandAlignmentToAnchorPairs
+ * (impl/pairwiseAligner.c:979-1003) touches them.
+ */
+#ifndef ORACLE_SHIM_PAIRWISEALIGNMENT_H_
+#define ORACLE_SHIM_PAIRWISEALIGNMENT_H_
+
+#include <stdint.h>
+
+#define PAIRWISE_INDEL_X 0
+#define PAIRWISE_INDEL_Y 1
+#define PAIRWISE_MATCH 2
+
+struct List {
+    void **list;
+    int64_t length;
+    int64_t maxLength;
+    void (*destroyElement)(void *);
+};
+
+struct AlignmentOperation {
+    int64_t opType;
+    int64_t length;
+    float score;
+};
+
+struct PairwiseAlignment {
+    char *contig1;
+    int64_t start1;
+    int64_t end1;
+    int64_t strand1;
+    char *contig2;
+    int64_t start2;
+    int64_t end2;
+    int64_t strand2;
+    float score;
+    struct List *operationList;
+};
+
+void destructPairwiseAlignment(struct PairwiseAlignment *pA);
+
+#endif
