@@ -1,0 +1,834 @@
+/*
+ * engine.cu -- host orchestration of libcpecan_b200 (C-ABI in include/cpecan_b200.h).
+ *
+ * One batch run =
+ *   host : split every pair at large anchor gaps into regions (cpb_split_points; reference
+ *          getPosteriorProbsWithBandingSplittingAlignmentsByLargeGaps, impl/pairwiseAligner.c:1273-1326)
+ *   K1   : device band builder + traceback schedule, one small D2H of per-region sizes
+ *   host : pack regions into chunks that fit the scratch budget, bucket work by band width
+ *   per chunk: k_forward -> k_backward -> k_totals -> k_posterior (count, write) | k_expect
+ * There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cpecan_b200.h"
+#include "internal.h"
+#include "kernels.cuh"
+
+using namespace cpb;
+
+/* ------------------------------------------------------------------------------------------------ */
+static thread_local char g_error[1024] = "";
+
+extern "C" void cpb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *cpb_last_error(void) { return g_error; }
+extern "C" const char *cpb_version(void) { return "cpecan_b200 0.1 (sm_100a)"; }
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            cpb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return CPB_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+/* grow-only device buffer */
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return CPB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            cpb_set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            (void) cudaGetLastError();
+            return CPB_ERR_MEMORY;
+        }
+        cap = bytes;
+        return CPB_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * width classes: window capacity (cells per diagonal) -> warps per CTA
+ * ---------------------------------------------------------------------------------------------- */
+static const int kNumClasses = 7; /* 32, 64, 128, 256, 512, 1024, 2048 */
+static int g_classWarps[kNumClasses] = { 1, 1, 1, 2, 4, 8, 8 };
+
+static int class_of_width(int w) {
+    int c = 0, cap = 32;
+    while (cap < w && c < kNumClasses) {
+        cap <<= 1;
+        c++;
+    }
+    return c; /* == kNumClasses when too wide */
+}
+static int class_wcap(int c) { return 32 << c; }
+
+template <int S> static size_t dp_smem_bytes(int wcap) {
+    return ((sizeof(Tables<S>) + 15) & ~size_t(15)) + size_t(2) * S * wcap * sizeof(double);
+}
+
+typedef void (*DpKernel)(const DpArgs, const CpbModel);
+
+template <int S> static DpKernel forward_kernel(int warps) {
+    switch (warps) {
+    case 1: return k_forward<S, 1>;
+    case 2: return k_forward<S, 2>;
+    case 4: return k_forward<S, 4>;
+    default: return k_forward<S, 8>;
+    }
+}
+template <int S> static DpKernel backward_kernel(int warps) {
+    switch (warps) {
+    case 1: return k_backward<S, 1>;
+    case 2: return k_backward<S, 2>;
+    case 4: return k_backward<S, 4>;
+    default: return k_backward<S, 8>;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+struct cpb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    size_t scratchBudget = 0;
+    DevBuf scratch;
+};
+
+static int configure_kernels() {
+    const int maxSmem = 227 * 1024;
+    const int warpsList[4] = { 1, 2, 4, 8 };
+    for (int wi = 0; wi < 4; wi++) {
+        const int w = warpsList[wi];
+        CUDA_TRY(cudaFuncSetAttribute((const void *) forward_kernel<5>(w), cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CUDA_TRY(cudaFuncSetAttribute((const void *) forward_kernel<3>(w), cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CUDA_TRY(cudaFuncSetAttribute((const void *) backward_kernel<5>(w), cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CUDA_TRY(cudaFuncSetAttribute((const void *) backward_kernel<3>(w), cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    }
+    CUDA_TRY(cudaFuncSetAttribute((const void *) k_expect<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    CUDA_TRY(cudaFuncSetAttribute((const void *) k_expect<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    return CPB_OK;
+}
+
+extern "C" int cpb_context_create(int device, void *stream, cpb_context **out) {
+    if (out == nullptr) return CPB_ERR_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cpb_set_error("no CUDA device available (%s); libcpecan_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        (void) cudaGetLastError();
+        return CPB_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        cpb_set_error("device %d out of range (have %d)", device, count);
+        return CPB_ERR_ARGUMENT;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cpb_context *ctx = new cpb_context();
+    ctx->device = device;
+    if (stream != nullptr) {
+        ctx->stream = (cudaStream_t) stream;
+    } else {
+        cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e2 != cudaSuccess) {
+            cpb_set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e2));
+            delete ctx;
+            return CPB_ERR_CUDA;
+        }
+        ctx->ownStream = true;
+    }
+    const char *w = getenv("CPB_CLASS_WARPS"); /* tuning knob: warps per CTA for the 7 width classes, e.g. "1,1,1,2,4,8,8" */
+    if (w != nullptr) {
+        int v[kNumClasses];
+        if (sscanf(w, "%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]) == kNumClasses) {
+            for (int i = 0; i < kNumClasses; i++) {
+                if (v[i] == 1 || v[i] == 2 || v[i] == 4 || v[i] == 8) g_classWarps[i] = v[i];
+            }
+        }
+    }
+    int rc = configure_kernels();
+    if (rc != CPB_OK) {
+        if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return CPB_OK;
+}
+
+extern "C" void cpb_context_destroy(cpb_context *ctx) {
+    if (ctx == nullptr) return;
+    cudaSetDevice(ctx->device);
+    ctx->scratch.release();
+    if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" void cpb_context_set_scratch_budget(cpb_context *ctx, size_t bytes) {
+    if (ctx) ctx->scratchBudget = bytes;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+struct Chunk {
+    int64_t region0, region1; /* [region0, region1) */
+    int64_t block0, block1;   /* positions in the compact block order */
+    int64_t cells, aux;
+    int64_t stride;
+    int64_t fwdListOff[kNumClasses + 1]; /* offsets into the forward list array */
+    int64_t bwdListOff[kNumClasses + 1];
+    int64_t allBlocksOff;                /* offset of the chunk's in-order block list */
+    int64_t pair0, pair1;                /* pairs touched: [pair0, pair1] inclusive */
+};
+
+struct cpb_batch {
+    cpb_context *ctx = nullptr;
+    int64_t n = 0;
+    std::vector<int64_t> xOff, yOff, aOff, anchors;
+    std::vector<uint8_t> rl, rr;
+    DevBuf symX, symY, dAnchors;
+    /* run state */
+    DevBuf regions, diags, blocks, totals, lists, counts, offsets, partials, pairBlockOff, perPair, hmmTotal, forwardOut;
+    DevBuf out[3];
+    int64_t outCount[3] = { 0, 0, 0 };
+    std::vector<int64_t> pairOff[3]; /* n+1 */
+    int lastMode = -1, lastS = 0;
+    CpbRunStats stats;
+    std::vector<RegionDev> hRegions;
+    std::vector<BlockRec> hBlocks; /* compact, region order */
+};
+
+extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *seqX, const int64_t *xOff, const char *seqY, const int64_t *yOff,
+                                const int64_t *anchors, const int64_t *anchorOff, const uint8_t *raggedLeft, const uint8_t *raggedRight,
+                                cpb_batch **out) {
+    if (ctx == nullptr || out == nullptr || nPairs < 0 || xOff == nullptr || yOff == nullptr) {
+        cpb_set_error("cpb_batch_create: bad argument");
+        return CPB_ERR_ARGUMENT;
+    }
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cpb_batch *b = new cpb_batch();
+    b->ctx = ctx;
+    b->n = nPairs;
+    b->xOff.assign(xOff, xOff + nPairs + 1);
+    b->yOff.assign(yOff, yOff + nPairs + 1);
+    if (anchorOff != nullptr) b->aOff.assign(anchorOff, anchorOff + nPairs + 1);
+    else b->aOff.assign(nPairs + 1, 0);
+    const int64_t nA = b->aOff[nPairs];
+    if (nA > 0) b->anchors.assign(anchors, anchors + 3 * nA);
+    b->rl.assign(nPairs, 0);
+    b->rr.assign(nPairs, 0);
+    if (raggedLeft) b->rl.assign(raggedLeft, raggedLeft + nPairs);
+    if (raggedRight) b->rr.assign(raggedRight, raggedRight + nPairs);
+    memset(&b->stats, 0, sizeof(b->stats));
+
+    const int64_t nx = xOff[nPairs], ny = yOff[nPairs];
+    int rc = CPB_OK;
+    if ((rc = b->symX.reserve(std::max<int64_t>(nx, 1))) != CPB_OK || (rc = b->symY.reserve(std::max<int64_t>(ny, 1))) != CPB_OK ||
+        (rc = b->dAnchors.reserve(std::max<int64_t>(nA, 1) * 3 * sizeof(int32_t))) != CPB_OK) {
+        cpb_batch_destroy(b);
+        return rc;
+    }
+    cudaStream_t st = ctx->stream;
+    if (nx > 0) {
+        CUDA_TRY(cudaMemcpyAsync(b->symX.p, seqX, nx, cudaMemcpyHostToDevice, st));
+        k_encode<<<(unsigned) ((nx + 255) / 256), 256, 0, st>>>(b->symX.as<uint8_t>(), nx);
+    }
+    if (ny > 0) {
+        CUDA_TRY(cudaMemcpyAsync(b->symY.p, seqY, ny, cudaMemcpyHostToDevice, st));
+        k_encode<<<(unsigned) ((ny + 255) / 256), 256, 0, st>>>(b->symY.as<uint8_t>(), ny);
+    }
+    if (nA > 0) {
+        std::vector<int32_t> a32(3 * nA);
+        for (int64_t i = 0; i < 3 * nA; i++) a32[i] = (int32_t) anchors[i];
+        CUDA_TRY(cudaMemcpyAsync(b->dAnchors.p, a32.data(), a32.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st)); /* a32 is a temporary */
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    *out = b;
+    return CPB_OK;
+}
+
+extern "C" void cpb_batch_destroy(cpb_batch *b) {
+    if (b == nullptr) return;
+    cudaSetDevice(b->ctx->device);
+    DevBuf *bufs[] = { &b->symX, &b->symY, &b->dAnchors, &b->regions, &b->diags, &b->blocks, &b->totals, &b->lists, &b->counts,
+                       &b->offsets, &b->partials, &b->pairBlockOff, &b->perPair, &b->hmmTotal, &b->forwardOut, &b->out[0], &b->out[1],
+                       &b->out[2] };
+    for (DevBuf *d : bufs) d->release();
+    delete b;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * region construction on the host
+ * ---------------------------------------------------------------------------------------------- */
+static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
+    b->hRegions.clear();
+    std::vector<int64_t> split;
+    int64_t diagBase = 0, blockBase = 0;
+    for (int64_t i = 0; i < b->n; i++) {
+        const int64_t lX = b->xOff[i + 1] - b->xOff[i], lY = b->yOff[i + 1] - b->yOff[i];
+        const int64_t a0 = b->aOff[i], nA = b->aOff[i + 1] - a0;
+        const int64_t *an = b->anchors.data() + 3 * a0;
+        int64_t nReg = 1;
+        if (mode == CPB_MODE_FORWARD) {
+            split.assign({ 0, 0, lX, lY });
+        } else {
+            split.resize(4 * 4);
+            nReg = cpb_split_points(an, nA, lX, lY, p->splitMatrixBiggerThanThis, b->rl[i], b->rr[i], split.data(), 4);
+            if (nReg > 4) {
+                split.resize(4 * nReg);
+                nReg = cpb_split_points(an, nA, lX, lY, p->splitMatrixBiggerThanThis, b->rl[i], b->rr[i], split.data(), nReg);
+            }
+        }
+        int64_t j = 0;
+        for (int64_t r = 0; r < nReg; r++) {
+            const int64_t x1 = split[4 * r], y1 = split[4 * r + 1], x2 = split[4 * r + 2], y2 = split[4 * r + 3];
+            RegionDev R;
+            memset(&R, 0, sizeof(R));
+            R.xBase = b->xOff[i] + x1;
+            R.yBase = b->yOff[i] + y1;
+            R.anchorBase = a0 + j;
+            int64_t cnt = 0;
+            /* anchors of this region: up to the first one on or past the region's last diagonal (impl/pairwiseAligner.c:1296-1308) */
+            while (j < nA && an[3 * j] + an[3 * j + 1] < x2 + y2) {
+                j++;
+                cnt++;
+            }
+            R.nAnchors = (int32_t) cnt;
+            R.lX = (int32_t) (x2 - x1);
+            R.lY = (int32_t) (y2 - y1);
+            R.pair = (int32_t) i;
+            R.ox = (int32_t) x1;
+            R.oy = (int32_t) y1;
+            if (mode == CPB_MODE_FORWARD) {
+                R.raggedL = b->rl[i];
+                R.raggedR = b->rr[i];
+            } else {
+                R.raggedL = b->rl[i] || r > 0;
+                R.raggedR = b->rr[i] || r < nReg - 1;
+            }
+            const int64_t N = (int64_t) R.lX + R.lY;
+            R.diagBase = diagBase;
+            R.blockBase = blockBase;
+            R.blockCap = (int32_t) (N / p->minDiagsBetweenTraceBack + 2);
+            diagBase += N + 2;
+            blockBase += R.blockCap;
+            b->hRegions.push_back(R);
+        }
+    }
+    return CPB_OK;
+}
+
+static int check_params(const CpbParams *p) {
+    /* the reference's preconditions, impl/pairwiseAligner.c:761-765 */
+    if (p->traceBackDiagonals < 1 || p->diagonalExpansion < 0 || p->diagonalExpansion % 2 != 0 || p->minDiagsBetweenTraceBack < 2 ||
+        p->traceBackDiagonals + 1 >= p->minDiagsBetweenTraceBack) {
+        cpb_set_error("invalid PairwiseAlignmentParameters: traceBackDiagonals %lld, diagonalExpansion %lld, minDiagsBetweenTraceBack %lld",
+                      (long long) p->traceBackDiagonals, (long long) p->diagonalExpansion, (long long) p->minDiagsBetweenTraceBack);
+        return CPB_ERR_ARGUMENT;
+    }
+    if (!(p->threshold >= 0.0 && p->threshold <= 1.0)) {
+        cpb_set_error("threshold %g outside [0,1]", p->threshold);
+        return CPB_ERR_ARGUMENT;
+    }
+    return CPB_OK;
+}
+
+struct EventPair {
+    cudaEvent_t a, b;
+    double *sink;
+};
+
+/* ------------------------------------------------------------------------------------------------ */
+template <int S>
+static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mode) {
+    cpb_context *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    CpbRunStats &stx = b->stats;
+    memset(&stx, 0, sizeof(stx));
+    stx.nPairs = b->n;
+    std::vector<EventPair> events;
+    auto tic = [&](double *sink) {
+        EventPair e;
+        cudaEventCreate(&e.a);
+        cudaEventCreate(&e.b);
+        e.sink = sink;
+        cudaEventRecord(e.a, st);
+        events.push_back(e);
+        return events.size() - 1;
+    };
+    auto toc = [&](size_t id) { cudaEventRecord(events[id].b, st); };
+    auto finish_events = [&]() {
+        for (auto &e : events) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) *e.sink += ms;
+            cudaEventDestroy(e.a);
+            cudaEventDestroy(e.b);
+        }
+        events.clear();
+    };
+
+    const int nPlanes = mode == CPB_MODE_FORWARD ? 0 : (mode == CPB_MODE_ALIGNED_PAIRS ? 1 : (mode == CPB_MODE_ALIGNED_PAIRS_INDELS ? 3 : S));
+    const int auxF = (mode == CPB_MODE_ALIGNED_PAIRS || mode == CPB_MODE_ALIGNED_PAIRS_INDELS) ? S : 0;
+    const int nLists = mode == CPB_MODE_ALIGNED_PAIRS ? 1 : (mode == CPB_MODE_ALIGNED_PAIRS_INDELS ? 3 : 0);
+    const int hmmLen = CPB_HMM_LEN(S);
+
+    int rc = build_regions(b, p, mode);
+    if (rc != CPB_OK) return rc;
+    std::vector<RegionDev> &regs = b->hRegions;
+    const int64_t nReg = (int64_t) regs.size();
+    stx.nRegions = nReg;
+    for (int l = 0; l < 3; l++) {
+        b->outCount[l] = 0;
+        b->pairOff[l].assign(b->n + 1, 0);
+    }
+    b->lastMode = mode;
+    b->lastS = S;
+    if (mode == CPB_MODE_EXPECTATIONS) {
+        if ((rc = b->perPair.reserve(std::max<int64_t>(b->n, 1) * hmmLen * sizeof(double))) != CPB_OK) return rc;
+        if ((rc = b->hmmTotal.reserve(hmmLen * sizeof(double))) != CPB_OK) return rc;
+        CUDA_TRY(cudaMemsetAsync(b->perPair.p, 0, std::max<int64_t>(b->n, 1) * hmmLen * sizeof(double), st));
+        CUDA_TRY(cudaMemsetAsync(b->hmmTotal.p, 0, hmmLen * sizeof(double), st));
+    }
+    if (nReg == 0) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return CPB_OK;
+    }
+    const int64_t nDiagRecs = regs.back().diagBase + regs.back().lX + regs.back().lY + 2;
+    const int64_t blockSlots = regs.back().blockBase + regs.back().blockCap;
+    stx.diagonals = nDiagRecs - 2 * nReg + nReg; /* lX+lY+1 per region */
+
+    if ((rc = b->regions.reserve(nReg * sizeof(RegionDev))) != CPB_OK) return rc;
+    if ((rc = b->diags.reserve(nDiagRecs * sizeof(DiagRec))) != CPB_OK) return rc;
+    if ((rc = b->blocks.reserve(blockSlots * sizeof(BlockRec))) != CPB_OK) return rc;
+    if (mode != CPB_MODE_FORWARD) {
+        if ((rc = b->totals.reserve(nDiagRecs * sizeof(double))) != CPB_OK) return rc;
+    } else {
+        if ((rc = b->forwardOut.reserve(nReg * sizeof(double))) != CPB_OK) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->regions.p, regs.data(), nReg * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
+
+    /* K1: band + schedule */
+    {
+        BandArgs ba;
+        ba.regions = b->regions.as<RegionDev>();
+        ba.anchors = b->dAnchors.as<int32_t>();
+        ba.diags = b->diags.as<DiagRec>();
+        ba.blocks = b->blocks.as<BlockRec>();
+        ba.nRegions = (int32_t) nReg;
+        ba.expansion = (int32_t) p->diagonalExpansion;
+        ba.dynamic = (mode == CPB_MODE_FORWARD) ? 0 : (p->dynamicAnchorExpansion != 0); /* forward prob always uses the static band (:894) */
+        ba.minDiags = (int32_t) p->minDiagsBetweenTraceBack;
+        ba.traceBack = (int32_t) p->traceBackDiagonals;
+        ba.auxF = auxF;
+        ba.scheduleOn = mode != CPB_MODE_FORWARD;
+        size_t ev = tic(&stx.msBand);
+        k_band<<<(unsigned) ((nReg + 63) / 64), 64, 0, st>>>(ba);
+        toc(ev);
+        stx.kernelLaunches++;
+    }
+    CUDA_TRY(cudaMemcpyAsync(regs.data(), b->regions.p, nReg * sizeof(RegionDev), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+
+    /* validate, gather the block table in compact region order */
+    int64_t totalBlocks = 0;
+    for (int64_t r = 0; r < nReg; r++) {
+        if (regs[r].err == 1) {
+            cpb_set_error("pair %d: anchors produce an invalid band diagonal (PAIRWISE_ALIGNMENT_EXCEPTION in the reference)", regs[r].pair);
+            finish_events();
+            return CPB_ERR_BAND;
+        }
+        if (regs[r].err == 2) {
+            cpb_set_error("internal: traceback block table overflow for pair %d", regs[r].pair);
+            finish_events();
+            return CPB_ERR_BAND;
+        }
+        if (class_of_width(regs[r].maxW) >= kNumClasses) {
+            cpb_set_error("pair %d: band is %d cells wide; the widest kernel configuration holds %d", regs[r].pair, regs[r].maxW,
+                          class_wcap(kNumClasses - 1));
+            finish_events();
+            return CPB_ERR_BAND_TOO_WIDE;
+        }
+        totalBlocks += regs[r].nBlocks;
+        stx.cells += regs[r].cells;
+        stx.maxWidth = std::max(stx.maxWidth, regs[r].maxW);
+    }
+    stx.nBlocks = totalBlocks;
+    std::vector<BlockRec> &hBlocks = b->hBlocks;
+    hBlocks.resize(totalBlocks);
+    std::vector<int64_t> regionBlock0(nReg + 1, 0);
+    if (totalBlocks > 0) {
+        std::vector<BlockRec> slots(blockSlots);
+        CUDA_TRY(cudaMemcpy(slots.data(), b->blocks.p, blockSlots * sizeof(BlockRec), cudaMemcpyDeviceToHost));
+        int64_t k = 0;
+        for (int64_t r = 0; r < nReg; r++) {
+            regionBlock0[r] = k;
+            for (int j = 0; j < regs[r].nBlocks; j++) hBlocks[k++] = slots[regs[r].blockBase + j];
+        }
+        regionBlock0[nReg] = k;
+        CUDA_TRY(cudaMemcpyAsync(b->blocks.p, hBlocks.data(), totalBlocks * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
+    }
+
+    /* chunk planning */
+    size_t freeB = 0, totalB = 0;
+    CUDA_TRY(cudaMemGetInfo(&freeB, &totalB));
+    size_t budget = ctx->scratchBudget ? ctx->scratchBudget : (size_t) ((double) (freeB + ctx->scratch.cap) * 0.70);
+    const int64_t bytesPerCell = (int64_t) sizeof(double) * 2 * nPlanes;
+    std::vector<Chunk> chunks;
+    {
+        int64_t r = 0;
+        while (r < nReg) {
+            Chunk c;
+            memset(&c, 0, sizeof(c));
+            c.region0 = r;
+            int64_t cells = 0, aux = 0;
+            while (r < nReg) {
+                const int64_t nc = cells + regs[r].cells + 32, na = aux + regs[r].auxDoubles + 4;
+                if (r > c.region0 && (size_t) (nc * bytesPerCell + na * 8) > budget) break;
+                regs[r].cellBase = cells;
+                regs[r].auxBase = aux;
+                cells = (nc + 3) & ~int64_t(3);
+                aux = (na + 1) & ~int64_t(1);
+                r++;
+            }
+            c.region1 = r;
+            c.cells = cells;
+            c.aux = aux;
+            c.stride = (cells + 31) & ~int64_t(31);
+            c.block0 = regionBlock0[c.region0];
+            c.block1 = regionBlock0[c.region1];
+            c.pair0 = regs[c.region0].pair;
+            c.pair1 = regs[c.region1 - 1].pair;
+            chunks.push_back(c);
+        }
+    }
+    stx.nChunks = (int64_t) chunks.size();
+    size_t scratchNeed = 0;
+    for (auto &c : chunks) scratchNeed = std::max(scratchNeed, (size_t) (c.stride * bytesPerCell + c.aux * 8 + 256));
+    if ((rc = ctx->scratch.reserve(std::max<size_t>(scratchNeed, 256))) != CPB_OK) return rc;
+
+    /* launch lists: forward regions per class, backward blocks per class, all blocks in order */
+    std::vector<int32_t> lists;
+    for (auto &c : chunks) {
+        std::vector<std::vector<int32_t>> byClass(kNumClasses);
+        for (int64_t r = c.region0; r < c.region1; r++) byClass[class_of_width(regs[r].maxW)].push_back((int32_t) r);
+        for (int k = 0; k < kNumClasses; k++) {
+            c.fwdListOff[k] = (int64_t) lists.size();
+            lists.insert(lists.end(), byClass[k].begin(), byClass[k].end());
+        }
+        c.fwdListOff[kNumClasses] = (int64_t) lists.size();
+        for (auto &v : byClass) v.clear();
+        for (int64_t k = c.block0; k < c.block1; k++) byClass[class_of_width(hBlocks[k].maxW)].push_back((int32_t) k);
+        for (int k = 0; k < kNumClasses; k++) {
+            c.bwdListOff[k] = (int64_t) lists.size();
+            lists.insert(lists.end(), byClass[k].begin(), byClass[k].end());
+        }
+        c.bwdListOff[kNumClasses] = (int64_t) lists.size();
+        c.allBlocksOff = (int64_t) lists.size();
+        for (int64_t k = c.block0; k < c.block1; k++) lists.push_back((int32_t) k);
+    }
+    if ((rc = b->lists.reserve(std::max<size_t>(lists.size(), 1) * sizeof(int32_t))) != CPB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(b->lists.p, lists.data(), lists.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->regions.p, regs.data(), nReg * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
+
+    int64_t maxChunkBlocks = 1;
+    for (auto &c : chunks) maxChunkBlocks = std::max(maxChunkBlocks, c.block1 - c.block0);
+    if (nLists > 0) {
+        if ((rc = b->counts.reserve(maxChunkBlocks * 3 * sizeof(int64_t))) != CPB_OK) return rc;
+        if ((rc = b->offsets.reserve(maxChunkBlocks * 3 * sizeof(int64_t))) != CPB_OK) return rc;
+    }
+    if (mode == CPB_MODE_EXPECTATIONS) {
+        if ((rc = b->partials.reserve(maxChunkBlocks * hmmLen * sizeof(double))) != CPB_OK) return rc;
+        if ((rc = b->pairBlockOff.reserve((b->n + 2) * sizeof(int64_t))) != CPB_OK) return rc;
+    }
+
+    std::vector<int64_t> hCounts, hOffsets, hPairBlockOff;
+    int64_t running[3] = { 0, 0, 0 };
+    std::vector<std::vector<int64_t>> pairCount(3, std::vector<int64_t>(nLists > 0 ? b->n : 0, 0));
+
+    for (auto &c : chunks) {
+        DpArgs a;
+        memset(&a, 0, sizeof(a));
+        a.regions = b->regions.as<RegionDev>();
+        a.blocks = b->blocks.as<BlockRec>();
+        a.diags = b->diags.as<DiagRec>();
+        a.symX = b->symX.as<uint8_t>();
+        a.symY = b->symY.as<uint8_t>();
+        double *scr = ctx->scratch.as<double>();
+        a.planesF = scr;
+        a.planesB = scr + (int64_t) nPlanes * c.stride;
+        a.aux = scr + (int64_t) 2 * nPlanes * c.stride;
+        a.totals = b->totals.as<double>();
+        a.planeStride = c.stride;
+        a.nPlanes = nPlanes;
+        a.auxF = auxF;
+        a.forwardOut = mode == CPB_MODE_FORWARD ? b->forwardOut.as<double>() : nullptr;
+        const int32_t *dLists = b->lists.as<int32_t>();
+
+        size_t ev = tic(&stx.msForward);
+        for (int k = 0; k < kNumClasses; k++) {
+            const int64_t cnt = c.fwdListOff[k + 1] - c.fwdListOff[k];
+            if (cnt == 0) continue;
+            a.wcap = class_wcap(k);
+            a.list = dLists + c.fwdListOff[k];
+            const int warps = g_classWarps[k];
+            forward_kernel<S>(warps)<<<(unsigned) cnt, 32 * warps, dp_smem_bytes<S>(a.wcap), st>>>(a, *m);
+            stx.kernelLaunches++;
+        }
+        toc(ev);
+        if (mode == CPB_MODE_FORWARD) continue;
+
+        const int64_t nb = c.block1 - c.block0;
+        if (nb == 0) continue;
+        ev = tic(&stx.msBackward);
+        for (int k = 0; k < kNumClasses; k++) {
+            const int64_t cnt = c.bwdListOff[k + 1] - c.bwdListOff[k];
+            if (cnt == 0) continue;
+            a.wcap = class_wcap(k);
+            a.list = dLists + c.bwdListOff[k];
+            const int warps = g_classWarps[k];
+            backward_kernel<S>(warps)<<<(unsigned) cnt, 32 * warps, dp_smem_bytes<S>(a.wcap), st>>>(a, *m);
+            stx.kernelLaunches++;
+        }
+        toc(ev);
+
+        a.list = dLists + c.allBlocksOff;
+        ev = tic(&stx.msTotals);
+        k_totals<<<(unsigned) ((nb * 32 + 127) / 128), 128, 0, st>>>(a, (int) nb);
+        stx.kernelLaunches++;
+        toc(ev);
+
+        if (nLists > 0) {
+            PostArgs pa;
+            memset(&pa, 0, sizeof(pa));
+            pa.threshold = p->threshold;
+            pa.logThresholdLo = p->threshold > 0.0 ? log(p->threshold) - 1e-6 : -INFINITY;
+            pa.nLists = nLists;
+            pa.counts = b->counts.as<int64_t>();
+            pa.offsets = b->offsets.as<int64_t>();
+            ev = tic(&stx.msPosterior);
+            k_posterior<false><<<(unsigned) ((nb * 32 + 127) / 128), 128, 0, st>>>(a, pa, (int) nb);
+            stx.kernelLaunches++;
+            toc(ev);
+            hCounts.resize(nb * 3);
+            CUDA_TRY(cudaMemcpyAsync(hCounts.data(), b->counts.p, nb * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            hOffsets.resize(nb * 3);
+            for (int64_t k = 0; k < nb; k++) {
+                const int pair = regs[hBlocks[c.block0 + k].region].pair;
+                for (int l = 0; l < nLists; l++) {
+                    hOffsets[k * 3 + l] = running[l];
+                    running[l] += hCounts[k * 3 + l];
+                    pairCount[l][pair] += hCounts[k * 3 + l];
+                }
+            }
+            for (int l = 0; l < nLists; l++) {
+                const size_t need = (size_t) std::max<int64_t>(running[l], 1) * 3 * sizeof(int32_t);
+                if (need > b->out[l].cap) {
+                    /* grow, keeping what earlier chunks wrote */
+                    DevBuf bigger;
+                    if ((rc = bigger.reserve(std::max(need + need / 2, (size_t) 1 << 20))) != CPB_OK) return rc;
+                    if (b->out[l].p && hOffsets[l] > 0)
+                        CUDA_TRY(cudaMemcpyAsync(bigger.p, b->out[l].p, (size_t) hOffsets[l] * 3 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                    b->out[l].release();
+                    b->out[l] = bigger;
+                }
+                pa.out[l] = b->out[l].as<int32_t>();
+            }
+            CUDA_TRY(cudaMemcpyAsync(b->offsets.p, hOffsets.data(), nb * 3 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+            ev = tic(&stx.msPosterior);
+            k_posterior<true><<<(unsigned) ((nb * 32 + 127) / 128), 128, 0, st>>>(a, pa, (int) nb);
+            stx.kernelLaunches++;
+            toc(ev);
+            CUDA_TRY(cudaStreamSynchronize(st)); /* hOffsets is reused by the next chunk */
+        } else if (mode == CPB_MODE_EXPECTATIONS) {
+            const size_t smem = ((sizeof(Tables<S>) + 15) & ~size_t(15)) + (size_t) S * 16 * 32 * sizeof(double);
+            ev = tic(&stx.msPosterior);
+            k_expect<S><<<(unsigned) nb, 32, smem, st>>>(a, *m, b->partials.as<double>());
+            stx.kernelLaunches++;
+            const int64_t np = c.pair1 - c.pair0 + 1;
+            hPairBlockOff.assign(np + 1, 0);
+            for (int64_t k = 0; k < nb; k++) hPairBlockOff[regs[hBlocks[c.block0 + k].region].pair - c.pair0 + 1]++;
+            for (int64_t q = 0; q < np; q++) hPairBlockOff[q + 1] += hPairBlockOff[q];
+            CUDA_TRY(cudaMemcpyAsync(b->pairBlockOff.p, hPairBlockOff.data(), (np + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+            k_reduce_pairs<<<(unsigned) ((np * hmmLen + 127) / 128), 128, 0, st>>>(b->partials.as<double>(), b->pairBlockOff.as<int64_t>(),
+                                                                                    (int) np, hmmLen, b->perPair.as<double>() + c.pair0 * hmmLen);
+            stx.kernelLaunches++;
+            toc(ev);
+            CUDA_TRY(cudaStreamSynchronize(st)); /* hPairBlockOff is reused */
+        }
+    }
+    if (mode == CPB_MODE_EXPECTATIONS) {
+        size_t ev = tic(&stx.msPosterior);
+        k_reduce_total<<<1, 128, 0, st>>>(b->perPair.as<double>(), (int) b->n, hmmLen, b->hmmTotal.as<double>());
+        stx.kernelLaunches++;
+        toc(ev);
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    finish_events();
+    for (int l = 0; l < nLists; l++) {
+        b->outCount[l] = running[l];
+        stx.outputTriples += running[l];
+        for (int64_t i = 0; i < b->n; i++) b->pairOff[l][i + 1] = b->pairOff[l][i] + pairCount[l][i];
+    }
+    return CPB_OK;
+}
+
+extern "C" int cpb_batch_run(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mode) {
+    if (b == nullptr || m == nullptr || p == nullptr || mode < CPB_MODE_ALIGNED_PAIRS || mode > CPB_MODE_FORWARD) {
+        cpb_set_error("cpb_batch_run: bad argument");
+        return CPB_ERR_ARGUMENT;
+    }
+    int rc = check_params(p);
+    if (rc != CPB_OK) return rc;
+    CUDA_TRY(cudaSetDevice(b->ctx->device));
+    if (m->stateNumber == 5) return run_impl<5>(b, m, p, mode);
+    if (m->stateNumber == 3) return run_impl<3>(b, m, p, mode);
+    cpb_set_error("cpb_batch_run: model has %d states (3 or 5 supported)", m->stateNumber);
+    return CPB_ERR_ARGUMENT;
+}
+
+extern "C" void cpb_batch_stats(const cpb_batch *b, CpbRunStats *out) {
+    if (b && out) *out = b->stats;
+}
+
+extern "C" int64_t cpb_batch_result_count(const cpb_batch *b, int list) {
+    if (b == nullptr || list < 0 || list > 2) return 0;
+    return b->outCount[list];
+}
+
+extern "C" const int32_t *cpb_batch_device_triples(const cpb_batch *b, int list) {
+    if (b == nullptr || list < 0 || list > 2) return nullptr;
+    return b->out[list].as<int32_t>();
+}
+
+extern "C" int cpb_batch_fetch_pairs(cpb_batch *b, int list, int64_t *offsets, int32_t *triples) {
+    if (b == nullptr || list < 0 || list > 2 || (b->lastMode != CPB_MODE_ALIGNED_PAIRS && b->lastMode != CPB_MODE_ALIGNED_PAIRS_INDELS)) {
+        cpb_set_error("cpb_batch_fetch_pairs: no aligned-pair results in this batch");
+        return CPB_ERR_ARGUMENT;
+    }
+    CUDA_TRY(cudaSetDevice(b->ctx->device));
+    if (offsets) memcpy(offsets, b->pairOff[list].data(), (b->n + 1) * sizeof(int64_t));
+    if (triples && b->outCount[list] > 0) {
+        CUDA_TRY(cudaMemcpyAsync(triples, b->out[list].p, (size_t) b->outCount[list] * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, b->ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+    }
+    return CPB_OK;
+}
+
+extern "C" int cpb_batch_fetch_expectations(cpb_batch *b, double *perPair, double *total) {
+    if (b == nullptr || b->lastMode != CPB_MODE_EXPECTATIONS) {
+        cpb_set_error("cpb_batch_fetch_expectations: last run was not in expectation mode");
+        return CPB_ERR_ARGUMENT;
+    }
+    CUDA_TRY(cudaSetDevice(b->ctx->device));
+    const int len = CPB_HMM_LEN(b->lastS);
+    if (perPair && b->n > 0) CUDA_TRY(cudaMemcpyAsync(perPair, b->perPair.p, (size_t) b->n * len * sizeof(double), cudaMemcpyDeviceToHost, b->ctx->stream));
+    if (total) CUDA_TRY(cudaMemcpyAsync(total, b->hmmTotal.p, len * sizeof(double), cudaMemcpyDeviceToHost, b->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+    return CPB_OK;
+}
+
+extern "C" const double *cpb_batch_device_expectation_total(const cpb_batch *b) {
+    return (b && b->lastMode == CPB_MODE_EXPECTATIONS) ? b->hmmTotal.as<double>() : nullptr;
+}
+
+extern "C" int cpb_batch_fetch_forward(cpb_batch *b, double *logProb) {
+    if (b == nullptr || b->lastMode != CPB_MODE_FORWARD || logProb == nullptr) {
+        cpb_set_error("cpb_batch_fetch_forward: last run was not in forward mode");
+        return CPB_ERR_ARGUMENT;
+    }
+    CUDA_TRY(cudaSetDevice(b->ctx->device));
+    if (b->n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(logProb, b->forwardOut.p, (size_t) b->n * sizeof(double), cudaMemcpyDeviceToHost, b->ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+    }
+    return CPB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * cpb_band: run the device band builder on one problem and copy the band back (unit-test / inspection entry)
+ * ---------------------------------------------------------------------------------------------- */
+extern "C" int cpb_band(cpb_context *ctx, const int64_t *anchors, int64_t nAnchors, int64_t lX, int64_t lY, int64_t expansion, int dynamic,
+                        int64_t *out3) {
+    if (ctx == nullptr || lX < 0 || lY < 0 || out3 == nullptr) return CPB_ERR_ARGUMENT;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int64_t N = lX + lY;
+    DevBuf dRegion, dDiags, dBlocks, dAnch;
+    int rc;
+    if ((rc = dRegion.reserve(sizeof(RegionDev))) != CPB_OK || (rc = dDiags.reserve((N + 2) * sizeof(DiagRec))) != CPB_OK ||
+        (rc = dBlocks.reserve(sizeof(BlockRec))) != CPB_OK || (rc = dAnch.reserve(std::max<int64_t>(nAnchors, 1) * 3 * sizeof(int32_t))) != CPB_OK)
+        return rc;
+    std::vector<int32_t> a32(3 * std::max<int64_t>(nAnchors, 1), 0);
+    for (int64_t i = 0; i < 3 * nAnchors; i++) a32[i] = (int32_t) anchors[i];
+    RegionDev R;
+    memset(&R, 0, sizeof(R));
+    R.lX = (int32_t) lX;
+    R.lY = (int32_t) lY;
+    R.nAnchors = (int32_t) nAnchors;
+    R.blockCap = 0;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(dAnch.p, a32.data(), a32.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dRegion.p, &R, sizeof(R), cudaMemcpyHostToDevice, st));
+    BandArgs ba;
+    memset(&ba, 0, sizeof(ba));
+    ba.regions = dRegion.as<RegionDev>();
+    ba.anchors = dAnch.as<int32_t>();
+    ba.diags = dDiags.as<DiagRec>();
+    ba.blocks = dBlocks.as<BlockRec>();
+    ba.nRegions = 1;
+    ba.expansion = (int32_t) expansion;
+    ba.dynamic = dynamic;
+    ba.minDiags = 2;
+    ba.traceBack = 1;
+    ba.scheduleOn = 0;
+    k_band<<<1, 32, 0, st>>>(ba);
+    std::vector<DiagRec> recs(N + 2);
+    CUDA_TRY(cudaMemcpyAsync(recs.data(), dDiags.p, (N + 2) * sizeof(DiagRec), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&R, dRegion.p, sizeof(R), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    dRegion.release();
+    dDiags.release();
+    dBlocks.release();
+    dAnch.release();
+    for (int64_t d = 0; d <= N; d++) {
+        out3[3 * d] = d;
+        out3[3 * d + 1] = recs[d].xmyL;
+        out3[3 * d + 2] = recs[d].xmyL + 2 * ((int64_t) recs[d].width - 1);
+    }
+    if (R.err != 0) {
+        cpb_set_error("cpb_band: anchors produce an invalid band diagonal");
+        return CPB_ERR_BAND;
+    }
+    return CPB_OK;
+}

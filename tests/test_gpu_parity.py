@@ -1,0 +1,326 @@
+"""GPU parity tests: the CUDA path through the C-ABI against the oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): aligned-pair (x, y) sets identical; pInt identical up to the last-bit
+difference between CUDA's and glibc's exp() (|delta| <= 1 in 1e7, and essentially never); forward
+log-probabilities bit-identical (pure logAdd arithmetic); expectations within 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+import cpecan_b200 as cp
+from cpecan_b200 import synth
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+EXPECT_RTOL = 1e-9
+
+
+def compare_triples(got, want, what=""):
+    g = helpers.sort_triples(got)
+    w = helpers.sort_triples(want)
+    assert g.shape == w.shape, "%s: %d pairs from the GPU, %d from the oracle" % (what, g.shape[0], w.shape[0])
+    if g.shape[0] == 0:
+        return 0
+    assert np.array_equal(g[:, 1:], w[:, 1:]), "%s: aligned-pair coordinate sets differ" % what
+    diff = np.abs(g[:, 0] - w[:, 0])
+    assert diff.max() <= 1, "%s: pInt differs by %d" % (what, diff.max())
+    return int((diff != 0).sum())
+
+
+def run_batch(ctx, spec, p, cases, mode):
+    """cases: list of (sX, sY, anchors[k,3], rl, rr)"""
+    b = cp.Batch(ctx, [c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases], [c[3] for c in cases], [c[4] for c in cases])
+    b.run(spec.cpb(), p, mode)
+    return b
+
+
+def check_aligned_pairs(ctx, oracle, spec, p, cases, what):
+    b = run_batch(ctx, spec, p, cases, cp.MODE_ALIGNED_PAIRS)
+    off, tri = b.fetch_pairs(0)
+    op = helpers.orc_params_from(p)
+    om = spec.orc()
+    nd = 0
+    total = 0
+    for i, c in enumerate(cases):
+        want = oracle.aligned_pairs(om, op, c[0], c[1], c[2], c[3], c[4])
+        got = tri[off[i]:off[i + 1]]
+        nd += compare_triples(got, want, "%s case %d (lX %d lY %d)" % (what, i, len(c[0]), len(c[1])))
+        total += want.shape[0]
+    b.close()
+    # last-bit exp() differences must be vanishingly rare
+    assert nd <= max(1, total // 100000), "%s: %d of %d pInt values differ by one" % (what, nd, total)
+    return total
+
+
+def small_cases(rng, n, max_len=100, ragged=False):
+    cases = []
+    for _ in range(n):
+        sX = synth.random_sequence(rng, int(rng.integers(0, max_len)))
+        sY = synth.evolve_like_reference(rng, sX)
+        a = synth.random_anchor_pairs(rng, len(sX), len(sY))
+        rl = bool(rng.random() > 0.5) if ragged else False
+        rr = bool(rng.random() > 0.5) if ragged else False
+        cases.append((sX, sY, a, rl, rr))
+    return cases
+
+
+def test_kat_agcg(ctx):
+    """tests/pairwiseAlignerTest.c:242-324 (values from the reference build)"""
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    p.threshold = 0.2
+    sM = cp.stateMachine5_construct(cp.fiveState)
+    pairs = cp.getAlignedPairsUsingAnchors(sM, "AGCG", "AGTTCG", [], p, False, False, ctx=ctx)
+    assert sorted(pairs, key=lambda t: t[1]) == [(9944673, 0, 0), (9259684, 1, 1), (8665179, 2, 4), (9893294, 3, 5)]
+    assert cp.computeForwardProbability("AGCG", "AGTTCG", [], p, sM, False, False, ctx=ctx) == -17.51932116123855
+
+
+def test_band_golden_and_random(ctx, oracle):
+    """tests/pairwiseAlignerTest.c:69-93 on the device band builder, then random anchors against the oracle"""
+    band = ctx.band([(1, 0, 2), (2, 1, 2), (3, 3, 2)], 6, 5, 2)
+    want = [(0, 0, 0), (1, -1, 1), (2, -2, 2), (3, -1, 3), (4, -2, 4), (5, -1, 3), (6, -2, 4), (7, -3, 3), (8, -2, 2), (9, -1, 3), (10, 0, 2),
+            (11, 1, 1)]
+    assert [tuple(r) for r in band.tolist()] == want
+    rng = np.random.default_rng(7)
+    for it in range(40):
+        lX, lY = int(rng.integers(0, 200)), int(rng.integers(0, 200))
+        a = synth.random_anchor_pairs(rng, lX, lY)
+        dyn = bool(it % 2)
+        e = 2 * int(rng.integers(0, 12))
+        assert np.array_equal(ctx.band(a, lX, lY, e, dyn), oracle.band(a, lX, lY, e, dyn))
+
+
+@pytest.mark.parametrize("type_", [cp.fiveState, cp.fiveStateAsymmetric, cp.threeState, cp.threeStateAsymmetric])
+def test_random_small_pairs(ctx, oracle, type_):
+    """the shape of test_getAlignedPairsWithBanding (tests/pairwiseAlignerTest.c:403-438), but checked for values"""
+    rng = np.random.default_rng(100 + type_)
+    for rep in range(6):
+        p = cp.pairwiseAlignmentBandingParameters_construct()
+        p.traceBackDiagonals = int(rng.integers(1, 10))
+        p.minDiagsBetweenTraceBack = p.traceBackDiagonals + int(rng.integers(2, 10))
+        p.diagonalExpansion = int(rng.integers(0, 10)) * 2
+        p.dynamicAnchorExpansion = int(rng.random() > 0.5)
+        p.threshold = [0.01, 0.2, 0.0, 0.5, 0.01, 0.05][rep]
+        if rep >= 4:
+            p.splitMatrixBiggerThanThis = int(rng.integers(5, 400))
+        spec = helpers.ModelSpec(type_) if rep % 2 == 0 else helpers.ModelSpec.random(rng, type_)
+        cases = small_cases(rng, 25, 120, ragged=rep >= 2)
+        check_aligned_pairs(ctx, oracle, spec, p, cases, "type %d rep %d" % (type_, rep))
+
+
+def test_evolved_1kb_lib_defaults(ctx, oracle):
+    """BASELINE config 1/2 shape: 1 kb evolved pairs, StateMachine5, library-default band and threshold"""
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    packed = synth.evolved_pairs(12, 1000, seed=11, trim=int(p.constraintDiagonalTrim), expansion=int(p.diagonalExpansion))
+    cases = [synth.unpack(packed, i) + (False, False) for i in range(12)]
+    n = check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.fiveState), p, cases, "1kb lib")
+    assert n > 12 * 900
+
+
+def test_evolved_1kb_cli_defaults(ctx, oracle):
+    """cPecanRealign's own defaults (cPecanRealign.c:355-357): trim 0, expansion 4, split 10 -> many tiny regions"""
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    p.constraintDiagonalTrim = 0
+    p.diagonalExpansion = 4
+    p.splitMatrixBiggerThanThis = 10
+    packed = synth.evolved_pairs(12, 1000, seed=12, trim=0, expansion=4)
+    cases = [synth.unpack(packed, i) + (False, False) for i in range(12)]
+    check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.fiveState), p, cases, "1kb cli")
+
+
+def test_long_pair_many_blocks(ctx, oracle):
+    """20 kb pair: ~36 traceback blocks, forward values around -3e4 (the FP64 contract matters here)"""
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    packed = synth.evolved_pairs(2, 20000, seed=13, trim=int(p.constraintDiagonalTrim), expansion=int(p.diagonalExpansion))
+    cases = [synth.unpack(packed, i) + (bool(i), bool(i)) for i in range(2)]
+    check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.fiveState), p, cases, "20kb")
+    p.diagonalExpansion = 10
+    p.constraintDiagonalTrim = 0
+    packed = synth.evolved_pairs(2, 20000, seed=14, trim=0, expansion=10)
+    cases = [synth.unpack(packed, i) + (False, False) for i in range(2)]
+    check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.threeState), p, cases, "20kb sm3 e10")
+
+
+def test_wide_bands_every_width_class(ctx, oracle):
+    """no anchors => the band is the whole matrix: widths 40..1100 exercise the multi-warp CTA classes"""
+    rng = np.random.default_rng(5)
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    cases = []
+    for L in (40, 70, 130, 300, 600, 1100):
+        sX = synth.random_sequence(rng, L, acgt_only=True)
+        sY = synth.evolve_like_reference(rng, sX)[: L + 20]
+        cases.append((sX, sY, np.zeros((0, 3), dtype=np.int64), False, False))
+    check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.fiveState), p, cases, "wide")
+    check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.threeStateAsymmetric), p, cases[:4], "wide sm3")
+
+
+def test_band_too_wide_fails_loudly(ctx):
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    p.splitMatrixBiggerThanThis = 1 << 40
+    s = "ACGT" * 700
+    with pytest.raises(cp.CpbError, match="wide"):
+        cp.getAlignedPairsUsingAnchors(cp.stateMachine5_construct(), s, s, [], p, ctx=ctx)
+
+
+def test_edge_cases(ctx, oracle):
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    e = np.zeros((0, 3), dtype=np.int64)
+    cases = [("", "", e, False, False), ("", "ACGT", e, False, False), ("ACGT", "", e, True, True), ("A", "A", e, False, False),
+             ("NNNN", "acgt", e, False, True), ("ACGTACGT", "ACGTACGT", np.array([[3, 3, 0]], dtype=np.int64), True, False)]
+    check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.fiveState), p, cases, "edge")
+    check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.threeState), p, cases, "edge sm3")
+    # an empty batch is fine too
+    b = cp.Batch(ctx, [], [], [])
+    b.run(cp.stateMachine5_construct(), p, cp.MODE_ALIGNED_PAIRS)
+    assert b.result_count(0) == 0
+
+
+def test_chunking_is_invisible(oracle):
+    """a tiny scratch budget forces one chunk per few pairs; results must not change"""
+    c2 = cp.Context(0)
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    packed = synth.evolved_pairs(40, 300, seed=21, trim=4, expansion=8)
+    p.diagonalExpansion = 8
+    p.minDiagsBetweenTraceBack = 100
+    m = cp.stateMachine5_construct()
+    b = cp.Batch(c2, None, None, packed=packed)
+    b.run(m, p, cp.MODE_ALIGNED_PAIRS)
+    off1, tri1 = b.fetch_pairs(0)
+    assert b.stats().nChunks == 1
+    c2.set_scratch_budget(600 * 1024)
+    b.run(m, p, cp.MODE_ALIGNED_PAIRS)
+    off2, tri2 = b.fetch_pairs(0)
+    assert b.stats().nChunks > 3
+    assert np.array_equal(off1, off2) and np.array_equal(tri1, tri2)
+    b.run(m, p, cp.MODE_EXPECTATIONS)
+    pp2, tot2 = b.fetch_expectations()
+    c2.set_scratch_budget(0)
+    b.run(m, p, cp.MODE_EXPECTATIONS)
+    pp1, tot1 = b.fetch_expectations()
+    assert np.array_equal(pp1, pp2)
+    np.testing.assert_allclose(tot1, tot2, rtol=1e-13)
+    b.close()
+    c2.close()
+
+
+@pytest.mark.parametrize("type_", [cp.threeState, cp.fiveState])
+def test_indel_posteriors(ctx, oracle, type_):
+    """getAlignedPairsWithIndelsUsingAnchors (tests/pairwiseAlignerTest.c:867-942 uses the three-state machine)"""
+    rng = np.random.default_rng(300 + type_)
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    p.minDiagsBetweenTraceBack = 60
+    spec = helpers.ModelSpec(type_)
+    cases = small_cases(rng, 30, 150, ragged=True)
+    b = run_batch(ctx, spec, p, cases, cp.MODE_ALIGNED_PAIRS_INDELS)
+    res = [b.fetch_pairs(k) for k in range(3)]
+    for i, c in enumerate(cases):
+        want = oracle.aligned_pairs_with_indels(spec.orc(), helpers.orc_params_from(p), c[0], c[1], c[2], c[3], c[4])
+        for k in range(3):
+            off, tri = res[k]
+            compare_triples(tri[off[i]:off[i + 1]], want[k], "indel list %d case %d" % (k, i))
+    b.close()
+
+
+@pytest.mark.parametrize("type_", [cp.fiveState, cp.fiveStateAsymmetric, cp.threeState, cp.threeStateAsymmetric])
+def test_expectations(ctx, oracle, type_):
+    """getExpectationsUsingAnchors incl. the block-boundary quirk: several blocks per pair"""
+    rng = np.random.default_rng(400 + type_)
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    p.diagonalExpansion = 10
+    p.minDiagsBetweenTraceBack = 50
+    p.traceBackDiagonals = 7
+    spec = helpers.ModelSpec.random(rng, type_) if type_ % 2 else helpers.ModelSpec(type_)
+    cases = small_cases(rng, 16, 200, ragged=True)
+    b = run_batch(ctx, spec, p, cases, cp.MODE_EXPECTATIONS)
+    pp, tot = b.fetch_expectations()
+    want_tot = np.zeros_like(tot)
+    for i, c in enumerate(cases):
+        want = oracle.expectations(spec.orc(), helpers.orc_params_from(p), c[0], c[1], c[2], c[3], c[4])
+        np.testing.assert_allclose(pp[i], want, rtol=EXPECT_RTOL, atol=1e-12, err_msg="expectations of case %d" % i)
+        want_tot += want
+    np.testing.assert_allclose(tot, want_tot, rtol=EXPECT_RTOL, atol=1e-12)
+    b.close()
+
+
+def test_expectations_2kb_em_defaults(ctx, oracle):
+    """BASELINE config 4 shape: 2 kb pairs, cPecanEm's realign options (--diagonalExpansion=10 --splitMatrixBiggerThanThis=3000, cPecanEm.py:371)"""
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    p.diagonalExpansion = 10
+    p.constraintDiagonalTrim = 0
+    p.splitMatrixBiggerThanThis = 3000 * 3000
+    packed = synth.evolved_pairs(6, 2000, seed=31, trim=0, expansion=10)
+    for type_ in (cp.fiveState, cp.threeState):
+        spec = helpers.ModelSpec(type_)
+        b = cp.Batch(ctx, None, None, packed=packed)
+        b.run(spec.cpb(), p, cp.MODE_EXPECTATIONS)
+        pp, tot = b.fetch_expectations()
+        for i in range(6):
+            sx, sy, a = synth.unpack(packed, i)
+            want = oracle.expectations(spec.orc(), helpers.orc_params_from(p), sx, sy, a)
+            np.testing.assert_allclose(pp[i], want, rtol=EXPECT_RTOL, atol=1e-12)
+        b.close()
+
+
+def test_forward_probability_bit_exact(ctx, oracle):
+    """computeForwardProbability is pure logAdd arithmetic: the GPU must reproduce every bit (test_computeForwardProbability, :1157-1188)"""
+    rng = np.random.default_rng(55)
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    for type_ in (cp.threeState, cp.fiveState):
+        spec = helpers.ModelSpec(type_)
+        cases = small_cases(rng, 40, 150, ragged=True)
+        cases = [(c[0], c[1], np.zeros((0, 3), dtype=np.int64), c[3], c[4]) for c in cases]
+        b = run_batch(ctx, spec, p, cases, cp.MODE_FORWARD)
+        got = b.fetch_forward()
+        for i, c in enumerate(cases):
+            want = oracle.forward_prob(spec.orc(), helpers.orc_params_from(p), c[0], c[1], c[2], c[3], c[4])
+            assert got[i] == want, "case %d: %r vs %r" % (i, got[i], want)
+            if len(c[0]) >= 10:
+                same = cp.computeForwardProbability(c[0], c[0], [], p, spec.cpb(), c[3], c[4], ctx=ctx)
+                assert -np.inf < got[i] <= same <= 0.0
+        b.close()
+
+
+def test_ragged_ends_recover_the_shifted_diagonal(ctx):
+    """test_getAlignedPairsWithRaggedEnds (tests/pairwiseAlignerTest.c:676-715) without the poset filter:
+    the best pair of every core base must lie on x + 100 == y"""
+    rng = np.random.default_rng(9)
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    sM = cp.stateMachine5_construct()
+    for _ in range(5):
+        core = synth.random_sequence(rng, 100, acgt_only=True)
+        sY = synth.random_sequence(rng, 100, acgt_only=True) + core + synth.random_sequence(rng, 100, acgt_only=True)
+        pairs = np.array(cp.getAlignedPairsUsingAnchors(sM, core, sY, [], p, True, True, ctx=ctx))
+        best = {}
+        for pi, x, y in pairs:
+            if x not in best or pi > best[x][0]:
+                best[x] = (pi, y)
+        on_diag = sum(1 for x, (pi, y) in best.items() if y == x + 100)
+        assert on_diag >= 95
+
+
+def test_roundtrip_properties_at_bench_scale(ctx):
+    """size-independent properties on a bench-shaped batch: unique (x,y) per pair, pInt range, every x row sums to <= 1
+    (within the logAdd approximation), identical results on a re-run (determinism)"""
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    packed = synth.evolved_pairs(512, 1000, seed=77, trim=int(p.constraintDiagonalTrim), expansion=int(p.diagonalExpansion))
+    b = cp.Batch(ctx, None, None, packed=packed)
+    m = cp.stateMachine5_construct()
+    b.run(m, p, cp.MODE_ALIGNED_PAIRS)
+    off, tri = b.fetch_pairs(0)
+    tri = tri.copy()
+    st = b.stats()
+    assert st.nPairs == 512 and st.cells > 512 * 50000
+    assert tri[:, 0].min() >= int(0.01 * 1e7) and tri[:, 0].max() <= 10000000
+    for i in range(0, 512, 37):
+        t = tri[off[i]:off[i + 1]]
+        lX = packed["xOff"][i + 1] - packed["xOff"][i]
+        lY = packed["yOff"][i + 1] - packed["yOff"][i]
+        assert t[:, 1].min() >= 0 and t[:, 1].max() < lX and t[:, 2].min() >= 0 and t[:, 2].max() < lY
+        key = t[:, 1].astype(np.int64) * (lY + 1) + t[:, 2]
+        assert np.unique(key).size == key.size
+        rows = np.bincount(t[:, 1], weights=t[:, 0] / 1e7, minlength=lX)
+        assert rows.max() < 1.02 and (rows > 0.5).sum() > 0.8 * lX
+    b.run(m, p, cp.MODE_ALIGNED_PAIRS)
+    off2, tri2 = b.fetch_pairs(0)
+    assert np.array_equal(off, off2) and np.array_equal(tri, tri2)
+    b.close()
