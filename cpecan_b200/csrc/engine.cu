@@ -336,7 +336,8 @@ static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
             const int64_t N = (int64_t) R.lX + R.lY;
             R.diagBase = diagBase;
             R.blockBase = blockBase;
-            R.blockCap = (int32_t) (N / p->minDiagsBetweenTraceBack + 2);
+            /* consecutive traceback points are at least minDiags - (traceBack+1) diagonals apart (T moves to d - traceBack - 1) */
+            R.blockCap = (int32_t) (N / (p->minDiagsBetweenTraceBack - p->traceBackDiagonals - 1) + 2);
             diagBase += N + 2;
             blockBase += R.blockCap;
             b->hRegions.push_back(R);
