@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the cPecan pair-HMM hot path on B200.
+
+Metric (BASELINE.json): GCUPS (band cells per second / 1e9, each cell counted once) and
+pairs/s of banded forward-backward + posterior on `configs[1]`: 100 000 synthetic 1 kb evolved pairs,
+StateMachine5, library-default band and posterior threshold 0.01.  One "step" = one pass of the whole hot path
+(band builder -> forward -> backward -> totals -> posterior scan/compaction) over the batch.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl reference]
+
+value : inputs resident in HBM, CUDA-event time on the launching stream, max over ranks.
+e2e   : the same pass through the C-ABI with HOST buffers (pinned): cpb_batch_create (H2D) + cpb_batch_run +
+        cpb_batch_fetch_pairs (D2H) inside the timed region.
+--impl reference : the reference's own CPU implementation (oracle/_ref when it was built, else the plain-C port)
+        on all host cores over a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "GCUPS (banded fwd-bwd+posterior)"
+UNIT = "GCUPS"
+WORKLOAD = "100k x 1 kb evolved pairs (randomSequences-style, ~10% divergence), StateMachine5, lib-default band (expansion 20, trim 14), threshold 0.01"
+FLOP_PER_CELL = 280.0      # SURVEY.md section 8d, five-state, reference arithmetic
+ALG_BYTES_PER_CELL = 80.0  # 5 states x 8 B written by forward + read by backward
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            pk = json.load(f)
+        return float(pk.get("hbm_gbs", 6650.0)), float(pk.get("sm_max_mhz", 1965.0)), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.index = index
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(n_pairs, rank, params):
+    from cpecan_b200 import synth
+
+    return synth.evolved_pairs(n_pairs, 1000, seed=0xC0FFEE + 7919 * rank, trim=int(params.constraintDiagonalTrim),
+                               expansion=int(params.diagonalExpansion))
+
+
+def cpu_arm(packed, n_sample, threads):
+    """Times the CPU implementation (reference build if present) on the first n_sample pairs of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from cpecan_b200 import synth
+    import cpecan_b200 as cp
+
+    orc = helpers.best_oracle()
+    sub = synth.subset(packed, range(n_sample))
+    p = helpers.orc_params_from(cp.pairwiseAlignmentBandingParameters_construct())
+    m = helpers.ModelSpec(cp.fiveState).orc()
+    t0 = time.perf_counter()
+    counts, _, _ = orc.batch(m, p, sub, mode=0, threads=threads)
+    dt = time.perf_counter() - t0
+    return orc.identity, dt, int(counts.sum())
+
+
+def count_cells(packed, n_sample):
+    """band cells of the first n_sample pairs, from the product's own band builder statistics"""
+    import cpecan_b200 as cp
+    from cpecan_b200 import synth
+
+    ctx = cp.Context(int(os.environ.get("LOCAL_RANK", "0")))
+    b = cp.Batch(ctx, None, None, packed=synth.subset(packed, range(n_sample)))
+    b.run(cp.stateMachine5_construct(), cp.pairwiseAlignmentBandingParameters_construct(), cp.MODE_FORWARD)
+    cells = b.stats().cells
+    b.close()
+    ctx.close()
+    return int(cells)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=100000, help="pairs per GPU (weak scaling)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: no end-to-end arm")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: no CPU baseline")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    threads = os.cpu_count() or 1
+
+    import cpecan_b200 as cp
+
+    params = cp.pairwiseAlignmentBandingParameters_construct()
+
+    if args.impl == "reference":
+        # the reference's CPU path on all host cores; rank 0 only
+        if rank != 0:
+            return
+        n_sample = max(2 * threads, 64)
+        packed = make_inputs(n_sample, 0, params)
+        ident, dt_probe, _ = cpu_arm(packed, min(8, n_sample), 1)
+        per_pair = dt_probe / min(8, n_sample)
+        # size each step to ~ cpu-seconds/ (steps+warmup) of wall time on all threads
+        steps_total = max(args.steps + args.warmup, 1)
+        budget = max(args.cpu_seconds * 4 / steps_total, 2.0)
+        n_step = int(min(n_sample, max(threads, budget * threads / max(per_pair, 1e-6))))
+        cells = count_cells(packed, n_step) if _has_gpu() else None
+        times = []
+        for i in range(args.warmup + args.steps):
+            _, dt, _ = cpu_arm(packed, n_step, threads)
+            if i >= args.warmup:
+                times.append(dt)
+        tsum = sum(times)
+        if cells is None:
+            cells = _cells_by_oracle(packed, n_step)
+        gcups = cells * len(times) / tsum / 1e9
+        line = {
+            "impl": "reference", "metric": METRIC, "value": gcups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tsum / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample_pairs_per_step": n_step, "host_threads": threads},
+            "pairs_per_s": n_step * len(times) / tsum,
+            "cpu_baseline": {"value": gcups, "unit": UNIT, "cores": threads, "kind": ident,
+                             "sample": "%d pairs of the workload per step, all %d host threads" % (n_step, threads)},
+            "e2e": {"value": gcups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return
+
+    import torch
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx = cp.Context(local_rank, stream=stream.cuda_stream)
+    model = cp.stateMachine5_construct(cp.fiveState)
+
+    t_gen = time.perf_counter()
+    packed = make_inputs(args.pairs, rank, params)
+    t_gen = time.perf_counter() - t_gen
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ----
+    batch = cp.Batch(ctx, None, None, packed=packed)
+    for _ in range(args.warmup):
+        batch.run(model, params, cp.MODE_ALIGNED_PAIRS)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    phase = {"band": 0.0, "forward": 0.0, "backward": 0.0, "totals": 0.0, "posterior": 0.0}
+    launches = 0
+    for _ in range(args.steps):
+        batch.run(model, params, cp.MODE_ALIGNED_PAIRS)
+        st = batch.stats()
+        phase["band"] += st.msBand
+        phase["forward"] += st.msForward
+        phase["backward"] += st.msBackward
+        phase["totals"] += st.msTotals
+        phase["posterior"] += st.msPosterior
+        launches += st.kernelLaunches
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    st = batch.stats()
+    cells, n_triples = int(st.cells), int(st.outputTriples)
+    t = torch.tensor([ms, float(cells), float(args.pairs)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_all, cells_all, pairs_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
+    else:
+        ms_all, cells_all, pairs_all = ms, float(cells), float(args.pairs)
+    value = cells_all * args.steps / (ms_all * 1e-3) / 1e9
+    pairs_per_s = pairs_all * args.steps / (ms_all * 1e-3)
+
+    # ---- end-to-end arm through the C-ABI with pinned host buffers ----
+    pinned = {}
+    for k in ("seqX", "xOff", "seqY", "yOff", "anchors", "aOff"):
+        tt = torch.from_numpy(packed[k]).pin_memory()
+        pinned[k] = tt.numpy()
+        pinned["_t_" + k] = tt
+    out_pinned = torch.empty((max(n_triples, 1) + 1024, 3), dtype=torch.int32).pin_memory()
+    h2d = int(packed["xOff"][-1] + packed["yOff"][-1] + 12 * packed["aOff"][-1])
+    d2h = int(n_triples * 12)
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def one_e2e():
+        b = cp.Batch(ctx, None, None, packed=pinned)
+        b.run(model, params, cp.MODE_ALIGNED_PAIRS)
+        off, tri = b.fetch_pairs(0, out=out_pinned.numpy())
+        b.close()
+        return int(off[-1])
+
+    batch.close()
+    wall = float("nan")
+    if not args.skip_e2e:
+        one_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            got = one_e2e()
+        barrier()
+        wall = time.perf_counter() - t0
+        assert got == n_triples, "e2e arm produced %d triples, resident arm %d" % (got, n_triples)
+    tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    e2e_value = cells_all * e2e_steps / float(tw[0]) / 1e9
+
+    if rank == 0:
+        hbm_peak, sm_max, peak_src = read_peaks()
+        # dominant kernels: the forward and backward wavefronts (one launch per width class and chunk)
+        k_ms = (phase["forward"] + phase["backward"]) / args.steps
+        dom = "k_forward+k_backward"
+        achieved_gbs = cells * ALG_BYTES_PER_CELL / (k_ms * 1e-3) / 1e9
+        fp64_peak = 148 * 64 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s non-tensor FP64 at max clock (half the FP32 rate)
+        achieved_tf = cells * FLOP_PER_CELL / (k_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": args.pairs, "cells_per_gpu": cells, "l2": "working set >> L2 (GBs of DP state per step)",
+                       "chunks": int(st.nChunks), "blocks": int(st.nBlocks), "max_band_width": int(st.maxWidth), "datagen_s": round(t_gen, 1)},
+            "pairs_per_s": pairs_per_s,
+            "gpu_launches": int(launches),
+            "phase_ms_per_step": {k: v / args.steps for k, v in phase.items()},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "pairs_per_s": pairs_all * e2e_steps / float(tw[0])},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_cell": ALG_BYTES_PER_CELL,
+                         "compute": {"bound": "fp64 CUDA-core issue", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                                     "frac": achieved_tf / fp64_peak, "flop_per_cell": FLOP_PER_CELL}},
+        }
+        # CPU baseline on a bounded sample of the same workload
+        try:
+            if args.skip_cpu:
+                raise RuntimeError("skipped (--skip-cpu)")
+            n_probe = 8
+            ident, dt_probe, _ = cpu_arm(packed, n_probe, 1)
+            per_pair = dt_probe / n_probe
+            n_sample = int(min(args.pairs, max(threads, args.cpu_seconds * threads / max(per_pair, 1e-6))))
+            ident, dt, _ = cpu_arm(packed, n_sample, threads)
+            sample_cells = count_cells(packed, n_sample)
+            line["cpu_baseline"] = {"value": sample_cells / dt / 1e9, "unit": UNIT, "cores": threads, "kind": ident,
+                                    "sample": "first %d pairs of the workload, %d host threads, %.1f s" % (n_sample, threads, dt),
+                                    "single_core_gcups": count_cells(packed, n_probe) / dt_probe / 1e9}
+        except Exception as ex:  # the baseline is reported, never required for the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "unavailable", "sample": str(ex)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _has_gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def _cells_by_oracle(packed, n):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from cpecan_b200 import synth
+    import cpecan_b200 as cp
+
+    orc = helpers.best_oracle()
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    total = 0
+    for i in range(n):
+        sx, sy, a = synth.unpack(packed, i)
+        b = orc.band(a, len(sx), len(sy), int(p.diagonalExpansion))
+        total += int(((b[:, 2] - b[:, 1]) // 2 + 1).sum())
+    return total
+
+
+if __name__ == "__main__":
+    main()
