@@ -75,7 +75,7 @@ struct DevBuf {
  * width classes: window capacity (cells per diagonal) -> warps per CTA
  * ---------------------------------------------------------------------------------------------- */
 static const int kNumClasses = 7; /* 32, 64, 128, 256, 512, 1024, 2048 */
-static int g_classWarps[kNumClasses] = { 1, 1, 1, 2, 4, 8, 8 };
+static int g_classWarps[kNumClasses] = { 1, 1, 2, 4, 8, 8, 8 };
 
 static int class_of_width(int w) {
     int c = 0, cap = 32;
@@ -93,21 +93,38 @@ template <int S> static size_t dp_smem_bytes(int wcap) {
 
 typedef void (*DpKernel)(const DpArgs, const CpbModel);
 
-template <int S> static DpKernel forward_kernel(int warps) {
-    switch (warps) {
-    case 1: return k_forward<S, 1>;
-    case 2: return k_forward<S, 2>;
-    case 4: return k_forward<S, 4>;
-    default: return k_forward<S, 8>;
+static const int kWarpChoices[5] = { 1, 2, 4, 8, 16 };
+static int warp_index(int warps) {
+    for (int i = 0; i < 5; i++) {
+        if (kWarpChoices[i] == warps) return i;
     }
+    return -1;
 }
-template <int S> static DpKernel backward_kernel(int warps) {
-    switch (warps) {
-    case 1: return k_backward<S, 1>;
-    case 2: return k_backward<S, 2>;
-    case 4: return k_backward<S, 4>;
-    default: return k_backward<S, 8>;
+
+/* [class][warp choice] tables of the template instantiations */
+template <int S> struct KernelTable {
+    DpKernel fwd[kNumClasses][5];
+    DpKernel bwd[kNumClasses][5];
+    KernelTable() {
+#define CPB_ROW(C, WCAP)                                                                         \
+        fwd[C][0] = k_forward<S, WCAP, 1>;  bwd[C][0] = k_backward<S, WCAP, 1>;                     \
+        fwd[C][1] = k_forward<S, WCAP, 2>;  bwd[C][1] = k_backward<S, WCAP, 2>;                     \
+        fwd[C][2] = k_forward<S, WCAP, 4>;  bwd[C][2] = k_backward<S, WCAP, 4>;                     \
+        fwd[C][3] = k_forward<S, WCAP, 8>;  bwd[C][3] = k_backward<S, WCAP, 8>;                     \
+        fwd[C][4] = k_forward<S, WCAP, 16>; bwd[C][4] = k_backward<S, WCAP, 16>;
+        CPB_ROW(0, 32)
+        CPB_ROW(1, 64)
+        CPB_ROW(2, 128)
+        CPB_ROW(3, 256)
+        CPB_ROW(4, 512)
+        CPB_ROW(5, 1024)
+        CPB_ROW(6, 2048)
+#undef CPB_ROW
     }
+};
+template <int S> static const KernelTable<S> &kernel_table() {
+    static const KernelTable<S> t;
+    return t;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -121,13 +138,13 @@ struct cpb_context {
 
 static int configure_kernels() {
     const int maxSmem = 227 * 1024;
-    const int warpsList[4] = { 1, 2, 4, 8 };
-    for (int wi = 0; wi < 4; wi++) {
-        const int w = warpsList[wi];
-        CUDA_TRY(cudaFuncSetAttribute((const void *) forward_kernel<5>(w), cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        CUDA_TRY(cudaFuncSetAttribute((const void *) forward_kernel<3>(w), cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        CUDA_TRY(cudaFuncSetAttribute((const void *) backward_kernel<5>(w), cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        CUDA_TRY(cudaFuncSetAttribute((const void *) backward_kernel<3>(w), cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    for (int c = 0; c < kNumClasses; c++) {
+        for (int w = 0; w < 5; w++) {
+            CUDA_TRY(cudaFuncSetAttribute((const void *) kernel_table<5>().fwd[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+            CUDA_TRY(cudaFuncSetAttribute((const void *) kernel_table<5>().bwd[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+            CUDA_TRY(cudaFuncSetAttribute((const void *) kernel_table<3>().fwd[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+            CUDA_TRY(cudaFuncSetAttribute((const void *) kernel_table<3>().bwd[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        }
     }
     CUDA_TRY(cudaFuncSetAttribute((const void *) k_expect<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
     CUDA_TRY(cudaFuncSetAttribute((const void *) k_expect<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
@@ -167,7 +184,7 @@ extern "C" int cpb_context_create(int device, void *stream, cpb_context **out) {
         int v[kNumClasses];
         if (sscanf(w, "%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]) == kNumClasses) {
             for (int i = 0; i < kNumClasses; i++) {
-                if (v[i] == 1 || v[i] == 2 || v[i] == 4 || v[i] == 8) g_classWarps[i] = v[i];
+                if (warp_index(v[i]) >= 0) g_classWarps[i] = v[i];
             }
         }
     }
@@ -197,7 +214,7 @@ extern "C" void cpb_context_set_scratch_budget(cpb_context *ctx, size_t bytes) {
 struct Chunk {
     int64_t region0, region1; /* [region0, region1) */
     int64_t block0, block1;   /* positions in the compact block order */
-    int64_t cells, aux;
+    int64_t cells, aux, maskWords, decades;
     int64_t stride;
     int64_t fwdListOff[kNumClasses + 1]; /* offsets into the forward list array */
     int64_t bwdListOff[kNumClasses + 1];
@@ -212,7 +229,7 @@ struct cpb_batch {
     std::vector<uint8_t> rl, rr;
     DevBuf symX, symY, dAnchors;
     /* run state */
-    DevBuf regions, diags, blocks, totals, lists, counts, offsets, partials, pairBlockOff, perPair, hmmTotal, forwardOut;
+    DevBuf regions, diags, blocks, totals, lists, counts, offsets, masks, tileSums, pairCounts, partials, pairBlockOff, perPair, hmmTotal, forwardOut;
     DevBuf out[3];
     int64_t outCount[3] = { 0, 0, 0 };
     std::vector<int64_t> pairOff[3]; /* n+1 */
@@ -278,7 +295,7 @@ extern "C" void cpb_batch_destroy(cpb_batch *b) {
     if (b == nullptr) return;
     cudaSetDevice(b->ctx->device);
     DevBuf *bufs[] = { &b->symX, &b->symY, &b->dAnchors, &b->regions, &b->diags, &b->blocks, &b->totals, &b->lists, &b->counts,
-                       &b->offsets, &b->partials, &b->pairBlockOff, &b->perPair, &b->hmmTotal, &b->forwardOut, &b->out[0], &b->out[1],
+                       &b->offsets, &b->masks, &b->tileSums, &b->pairCounts, &b->partials, &b->pairBlockOff, &b->perPair, &b->hmmTotal, &b->forwardOut, &b->out[0], &b->out[1],
                        &b->out[2] };
     for (DevBuf *d : bufs) d->release();
     delete b;
@@ -471,8 +488,8 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             finish_events();
             return CPB_ERR_BAND;
         }
-        if (class_of_width(regs[r].maxW) >= kNumClasses) {
-            cpb_set_error("pair %d: band is %d cells wide; the widest kernel configuration holds %d", regs[r].pair, regs[r].maxW,
+        if (class_of_width(regs[r].maxSpan) >= kNumClasses) {
+            cpb_set_error("pair %d: band is %d cells wide; the widest kernel configuration holds %d", regs[r].pair, regs[r].maxSpan,
                           class_wcap(kNumClasses - 1));
             finish_events();
             return CPB_ERR_BAND_TOO_WIDE;
@@ -509,28 +526,39 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             Chunk c;
             memset(&c, 0, sizeof(c));
             c.region0 = r;
-            int64_t cells = 0, aux = 0;
+            int64_t cells = 0, aux = 0, words = 0;
             while (r < nReg) {
                 const int64_t nc = cells + regs[r].cells + 32, na = aux + regs[r].auxDoubles + 4;
                 if (r > c.region0 && (size_t) (nc * bytesPerCell + na * 8) > budget) break;
                 regs[r].cellBase = cells;
                 regs[r].auxBase = aux;
+                regs[r].maskBase = words;
                 cells = (nc + 3) & ~int64_t(3);
                 aux = (na + 1) & ~int64_t(1);
+                words += (regs[r].cells >> 5) + regs[r].lX + regs[r].lY + 4;
                 r++;
             }
             c.region1 = r;
             c.cells = cells;
             c.aux = aux;
+            c.maskWords = words;
             c.stride = (cells + 31) & ~int64_t(31);
             c.block0 = regionBlock0[c.region0];
             c.block1 = regionBlock0[c.region1];
             c.pair0 = regs[c.region0].pair;
             c.pair1 = regs[c.region1 - 1].pair;
+            /* decades: ceil(owned diagonals / 10) per block, numbered consecutively inside the chunk */
+            int64_t dec = 0;
+            for (int64_t k = c.block0; k < c.block1; k++) {
+                hBlocks[k].decadeBase = dec;
+                dec += (hBlocks[k].from - hBlocks[k].T + 9) / 10;
+            }
+            c.decades = dec;
             chunks.push_back(c);
         }
     }
     stx.nChunks = (int64_t) chunks.size();
+    if (totalBlocks > 0) CUDA_TRY(cudaMemcpyAsync(b->blocks.p, hBlocks.data(), totalBlocks * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
     size_t scratchNeed = 0;
     for (auto &c : chunks) scratchNeed = std::max(scratchNeed, (size_t) (c.stride * bytesPerCell + c.aux * 8 + 256));
     if ((rc = ctx->scratch.reserve(std::max<size_t>(scratchNeed, 256))) != CPB_OK) return rc;
@@ -539,14 +567,14 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     std::vector<int32_t> lists;
     for (auto &c : chunks) {
         std::vector<std::vector<int32_t>> byClass(kNumClasses);
-        for (int64_t r = c.region0; r < c.region1; r++) byClass[class_of_width(regs[r].maxW)].push_back((int32_t) r);
+        for (int64_t r = c.region0; r < c.region1; r++) byClass[class_of_width(regs[r].maxSpan)].push_back((int32_t) r);
         for (int k = 0; k < kNumClasses; k++) {
             c.fwdListOff[k] = (int64_t) lists.size();
             lists.insert(lists.end(), byClass[k].begin(), byClass[k].end());
         }
         c.fwdListOff[kNumClasses] = (int64_t) lists.size();
         for (auto &v : byClass) v.clear();
-        for (int64_t k = c.block0; k < c.block1; k++) byClass[class_of_width(hBlocks[k].maxW)].push_back((int32_t) k);
+        for (int64_t k = c.block0; k < c.block1; k++) byClass[class_of_width(hBlocks[k].maxSpan)].push_back((int32_t) k);
         for (int k = 0; k < kNumClasses; k++) {
             c.bwdListOff[k] = (int64_t) lists.size();
             lists.insert(lists.end(), byClass[k].begin(), byClass[k].end());
@@ -559,20 +587,30 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     CUDA_TRY(cudaMemcpyAsync(b->lists.p, lists.data(), lists.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->regions.p, regs.data(), nReg * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
 
-    int64_t maxChunkBlocks = 1;
-    for (auto &c : chunks) maxChunkBlocks = std::max(maxChunkBlocks, c.block1 - c.block0);
+    int64_t maxChunkBlocks = 1, maxDecades = 1, maxMaskWords = 1, maxChunkPairs = 1;
+    for (auto &c : chunks) {
+        maxChunkBlocks = std::max(maxChunkBlocks, c.block1 - c.block0);
+        maxDecades = std::max(maxDecades, c.decades);
+        maxMaskWords = std::max(maxMaskWords, c.maskWords);
+        maxChunkPairs = std::max(maxChunkPairs, c.pair1 - c.pair0 + 1);
+    }
+    const int64_t maxTiles = (maxDecades + SCAN_TILE - 1) / SCAN_TILE;
     if (nLists > 0) {
-        if ((rc = b->counts.reserve(maxChunkBlocks * 3 * sizeof(int64_t))) != CPB_OK) return rc;
-        if ((rc = b->offsets.reserve(maxChunkBlocks * 3 * sizeof(int64_t))) != CPB_OK) return rc;
+        if ((rc = b->counts.reserve((size_t) nLists * maxDecades * sizeof(int32_t))) != CPB_OK) return rc;
+        if ((rc = b->offsets.reserve((size_t) nLists * maxDecades * sizeof(int64_t))) != CPB_OK) return rc;
+        if ((rc = b->masks.reserve((size_t) nLists * maxMaskWords * sizeof(uint32_t))) != CPB_OK) return rc;
+        if ((rc = b->tileSums.reserve((size_t) (nLists * maxTiles + 8) * sizeof(int64_t))) != CPB_OK) return rc;
+        if ((rc = b->pairCounts.reserve((size_t) nLists * std::max<int64_t>(b->n, 1) * sizeof(int64_t))) != CPB_OK) return rc;
+        if ((rc = b->pairBlockOff.reserve((size_t) (maxChunkPairs + 2) * sizeof(int64_t))) != CPB_OK) return rc;
+        CUDA_TRY(cudaMemsetAsync(b->pairCounts.p, 0, (size_t) nLists * std::max<int64_t>(b->n, 1) * sizeof(int64_t), st));
     }
     if (mode == CPB_MODE_EXPECTATIONS) {
         if ((rc = b->partials.reserve(maxChunkBlocks * hmmLen * sizeof(double))) != CPB_OK) return rc;
-        if ((rc = b->pairBlockOff.reserve((b->n + 2) * sizeof(int64_t))) != CPB_OK) return rc;
+        if ((rc = b->pairBlockOff.reserve((size_t) (maxChunkPairs + 2) * sizeof(int64_t))) != CPB_OK) return rc;
     }
 
-    std::vector<int64_t> hCounts, hOffsets, hPairBlockOff;
+    std::vector<int64_t> hPairOff;
     int64_t running[3] = { 0, 0, 0 };
-    std::vector<std::vector<int64_t>> pairCount(3, std::vector<int64_t>(nLists > 0 ? b->n : 0, 0));
 
     for (auto &c : chunks) {
         DpArgs a;
@@ -597,10 +635,9 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         for (int k = 0; k < kNumClasses; k++) {
             const int64_t cnt = c.fwdListOff[k + 1] - c.fwdListOff[k];
             if (cnt == 0) continue;
-            a.wcap = class_wcap(k);
             a.list = dLists + c.fwdListOff[k];
             const int warps = g_classWarps[k];
-            forward_kernel<S>(warps)<<<(unsigned) cnt, 32 * warps, dp_smem_bytes<S>(a.wcap), st>>>(a, *m);
+            kernel_table<S>().fwd[k][warp_index(warps)]<<<(unsigned) cnt, 32 * warps, dp_smem_bytes<S>(class_wcap(k)), st>>>(a, *m);
             stx.kernelLaunches++;
         }
         toc(ev);
@@ -612,10 +649,9 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         for (int k = 0; k < kNumClasses; k++) {
             const int64_t cnt = c.bwdListOff[k + 1] - c.bwdListOff[k];
             if (cnt == 0) continue;
-            a.wcap = class_wcap(k);
             a.list = dLists + c.bwdListOff[k];
             const int warps = g_classWarps[k];
-            backward_kernel<S>(warps)<<<(unsigned) cnt, 32 * warps, dp_smem_bytes<S>(a.wcap), st>>>(a, *m);
+            kernel_table<S>().bwd[k][warp_index(warps)]<<<(unsigned) cnt, 32 * warps, dp_smem_bytes<S>(class_wcap(k)), st>>>(a, *m);
             stx.kernelLaunches++;
         }
         toc(ev);
@@ -626,65 +662,77 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         stx.kernelLaunches++;
         toc(ev);
 
+        /* decades of each pair are contiguous in the chunk: [pairDecade0[q], pairDecade0[q+1]) */
+        const int64_t np = c.pair1 - c.pair0 + 1;
         if (nLists > 0) {
             PostArgs pa;
             memset(&pa, 0, sizeof(pa));
             pa.threshold = p->threshold;
             pa.logThresholdLo = p->threshold > 0.0 ? log(p->threshold) - 1e-6 : -INFINITY;
             pa.nLists = nLists;
-            pa.counts = b->counts.as<int64_t>();
+            pa.nDecades = c.decades;
+            pa.maskWords = c.maskWords;
+            pa.counts = b->counts.as<int32_t>();
             pa.offsets = b->offsets.as<int64_t>();
+            pa.masks = b->masks.as<uint32_t>();
             ev = tic(&stx.msPosterior);
-            k_posterior<false><<<(unsigned) ((nb * 32 + 127) / 128), 128, 0, st>>>(a, pa, (int) nb);
+            k_posterior<false><<<(unsigned) nb, 32 * POST_WARPS, 0, st>>>(a, pa);
+            stx.kernelLaunches++;
+            const int64_t nTiles = (c.decades + SCAN_TILE - 1) / SCAN_TILE;
+            int64_t *tileSums = b->tileSums.as<int64_t>();
+            int64_t *totalsOut = tileSums + (int64_t) nLists * maxTiles;
+            for (int l = 0; l < nLists; l++) {
+                const int32_t *cnt = pa.counts + (int64_t) l * c.decades;
+                k_scan_tiles<<<(unsigned) nTiles, 256, 0, st>>>(cnt, c.decades, tileSums + l * maxTiles);
+                k_scan_sums<<<1, 1, 0, st>>>(tileSums + l * maxTiles, nTiles, running[l], totalsOut + l);
+                k_scan_apply<<<(unsigned) nTiles, 256, 0, st>>>(cnt, c.decades, tileSums + l * maxTiles, b->offsets.as<int64_t>() + (int64_t) l * c.decades);
+                stx.kernelLaunches += 3;
+            }
+            hPairOff.assign(np + 1, 0);
+            for (int64_t k = c.block0; k < c.block1; k++)
+                hPairOff[regs[hBlocks[k].region].pair - c.pair0 + 1] += (hBlocks[k].from - hBlocks[k].T + 9) / 10;
+            for (int64_t q = 0; q < np; q++) hPairOff[q + 1] += hPairOff[q];
+            CUDA_TRY(cudaMemcpyAsync(b->pairBlockOff.p, hPairOff.data(), (np + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+            k_pair_counts<<<(unsigned) ((np * nLists + 127) / 128), 128, 0, st>>>(pa.counts, c.decades, nLists, b->pairBlockOff.as<int64_t>(), (int) np,
+                                                                                  b->pairCounts.as<int64_t>() + c.pair0, std::max<int64_t>(b->n, 1));
             stx.kernelLaunches++;
             toc(ev);
-            hCounts.resize(nb * 3);
-            CUDA_TRY(cudaMemcpyAsync(hCounts.data(), b->counts.p, nb * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            hOffsets.resize(nb * 3);
-            for (int64_t k = 0; k < nb; k++) {
-                const int pair = regs[hBlocks[c.block0 + k].region].pair;
-                for (int l = 0; l < nLists; l++) {
-                    hOffsets[k * 3 + l] = running[l];
-                    running[l] += hCounts[k * 3 + l];
-                    pairCount[l][pair] += hCounts[k * 3 + l];
-                }
-            }
+            int64_t newTotals[3] = { 0, 0, 0 };
+            CUDA_TRY(cudaMemcpyAsync(newTotals, totalsOut, nLists * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st)); /* also protects hPairOff */
             for (int l = 0; l < nLists; l++) {
-                const size_t need = (size_t) std::max<int64_t>(running[l], 1) * 3 * sizeof(int32_t);
+                const size_t need = (size_t) std::max<int64_t>(newTotals[l], 1) * 3 * sizeof(int32_t);
                 if (need > b->out[l].cap) {
                     /* grow, keeping what earlier chunks wrote */
                     DevBuf bigger;
                     if ((rc = bigger.reserve(std::max(need + need / 2, (size_t) 1 << 20))) != CPB_OK) return rc;
-                    if (b->out[l].p && hOffsets[l] > 0)
-                        CUDA_TRY(cudaMemcpyAsync(bigger.p, b->out[l].p, (size_t) hOffsets[l] * 3 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+                    if (b->out[l].p && running[l] > 0)
+                        CUDA_TRY(cudaMemcpyAsync(bigger.p, b->out[l].p, (size_t) running[l] * 3 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
                     CUDA_TRY(cudaStreamSynchronize(st));
                     b->out[l].release();
                     b->out[l] = bigger;
                 }
                 pa.out[l] = b->out[l].as<int32_t>();
+                running[l] = newTotals[l];
             }
-            CUDA_TRY(cudaMemcpyAsync(b->offsets.p, hOffsets.data(), nb * 3 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
             ev = tic(&stx.msPosterior);
-            k_posterior<true><<<(unsigned) ((nb * 32 + 127) / 128), 128, 0, st>>>(a, pa, (int) nb);
+            k_posterior<true><<<(unsigned) nb, 32 * POST_WARPS, 0, st>>>(a, pa);
             stx.kernelLaunches++;
             toc(ev);
-            CUDA_TRY(cudaStreamSynchronize(st)); /* hOffsets is reused by the next chunk */
         } else if (mode == CPB_MODE_EXPECTATIONS) {
             const size_t smem = ((sizeof(Tables<S>) + 15) & ~size_t(15)) + (size_t) S * 16 * 32 * sizeof(double);
             ev = tic(&stx.msPosterior);
             k_expect<S><<<(unsigned) nb, 32, smem, st>>>(a, *m, b->partials.as<double>());
             stx.kernelLaunches++;
-            const int64_t np = c.pair1 - c.pair0 + 1;
-            hPairBlockOff.assign(np + 1, 0);
-            for (int64_t k = 0; k < nb; k++) hPairBlockOff[regs[hBlocks[c.block0 + k].region].pair - c.pair0 + 1]++;
-            for (int64_t q = 0; q < np; q++) hPairBlockOff[q + 1] += hPairBlockOff[q];
-            CUDA_TRY(cudaMemcpyAsync(b->pairBlockOff.p, hPairBlockOff.data(), (np + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+            hPairOff.assign(np + 1, 0);
+            for (int64_t k = 0; k < nb; k++) hPairOff[regs[hBlocks[c.block0 + k].region].pair - c.pair0 + 1]++;
+            for (int64_t q = 0; q < np; q++) hPairOff[q + 1] += hPairOff[q];
+            CUDA_TRY(cudaMemcpyAsync(b->pairBlockOff.p, hPairOff.data(), (np + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
             k_reduce_pairs<<<(unsigned) ((np * hmmLen + 127) / 128), 128, 0, st>>>(b->partials.as<double>(), b->pairBlockOff.as<int64_t>(),
                                                                                     (int) np, hmmLen, b->perPair.as<double>() + c.pair0 * hmmLen);
             stx.kernelLaunches++;
             toc(ev);
-            CUDA_TRY(cudaStreamSynchronize(st)); /* hPairBlockOff is reused */
+            CUDA_TRY(cudaStreamSynchronize(st)); /* hPairOff is reused */
         }
     }
     if (mode == CPB_MODE_EXPECTATIONS) {
@@ -693,13 +741,18 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         stx.kernelLaunches++;
         toc(ev);
     }
+    std::vector<int64_t> hPairCounts;
+    if (nLists > 0 && b->n > 0) {
+        hPairCounts.resize((size_t) nLists * b->n);
+        CUDA_TRY(cudaMemcpyAsync(hPairCounts.data(), b->pairCounts.p, hPairCounts.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     finish_events();
     for (int l = 0; l < nLists; l++) {
         b->outCount[l] = running[l];
         stx.outputTriples += running[l];
-        for (int64_t i = 0; i < b->n; i++) b->pairOff[l][i + 1] = b->pairOff[l][i] + pairCount[l][i];
+        for (int64_t i = 0; i < b->n; i++) b->pairOff[l][i + 1] = b->pairOff[l][i] + hPairCounts[(size_t) l * b->n + i];
     }
     return CPB_OK;
 }

@@ -43,6 +43,7 @@ struct RegionDev {
     int64_t blockBase;     /* first BlockRec slot */
     int64_t cellBase;      /* chunk-relative first cell (host, after planning) */
     int64_t auxBase;       /* chunk-relative first aux double (host, after planning) */
+    int64_t maskBase;      /* chunk-relative first keep-mask word (host, after planning) */
     int64_t cells;         /* out: band cells */
     int64_t auxDoubles;    /* out */
     int32_t lX, lY;
@@ -51,10 +52,11 @@ struct RegionDev {
     int32_t ox, oy;        /* region origin in pair coordinates */
     int32_t blockCap;
     int32_t nBlocks;       /* out */
-    int32_t maxW;          /* out */
+    int32_t maxW;          /* out: widest diagonal */
+    int32_t maxSpan;       /* out: window slots needed (see k_band) */
     int32_t err;           /* out: 0 ok, 1 invalid diagonal, 2 block table overflow */
     uint8_t raggedL, raggedR;
-    uint8_t pad_[6];
+    uint8_t pad_[2];
 };
 
 struct BlockRec {
@@ -62,8 +64,9 @@ struct BlockRec {
     int32_t top;   /* diagonal the traceback starts from */
     int32_t T;     /* tracedBackTo before this block: owned diagonals are (T, from] */
     int32_t from;  /* tracedBackFrom */
-    int32_t maxW;  /* widest diagonal in (T, top] */
+    int32_t maxSpan; /* window slots needed for the diagonals in (T, top] */
     int32_t atEnd;
+    int64_t decadeBase; /* chunk-relative index of the block's first decade (host, after planning) */
 };
 
 /* Everything the DP kernels need besides the launch list. */
@@ -79,7 +82,6 @@ struct DpArgs {
     int64_t planeStride;
     int32_t nPlanes;       /* 0 forward-only, 1 match, 3 match+gaps, S expectations */
     int32_t auxF;          /* planes of full forward state kept in aux records of total diagonals (S or 0) */
-    int32_t wcap;          /* window capacity (power of two >= widest diagonal of the class) */
     const int32_t *list;   /* region ids (forward) or block ids (others) */
     double *forwardOut;    /* per region, forward-only mode */
 };
@@ -88,15 +90,14 @@ struct DpArgs {
  * logAdd, bit-compatible with impl/pairwiseAligner.c:290-307
  * ------------------------------------------------------------------------------------------- */
 /* coefficient table laid out [segment][a,b,c,k]; the literals are floats promoted to double exactly as in C */
+__constant__ double c_coefficients[16] = {
+    (double) -0.009350833524763f, (double) 0.130659527668286f, (double) 0.498799810682272f, (double) 0.693203116424741f,
+    (double) -0.014532321752540f, (double) 0.139942324101744f, (double) 0.495635523139337f, (double) 0.692140569840976f,
+    (double) -0.004605031767994f, (double) 0.063427417320019f, (double) 0.695956496475118f, (double) 0.514272634594009f,
+    (double) -0.000458661602210f, (double) 0.009695946122598f, (double) 0.930734667215156f, (double) 0.168037164329057f };
+
 __device__ __forceinline__ void fill_coefficients(double *ctab, int tid) {
-    if (tid < 16) {
-        const double t[16] = {
-            (double) -0.009350833524763f, (double) 0.130659527668286f, (double) 0.498799810682272f, (double) 0.693203116424741f,
-            (double) -0.014532321752540f, (double) 0.139942324101744f, (double) 0.495635523139337f, (double) 0.692140569840976f,
-            (double) -0.004605031767994f, (double) 0.063427417320019f, (double) 0.695956496475118f, (double) 0.514272634594009f,
-            (double) -0.000458661602210f, (double) 0.009695946122598f, (double) 0.930734667215156f, (double) 0.168037164329057f };
-        ctab[tid] = t[tid];
-    }
+    if (tid < 16) ctab[tid] = c_coefficients[tid];
 }
 
 __device__ __forceinline__ double log_add(double x, double y, const double *__restrict__ ctab) {
@@ -218,20 +219,45 @@ __device__ __forceinline__ void cell_backward(double *out, double t2m, const dou
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * The rolling window.  Two parity buffers of S x WCAP doubles in shared memory, indexed by
+ * slot(x-y) = floor((x-y)/2) mod WCAP.  Diagonal d overwrites diagonal d-2 in place (same parity, a
+ * cell and its "middle" neighbour share x-y).  Invariant kept by clear_stale(): a buffer holds the
+ * cells of its latest diagonal and LOG_ZERO in every other slot, so neighbours outside the band read
+ * as LOG_ZERO without any bounds test (the reference skips NULL neighbours; logAdd with LOG_ZERO is
+ * the identity, so the results are the same bits).  WCAP >= the region's maxSpan (k_band) guarantees
+ * that no two live cells alias.
+ * ------------------------------------------------------------------------------------------- */
+template <int S, int WCAP, int NT>
+__device__ __forceinline__ void clear_stale(double *buf, int oldL, int oldR, int newL, int newR, int tid) {
+    /* cells of [oldL, oldR] (step 2) that are not in [newL, newR] */
+    const int leftEnd = min(oldR, newL - 2);
+    const int nLeft = leftEnd >= oldL ? ((leftEnd - oldL) >> 1) + 1 : 0;
+    const int rightStart = max(oldL, newR + 2);
+    const int nRight = oldR >= rightStart ? ((oldR - rightStart) >> 1) + 1 : 0;
+    for (int i = tid; i < nLeft + nRight; i += NT) {
+        const int xmy = i < nLeft ? oldL + 2 * i : rightStart + 2 * (i - nLeft);
+        const int sl = slot_of(xmy, WCAP - 1);
+#pragma unroll
+        for (int s = 0; s < S; s++) buf[s * WCAP + sl] = CPB_NEG_INF;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
  * k_forward : one CTA (WARPS warps) per region
  * ------------------------------------------------------------------------------------------- */
-template <int S, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS) k_forward(const DpArgs a, const CpbModel model) {
+template <int S, int WCAP, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) k_forward(const DpArgs a, const CpbModel model) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     Tables<S> &tab = *reinterpret_cast<Tables<S> *>(smemRaw);
     double *win = reinterpret_cast<double *>(smemRaw + ((sizeof(Tables<S>) + 15) & ~size_t(15)));
     constexpr int NT = 32 * WARPS;
+    constexpr int mask = WCAP - 1;
     const int tid = threadIdx.x;
-    const int wcap = a.wcap, mask = wcap - 1;
 
     const int regionId = a.list[blockIdx.x];
     const RegionDev R = a.regions[regionId];
     fill_tables<S>(tab, model, tid, NT);
+    for (int i = tid; i < 2 * S * WCAP; i += NT) win[i] = CPB_NEG_INF;
     const int N = R.lX + R.lY;
     const DiagRec *dg = a.diags + R.diagBase;
     const uint8_t *sx = a.symX + R.xBase, *sy = a.symY + R.yBase;
@@ -246,21 +272,22 @@ __global__ void __launch_bounds__(32 * WARPS) k_forward(const DpArgs a, const Cp
         const int s0 = slot_of(0, mask);
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            win[(0 * S + s) * wcap + s0] = sv[s];
+            win[(0 * S + s) * WCAP + s0] = sv[s];
             if (s < a.nPlanes) pf[(int64_t) s * a.planeStride] = sv[s];
         }
     }
-    int l2 = 1, r2 = 0; /* band of diagonal d-2: empty */
-    int l1 = prev1.xmyL, r1 = prev1.xmyL + 2 * (prev1.width - 1);
+    int l2 = 1, r2 = -1; /* band of diagonal d-2: empty */
     DiagRec cur = dg[N >= 1 ? 1 : 0];
     cta_sync<WARPS>();
 
     for (int d = 1; d <= N; d++) {
         const DiagRec nxt = dg[d + 1]; /* prefetch (record N+1 is a sentinel) */
         const int par = d & 1;
-        double *wOwn = win + (par * S) * wcap;         /* holds diagonal d-2, overwritten in place with d */
-        const double *wPrev = win + ((par ^ 1) * S) * wcap; /* diagonal d-1 */
+        double *wOwn = win + (par * S) * WCAP;               /* holds diagonal d-2, overwritten in place with d */
+        const double *wPrev = win + ((par ^ 1) * S) * WCAP;  /* diagonal d-1 */
         const bool fullToAux = a.auxF != 0 && cur.aoff != NO_AUX;
+        const int curR = cur.xmyL + 2 * (cur.width - 1);
+#pragma unroll 1
         for (int i = tid; i < cur.width; i += NT) {
             const int xmy = cur.xmyL + 2 * i;
             const int x = (d + xmy) >> 1, y = (d - xmy) >> 1;
@@ -268,21 +295,18 @@ __global__ void __launch_bounds__(32 * WARPS) k_forward(const DpArgs a, const Cp
             const int own = slot_of(xmy, mask);
             const int sl = par ? own : ((own - 1) & mask); /* slot of xmy-1 on diagonal d-1 */
             const int su = par ? ((own + 1) & mask) : own; /* slot of xmy+1 on diagonal d-1 */
-            const bool inL = xmy - 1 >= l1 && xmy - 1 <= r1;
-            const bool inU = xmy + 1 >= l1 && xmy + 1 <= r1;
-            const bool inM = xmy >= l2 && xmy <= r2;
             double lo[S], mid[S], up[S], out[S];
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                lo[s] = inL ? wPrev[s * wcap + sl] : CPB_NEG_INF;
-                up[s] = inU ? wPrev[s * wcap + su] : CPB_NEG_INF;
-                mid[s] = inM ? wOwn[s * wcap + own] : CPB_NEG_INF;
+                lo[s] = wPrev[s * WCAP + sl];
+                up[s] = wPrev[s * WCAP + su];
+                mid[s] = wOwn[s * WCAP + own];
             }
             cell_forward<S>(out, lo, mid, up, tab.tl[cX], tab.tm[cX * 5 + cY], tab.tu[cY], tab.ctab);
             const int64_t cell = (int64_t) cur.coff + i;
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                wOwn[s * wcap + own] = out[s];
+                wOwn[s * WCAP + own] = out[s];
                 if (s < a.nPlanes) pf[(int64_t) s * a.planeStride + cell] = out[s];
             }
             if (fullToAux) {
@@ -290,9 +314,11 @@ __global__ void __launch_bounds__(32 * WARPS) k_forward(const DpArgs a, const Cp
                 for (int s = 0; s < S; s++) aux[(int64_t) cur.aoff + (int64_t) s * cur.width + i] = out[s];
             }
         }
+        clear_stale<S, WCAP, NT>(wOwn, l2, r2, cur.xmyL, curR, tid);
         cta_sync<WARPS>();
-        l2 = l1; r2 = r1;
-        l1 = cur.xmyL; r1 = cur.xmyL + 2 * (cur.width - 1);
+        l2 = prev1.xmyL;
+        r2 = prev1.xmyL + 2 * (prev1.width - 1);
+        prev1 = cur;
         cur = nxt;
     }
 
@@ -301,11 +327,11 @@ __global__ void __launch_bounds__(32 * WARPS) k_forward(const DpArgs a, const Cp
         double v = 0.0; /* LOG_ONE for the empty problem */
         if (N > 0) {
             const int own = slot_of(R.lX - R.lY, mask);
-            const double *w = win + ((N & 1) * S) * wcap;
+            const double *w = win + ((N & 1) * S) * WCAP;
             const double *ev = R.raggedR ? tab.rendv : tab.endv;
-            v = w[0 * wcap + own] + ev[0];
+            v = w[0 * WCAP + own] + ev[0];
 #pragma unroll
-            for (int s = 1; s < S; s++) v = log_add(v, w[s * wcap + own] + ev[s], tab.ctab);
+            for (int s = 1; s < S; s++) v = log_add(v, w[s * WCAP + own] + ev[s], tab.ctab);
         }
         a.forwardOut[regionId] = v;
     }
@@ -314,18 +340,19 @@ __global__ void __launch_bounds__(32 * WARPS) k_forward(const DpArgs a, const Cp
 /* ---------------------------------------------------------------------------------------------
  * k_backward : one CTA per traceback block
  * ------------------------------------------------------------------------------------------- */
-template <int S, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS) k_backward(const DpArgs a, const CpbModel model) {
+template <int S, int WCAP, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) k_backward(const DpArgs a, const CpbModel model) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     Tables<S> &tab = *reinterpret_cast<Tables<S> *>(smemRaw);
     double *win = reinterpret_cast<double *>(smemRaw + ((sizeof(Tables<S>) + 15) & ~size_t(15)));
     constexpr int NT = 32 * WARPS;
+    constexpr int mask = WCAP - 1;
     const int tid = threadIdx.x;
-    const int wcap = a.wcap, mask = wcap - 1;
 
     const BlockRec K = a.blocks[a.list[blockIdx.x]];
     const RegionDev R = a.regions[K.region];
     fill_tables<S>(tab, model, tid, NT);
+    for (int i = tid; i < 2 * S * WCAP; i += NT) win[i] = CPB_NEG_INF;
     const DiagRec *dg = a.diags + R.diagBase;
     const uint8_t *sx = a.symX + R.xBase, *sy = a.symY + R.yBase;
     const double *pf = a.planesF + R.cellBase;
@@ -334,18 +361,21 @@ __global__ void __launch_bounds__(32 * WARPS) k_backward(const DpArgs a, const C
     const int top = K.top, T = K.T, from = K.from;
     cta_sync<WARPS>();
     const double *endVec = (K.atEnd && R.raggedR) ? tab.rendv : tab.endv;
+    const int nF = a.auxF; /* full-F planes stored in aux (0 in expectation mode) */
 
-    int l1 = 1, r1 = 0, l2 = 1, r2 = 0; /* bands of diagonals d+1, d+2 */
-    DiagRec cur = dg[top];
+    int l2 = 1, r2 = -1; /* band of diagonal d+2 */
+    DiagRec prev1 = dg[top];
+    DiagRec cur = prev1;
     for (int d = top; d > T; d--) {
         const DiagRec nxt = dg[d - 1]; /* the next diagonal down (d-1 >= T >= 0) */
         const int par = d & 1;
-        double *wOwn = win + (par * S) * wcap;              /* holds B[d+2], overwritten in place with B[d] */
-        const double *wNext = win + ((par ^ 1) * S) * wcap; /* B[d+1] */
+        double *wOwn = win + (par * S) * WCAP;               /* holds B[d+2], overwritten in place with B[d] */
+        const double *wNext = win + ((par ^ 1) * S) * WCAP;  /* B[d+1] */
         const bool owned = d <= from;
         const bool isTotal = owned && cur.aoff != NO_AUX;
-        const bool feedsTotal = d - 1 > T && d - 1 <= from && nxt.aoff != NO_AUX; /* diagonal d-1 is a total diagonal: it needs F.M+B.M of d */
-        const int nF = a.auxF;                                  /* full-F planes stored in aux (0 in expectation mode) */
+        const bool feedsTotal = d - 1 > T && d - 1 <= from && nxt.aoff != NO_AUX; /* d-1 is a total diagonal: it needs F.M+B.M of d */
+        const int curR = cur.xmyL + 2 * (cur.width - 1);
+#pragma unroll 1
         for (int i = tid; i < cur.width; i += NT) {
             const int xmy = cur.xmyL + 2 * i;
             const int own = slot_of(xmy, mask);
@@ -358,22 +388,19 @@ __global__ void __launch_bounds__(32 * WARPS) k_backward(const DpArgs a, const C
                 const int cX = x < R.lX ? sx[x] : 4, cY = y < R.lY ? sy[y] : 4; /* symbols of row x+1 / column y+1 */
                 const int sU = par ? own : ((own - 1) & mask); /* slot of xmy-1 on diagonal d+1: cell (x,y+1) */
                 const int sL = par ? ((own + 1) & mask) : own; /* slot of xmy+1 on diagonal d+1: cell (x+1,y) */
-                const bool inU = xmy - 1 >= l1 && xmy - 1 <= r1;
-                const bool inL = xmy + 1 >= l1 && xmy + 1 <= r1;
-                const bool in2 = xmy >= l2 && xmy <= r2;
                 double toU[S], toL[S];
 #pragma unroll
                 for (int s = 0; s < S; s++) {
-                    toU[s] = inU ? wNext[s * wcap + sU] : CPB_NEG_INF;
-                    toL[s] = inL ? wNext[s * wcap + sL] : CPB_NEG_INF;
+                    toU[s] = wNext[s * WCAP + sU];
+                    toL[s] = wNext[s * WCAP + sL];
                 }
-                const double t2m = in2 ? wOwn[0 * wcap + own] : CPB_NEG_INF;
+                const double t2m = wOwn[0 * WCAP + own];
                 cell_backward<S>(out, t2m, toU, toL, tab.tm[cX * 5 + cY], tab.tu[cY], tab.tl[cX], tab.ctab);
             }
             const int64_t cell = (int64_t) cur.coff + i;
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                wOwn[s * wcap + own] = out[s];
+                wOwn[s * WCAP + own] = out[s];
                 if (owned && s < a.nPlanes) pb[(int64_t) s * a.planeStride + cell] = out[s];
             }
             if (isTotal) {
@@ -396,9 +423,12 @@ __global__ void __launch_bounds__(32 * WARPS) k_backward(const DpArgs a, const C
                 aux[(int64_t) nxt.aoff + (int64_t) (nF + 1) * nxt.width + i] = pf[cell] + out[0];
             }
         }
+        clear_stale<S, WCAP, NT>(wOwn, l2, r2, cur.xmyL, curR, tid);
         cta_sync<WARPS>();
-        l2 = l1; r2 = r1;
-        l1 = cur.xmyL; r1 = cur.xmyL + 2 * (cur.width - 1);
+        l2 = prev1.xmyL;
+        r2 = prev1.xmyL + 2 * (prev1.width - 1);
+        if (d == top) { l2 = 1; r2 = -1; } /* nothing above the top diagonal */
+        prev1 = cur;
         cur = nxt;
     }
 }
@@ -409,7 +439,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_backward(const DpArgs a, const C
  * cells of the diagonal (dpDiagonal_dotProduct, :513-523), so lanes run independent folds in parallel.
  * ------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(128) k_totals(const DpArgs a, int nBlocks) {
-    __shared__ double ctab[16];
+    __shared__ __align__(16) double ctab[16];
     fill_coefficients(ctab, threadIdx.x);
     __syncthreads();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -437,72 +467,170 @@ __global__ void __launch_bounds__(128) k_totals(const DpArgs a, int nBlocks) {
 }
 
 /* ---------------------------------------------------------------------------------------------
- * k_posterior : one warp per block.  WRITE == false counts kept cells per list, WRITE == true writes the
- * (pInt, x, y) triples at the block's offsets (diagonalCalculationPosteriorMatchProbs / ...PosteriorProbs,
- * impl/pairwiseAligner.c:655-733).
+ * k_posterior : one CTA of POST_WARPS warps per block, one warp per decade at a time.
+ *   WRITE == false : evaluates exp(F+B-total) >= threshold for every owned cell (addPosteriorProb,
+ *                    impl/pairwiseAligner.c:655-664), stores one ballot word per 32 cells and the
+ *                    number of kept cells of the decade;
+ *   (device scan of the decade counts)
+ *   WRITE == true  : revisits only the set bits and writes (pInt, x, y) at the decade's offset.
+ * Decades are numbered in ascending-diagonal order inside a block, so the output of a region is
+ * sorted by (x+y, x).
  * ------------------------------------------------------------------------------------------- */
+constexpr int POST_WARPS = 8;
+
 struct PostArgs {
     double threshold;
-    double logThresholdLo; /* log(threshold) minus a safety margin: cells below it cannot pass p >= threshold */
-    int32_t nLists;        /* 1 or 3 */
-    int64_t *counts;       /* [nBlocksInLaunch][3] */
-    const int64_t *offsets; /* [nBlocksInLaunch][3] start offset per list (WRITE) */
+    double logThresholdLo;   /* log(threshold) minus a safety margin: cells below it cannot pass p >= threshold */
+    int32_t nLists;          /* 1 or 3 */
+    int32_t pad_;
+    int64_t nDecades;        /* decades in this chunk (stride between lists in counts/offsets) */
+    int64_t maskWords;       /* mask words per list */
+    int32_t *counts;         /* [nLists][nDecades] */
+    const int64_t *offsets;  /* [nLists][nDecades] exclusive, global (WRITE) */
+    uint32_t *masks;         /* [nLists][maskWords] */
     int32_t *out[3];
 };
 
 template <bool WRITE>
-__global__ void __launch_bounds__(128) k_posterior(const DpArgs a, const PostArgs p, int nBlocks) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= nBlocks) return;
-    const BlockRec K = a.blocks[a.list[warp]];
+__global__ void __launch_bounds__(32 * POST_WARPS) k_posterior(const DpArgs a, const PostArgs p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const BlockRec K = a.blocks[a.list[blockIdx.x]];
     const RegionDev R = a.regions[K.region];
     const DiagRec *dg = a.diags + R.diagBase;
     const double *tot = a.totals + R.diagBase;
-    int64_t run[3] = { 0, 0, 0 };
-    if (WRITE) {
-        for (int l = 0; l < p.nLists; l++) run[l] = p.offsets[(int64_t) warp * 3 + l];
-    }
+    const int nDecades = (K.from - K.T + 9) / 10;
     const unsigned ltMask = (1u << lane) - 1u;
-    for (int d = K.T + 1; d <= K.from; d++) {
-        const int dt = K.from - 10 * ((K.from - d) / 10);
+    for (int j = warp; j < nDecades; j += POST_WARPS) {
+        const int dt = K.from - 10 * j;                       /* the decade's total diagonal (its highest) */
+        const int64_t g = K.decadeBase + (nDecades - 1 - j);  /* ascending-diagonal numbering */
         const double total = tot[dt];
-        const DiagRec rec = dg[d];
-        for (int i0 = 0; i0 < rec.width; i0 += 32) {
-            const int i = i0 + lane;
-            const bool valid = i < rec.width;
-            const int xmy = rec.xmyL + 2 * i;
-            const int x = (d + xmy) >> 1, y = (d - xmy) >> 1;
-            const int64_t cell = R.cellBase + (int64_t) rec.coff + i;
-            for (int l = 0; l < p.nLists; l++) {
-                /* list 0: match (x>0 && y>0); 1: gapX (x>0); 2: gapY (y>0) -- planes 0,1,2 are M, gapX, gapY */
-                const bool eligible = valid && (l == 0 ? (x > 0 && y > 0) : (l == 1 ? x > 0 : y > 0));
-                bool keep = false;
-                int pInt = 0;
-                if (eligible) {
-                    const double z = (a.planesF[(int64_t) l * a.planeStride + cell] + a.planesB[(int64_t) l * a.planeStride + cell]) - total;
-                    if (z >= p.logThresholdLo) {
-                        double pr = exp(z);
-                        if (pr >= p.threshold) {
-                            keep = true;
-                            if (pr > 1.0) pr = 1.0;
-                            pInt = (int) floor(pr * (double) CPB_PAIR_ALIGNMENT_PROB_1);
+        const int dLow = max(dt - 9, K.T + 1);
+        int64_t run[3] = { 0, 0, 0 };
+        if (WRITE) {
+            for (int l = 0; l < p.nLists; l++) run[l] = p.offsets[(int64_t) l * p.nDecades + g];
+        }
+        for (int d = dLow; d <= dt; d++) {
+            const DiagRec rec = dg[d];
+            const int64_t word0 = R.maskBase + (rec.coff >> 5) + d;
+            for (int i0 = 0; i0 < rec.width; i0 += 32) {
+                const int i = i0 + lane;
+                const bool valid = i < rec.width;
+                const int xmy = rec.xmyL + 2 * i;
+                const int x = (d + xmy) >> 1, y = (d - xmy) >> 1;
+                const int64_t cell = R.cellBase + (int64_t) rec.coff + i;
+                const int64_t word = word0 + (i0 >> 5);
+                for (int l = 0; l < p.nLists; l++) {
+                    /* list 0: match (x>0 && y>0); 1: gapX (x>0); 2: gapY (y>0) -- planes 0,1,2 are M, gapX, gapY */
+                    unsigned m;
+                    bool keep = false;
+                    int pInt = 0;
+                    if (WRITE) {
+                        m = p.masks[(int64_t) l * p.maskWords + word];
+                        keep = (m >> lane) & 1u;
+                    } else {
+                        keep = valid && (l == 0 ? (x > 0 && y > 0) : (l == 1 ? x > 0 : y > 0));
+                    }
+                    if (keep) {
+                        const double z = (a.planesF[(int64_t) l * a.planeStride + cell] + a.planesB[(int64_t) l * a.planeStride + cell]) - total;
+                        keep = false;
+                        if (z >= p.logThresholdLo) {
+                            double pr = exp(z);
+                            if (pr >= p.threshold) {
+                                keep = true;
+                                if (pr > 1.0) pr = 1.0;
+                                pInt = (int) floor(pr * (double) CPB_PAIR_ALIGNMENT_PROB_1);
+                            }
                         }
                     }
+                    if (WRITE) {
+                        if (keep) {
+                            int32_t *o = p.out[l] + 3 * (run[l] + __popc(m & ltMask));
+                            o[0] = pInt;
+                            o[1] = x - 1 + R.ox;
+                            o[2] = y - 1 + R.oy;
+                        }
+                    } else {
+                        m = __ballot_sync(0xFFFFFFFFu, keep);
+                        if (lane == 0) p.masks[(int64_t) l * p.maskWords + word] = m;
+                    }
+                    run[l] += __popc(m);
                 }
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-                if (WRITE && keep) {
-                    int32_t *o = p.out[l] + 3 * (run[l] + __popc(m & ltMask));
-                    o[0] = pInt;
-                    o[1] = x - 1 + R.ox;
-                    o[2] = y - 1 + R.oy;
-                }
-                run[l] += __popc(m);
             }
         }
+        if (!WRITE && lane == 0) {
+            for (int l = 0; l < p.nLists; l++) p.counts[(int64_t) l * p.nDecades + g] = (int32_t) run[l];
+        }
     }
-    if (!WRITE && lane == 0) {
-        for (int l = 0; l < 3; l++) p.counts[(int64_t) warp * 3 + l] = run[l];
+}
+
+/* ---- exclusive scan of int32 counts into int64 offsets (three small kernels) ---- */
+constexpr int SCAN_TILE = 2048;
+
+__global__ void __launch_bounds__(256) k_scan_tiles(const int32_t *counts, int64_t n, int64_t *tileSums) {
+    __shared__ int64_t red[256];
+    const int64_t base = (int64_t) blockIdx.x * SCAN_TILE;
+    int64_t s = 0;
+    for (int k = threadIdx.x; k < SCAN_TILE; k += 256) {
+        const int64_t i = base + k;
+        if (i < n) s += counts[i];
     }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tileSums[blockIdx.x] = red[0];
+}
+
+/* single thread block: exclusive scan of the tile sums, starting from *startAt; writes the grand total to *totalOut */
+__global__ void __launch_bounds__(1) k_scan_sums(int64_t *tileSums, int64_t nTiles, int64_t startAt, int64_t *totalOut) {
+    int64_t run = startAt;
+    for (int64_t t = 0; t < nTiles; t++) {
+        const int64_t v = tileSums[t];
+        tileSums[t] = run;
+        run += v;
+    }
+    *totalOut = run;
+}
+
+__global__ void __launch_bounds__(256) k_scan_apply(const int32_t *counts, int64_t n, const int64_t *tileOff, int64_t *offsets) {
+    /* each thread owns 8 consecutive elements of the tile */
+    __shared__ int64_t part[256];
+    const int64_t base = (int64_t) blockIdx.x * SCAN_TILE + (int64_t) threadIdx.x * 8;
+    int32_t v[8];
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        v[k] = base + k < n ? counts[base + k] : 0;
+        s += v[k];
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    /* Hillis-Steele inclusive scan over 256 partials */
+    for (int o = 1; o < 256; o <<= 1) {
+        int64_t t = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    int64_t run = tileOff[blockIdx.x] + part[threadIdx.x] - s;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (base + k < n) offsets[base + k] = run;
+        run += v[k];
+    }
+}
+
+/* per pair: add the kept-cell counts of its decades in this chunk; decades of a pair are contiguous */
+__global__ void k_pair_counts(const int32_t *counts, int64_t nDecades, int nLists, const int64_t *pairDecade0, int nPairs, int64_t *pairCounts,
+                              int64_t pairStride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nPairs * nLists) return;
+    const int l = i / nPairs, q = i % nPairs;
+    int64_t s = 0;
+    for (int64_t g = pairDecade0[q]; g < pairDecade0[q + 1]; g++) s += counts[(int64_t) l * nDecades + g];
+    pairCounts[(int64_t) l * pairStride + q] += s;
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -674,7 +802,8 @@ __global__ void k_band(const BandArgs b) {
     int64_t ai = 0, pxay = 0, pxmy = 0, nxay = 0, nxmy = 0, xL = 0, yL = 0, xU = 0, yU = 0;
     int64_t e = b.dynamic ? 0 : b.expansion;
     int64_t coff = 0;
-    int maxW = 0, err = 0;
+    int maxW = 0, maxSpan = 1, err = 0;
+    int64_t bl1 = 0, br1 = 0, bl2 = 0, br2 = -1; /* bands of the two previous diagonals */
     for (int64_t xay = 0; xay <= N; xay++) {
         int64_t l = xL - yL, rr = xU - yU, v;
         if ((xay + l) % 2 != 0) l += 1;
@@ -696,6 +825,19 @@ __global__ void k_band(const BandArgs b) {
         dg[xay] = rec;
         coff += w;
         maxW = w > maxW ? w : maxW;
+        {
+            /* window slots the kernels need around this diagonal: same parity as xay-2, and xay-1 vs the +-1 neighbourhood */
+            int span = w;
+            if (xay >= 2 && br2 >= bl2) span = (int) (((rr > br2 ? rr : br2) - (l < bl2 ? l : bl2)) / 2 + 1);
+            if (xay >= 1) {
+                const int64_t hi = br1 > rr + 1 ? br1 : rr + 1, lo = bl1 < l - 1 ? bl1 : l - 1;
+                const int sb = (int) ((hi - lo) / 2 + 1);
+                span = sb > span ? sb : span;
+            }
+            dg[xay].aoff = (uint32_t) span; /* parked here until the schedule pass below consumes it */
+            maxSpan = span > maxSpan ? span : maxSpan;
+            bl2 = bl1; br2 = br1; bl1 = l; br1 = rr;
+        }
         if (nxay == xay) {
             pxay = nxay;
             pxmy = nxmy;
@@ -723,6 +865,7 @@ __global__ void k_band(const BandArgs b) {
 
     int nBlocks = 0;
     int64_t auxD = 0;
+    /* the per-diagonal spans were parked in aoff; blocks take their maximum, then aoff gets its real meaning */
     if (b.scheduleOn && N > 0) {
         BlockRec *bl = b.blocks + R.blockBase;
         int64_t T = 0;
@@ -732,15 +875,20 @@ __global__ void k_band(const BandArgs b) {
             if (!(atEnd || tb)) continue;
             const int64_t from = d - (atEnd ? 0 : b.traceBack + 1);
             int mw = 0;
-            for (int64_t k = T + 1; k <= d; k++) mw = dg[k].width > mw ? dg[k].width : mw;
+            for (int64_t k = T + 1; k <= d; k++) {
+                const int sp = (int) dg[k].aoff; /* still the parked span: diagonals above T have no owner yet */
+                mw = sp > mw ? sp : mw;
+                if (k <= from) dg[k].aoff = NO_AUX;
+            }
             if (nBlocks < R.blockCap) {
                 BlockRec K;
                 K.region = r;
                 K.top = (int32_t) d;
                 K.T = (int32_t) T;
                 K.from = (int32_t) from;
-                K.maxW = mw;
+                K.maxSpan = mw;
                 K.atEnd = atEnd;
+                K.decadeBase = 0;
                 bl[nBlocks] = K;
             } else {
                 err = 2;
@@ -753,11 +901,15 @@ __global__ void k_band(const BandArgs b) {
             }
             T = from;
         }
+        dg[0].aoff = NO_AUX;
+    } else {
+        for (int64_t k = 0; k <= N; k++) dg[k].aoff = NO_AUX;
     }
     R.cells = coff;
     R.auxDoubles = auxD;
     R.nBlocks = nBlocks;
     R.maxW = maxW;
+    R.maxSpan = maxSpan;
     R.err = err;
     b.regions[r] = R;
 }
