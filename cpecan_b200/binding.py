@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcpecan_b200.so")
+LIB_PATH = os.environ.get("CPB_LIB") or os.path.join(_HERE, "lib", "libcpecan_b200.so")  # CPB_LIB: kernel-variant experiments only
 
 PAIR_ALIGNMENT_PROB_1 = 10000000
 fiveState, fiveStateAsymmetric, threeState, threeStateAsymmetric = 0, 1, 2, 3

@@ -96,9 +96,23 @@ __constant__ double c_coefficients[16] = {
     (double) -0.004605031767994f, (double) 0.063427417320019f, (double) 0.695956496475118f, (double) 0.514272634594009f,
     (double) -0.000458661602210f, (double) 0.009695946122598f, (double) 0.930734667215156f, (double) 0.168037164329057f };
 
+__constant__ float c_coefficients_f32[16] = {
+    -0.009350833524763f, 0.130659527668286f, 0.498799810682272f, 0.693203116424741f,
+    -0.014532321752540f, 0.139942324101744f, 0.495635523139337f, 0.692140569840976f,
+    -0.004605031767994f, 0.063427417320019f, 0.695956496475118f, 0.514272634594009f,
+    -0.000458661602210f, 0.009695946122598f, 0.930734667215156f, 0.168037164329057f };
+
 __device__ __forceinline__ void fill_coefficients(double *ctab, int tid) {
+#if CPB_COEF_MODE == 1
+    if (tid < 16) reinterpret_cast<float *>(ctab)[tid] = c_coefficients_f32[tid];
+#else
     if (tid < 16) ctab[tid] = c_coefficients[tid];
+#endif
 }
+
+#ifndef CPB_COEF_MODE
+#define CPB_COEF_MODE 0 /* 0: FP64 table in shared memory; 1: FP32 table in shared memory, widened per use; 2: FP64 table in constant memory */
+#endif
 
 __device__ __forceinline__ double log_add(double x, double y, const double *__restrict__ ctab) {
     const double diff = __dsub_rn(x, y);
@@ -107,8 +121,17 @@ __device__ __forceinline__ double log_add(double x, double y, const double *__re
     const double small = xSmaller ? x : y;
     const double d = fabs(diff);
     const int seg = (d > 1.0) + (d > 2.5) + (d > 4.5);
+#if CPB_COEF_MODE == 1
+    /* the reference's coefficients are float literals: fetch 16 bytes and widen exactly */
+    const float4 c4 = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(ctab) + 4 * seg);
+    const double2 ab = make_double2((double) c4.x, (double) c4.y), ck = make_double2((double) c4.z, (double) c4.w);
+#elif CPB_COEF_MODE == 2
+    const double2 ab = *reinterpret_cast<const double2 *>(c_coefficients + 4 * seg);
+    const double2 ck = *reinterpret_cast<const double2 *>(c_coefficients + 4 * seg + 2);
+#else
     const double2 ab = *reinterpret_cast<const double2 *>(ctab + 4 * seg);
     const double2 ck = *reinterpret_cast<const double2 *>(ctab + 4 * seg + 2);
+#endif
     double r = __dadd_rn(__dmul_rn(ab.x, d), ab.y);
     r = __dadd_rn(__dmul_rn(r, d), ck.x);
     r = __dadd_rn(__dmul_rn(r, d), ck.y);
@@ -130,6 +153,7 @@ template <int S> struct Tables {
     double tm[25][Shape<S>::NM];     /* [cX*5+cY][k] */
     double tu[5][Shape<S>::NU];      /* [cY][k] */
     double startv[S], rstartv[S], endv[S], rendv[S];
+    double eGapX[5], eGapY[5], eMatch[25]; /* bare emissions: the DP kernels add the (uniform) transition per cell */
 };
 
 template <int S> __device__ __forceinline__ void fill_tables(Tables<S> &t, const CpbModel &m, int tid, int nthreads) {
@@ -146,6 +170,11 @@ template <int S> __device__ __forceinline__ void fill_tables(Tables<S> &t, const
         const int c = i / Shape<S>::NU, k = i % Shape<S>::NU;
         t.tu[c][k] = m.eGapY[c] + m.tUpper[k];
     }
+    if (tid < 5) {
+        t.eGapX[tid] = m.eGapX[tid];
+        t.eGapY[tid] = m.eGapY[tid];
+    }
+    if (tid < 25) t.eMatch[tid] = m.eMatch[tid];
     if (tid < S) {
         t.startv[tid] = m.start[tid];
         t.rstartv[tid] = m.raggedStart[tid];
@@ -302,7 +331,18 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) k_forward(const DpArgs
                 up[s] = wPrev[s * WCAP + su];
                 mid[s] = wOwn[s * WCAP + own];
             }
-            cell_forward<S>(out, lo, mid, up, tab.tl[cX], tab.tm[cX * 5 + cY], tab.tu[cY], tab.ctab);
+            /* eP + tP per transition: one emission load per group, the transition comes from the constant bank */
+            double tl[Shape<S>::NL], tm[Shape<S>::NM], tu[Shape<S>::NU];
+            {
+                const double eX = tab.eGapX[cX], eM = tab.eMatch[cX * 5 + cY], eY = tab.eGapY[cY];
+#pragma unroll
+                for (int k = 0; k < Shape<S>::NL; k++) tl[k] = eX + model.tLower[k];
+#pragma unroll
+                for (int k = 0; k < Shape<S>::NM; k++) tm[k] = eM + model.tMiddle[k];
+#pragma unroll
+                for (int k = 0; k < Shape<S>::NU; k++) tu[k] = eY + model.tUpper[k];
+            }
+            cell_forward<S>(out, lo, mid, up, tl, tm, tu, tab.ctab);
             const int64_t cell = (int64_t) cur.coff + i;
 #pragma unroll
             for (int s = 0; s < S; s++) {
@@ -314,7 +354,7 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) k_forward(const DpArgs
                 for (int s = 0; s < S; s++) aux[(int64_t) cur.aoff + (int64_t) s * cur.width + i] = out[s];
             }
         }
-        clear_stale<S, WCAP, NT>(wOwn, l2, r2, cur.xmyL, curR, tid);
+        if (l2 < cur.xmyL || r2 > curR) clear_stale<S, WCAP, NT>(wOwn, l2, r2, cur.xmyL, curR, tid);
         cta_sync<WARPS>();
         l2 = prev1.xmyL;
         r2 = prev1.xmyL + 2 * (prev1.width - 1);
@@ -395,7 +435,17 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) k_backward(const DpArg
                     toL[s] = wNext[s * WCAP + sL];
                 }
                 const double t2m = wOwn[0 * WCAP + own];
-                cell_backward<S>(out, t2m, toU, toL, tab.tm[cX * 5 + cY], tab.tu[cY], tab.tl[cX], tab.ctab);
+                double tl[Shape<S>::NL], tm[Shape<S>::NM], tu[Shape<S>::NU];
+                {
+                    const double eX = tab.eGapX[cX], eM = tab.eMatch[cX * 5 + cY], eY = tab.eGapY[cY];
+#pragma unroll
+                    for (int k = 0; k < Shape<S>::NL; k++) tl[k] = eX + model.tLower[k];
+#pragma unroll
+                    for (int k = 0; k < Shape<S>::NM; k++) tm[k] = eM + model.tMiddle[k];
+#pragma unroll
+                    for (int k = 0; k < Shape<S>::NU; k++) tu[k] = eY + model.tUpper[k];
+                }
+                cell_backward<S>(out, t2m, toU, toL, tm, tu, tl, tab.ctab);
             }
             const int64_t cell = (int64_t) cur.coff + i;
 #pragma unroll
@@ -423,7 +473,7 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) k_backward(const DpArg
                 aux[(int64_t) nxt.aoff + (int64_t) (nF + 1) * nxt.width + i] = pf[cell] + out[0];
             }
         }
-        clear_stale<S, WCAP, NT>(wOwn, l2, r2, cur.xmyL, curR, tid);
+        if (l2 < cur.xmyL || r2 > curR) clear_stale<S, WCAP, NT>(wOwn, l2, r2, cur.xmyL, curR, tid);
         cta_sync<WARPS>();
         l2 = prev1.xmyL;
         r2 = prev1.xmyL + 2 * (prev1.width - 1);
