@@ -21,6 +21,7 @@
 #include "cpecan_b200.h"
 #include "internal.h"
 #include "kernels.cuh"
+#include "strip_kernels.cuh"
 
 using namespace cpb;
 
@@ -134,7 +135,12 @@ struct cpb_context {
     bool ownStream = false;
     size_t scratchBudget = 0;
     DevBuf scratch;
+    DevBuf boundary, counters; /* strip engine: per-warp-slot boundary rings, work-fetch counters */
+    int smCount = 148;
+    int stripEngine = 1;       /* 1: barrier-free warp-per-region kernels (default); 0: CTA-per-region kernels (CPB_ENGINE=cta) */
 };
+
+static const int kStripWPC = 4; /* warps per CTA of the strip kernels */
 
 static int configure_kernels() {
     const int maxSmem = 227 * 1024;
@@ -188,6 +194,12 @@ extern "C" int cpb_context_create(int device, void *stream, cpb_context **out) {
             }
         }
     }
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->smCount = prop.multiProcessorCount;
+        const char *eng = getenv("CPB_ENGINE");
+        if (eng != nullptr && strcmp(eng, "cta") == 0) ctx->stripEngine = 0;
+    }
     int rc = configure_kernels();
     if (rc != CPB_OK) {
         if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
@@ -202,6 +214,8 @@ extern "C" void cpb_context_destroy(cpb_context *ctx) {
     if (ctx == nullptr) return;
     cudaSetDevice(ctx->device);
     ctx->scratch.release();
+    ctx->boundary.release();
+    ctx->counters.release();
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -219,6 +233,7 @@ struct Chunk {
     int64_t fwdListOff[kNumClasses + 1]; /* offsets into the forward list array */
     int64_t bwdListOff[kNumClasses + 1];
     int64_t allBlocksOff;                /* offset of the chunk's in-order block list */
+    int64_t stripFwdOff, stripBwdOff;    /* strip engine: regions / blocks sorted by cost */
     int64_t pair0, pair1;                /* pairs touched: [pair0, pair1] inclusive */
 };
 
@@ -229,6 +244,7 @@ struct cpb_batch {
     std::vector<uint8_t> rl, rr;
     DevBuf symX, symY, dAnchors;
     /* run state */
+    DevBuf strips;
     DevBuf regions, diags, blocks, totals, lists, counts, offsets, masks, tileSums, pairCounts, partials, pairBlockOff, perPair, hmmTotal, forwardOut;
     DevBuf out[3];
     int64_t outCount[3] = { 0, 0, 0 };
@@ -294,7 +310,7 @@ extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *se
 extern "C" void cpb_batch_destroy(cpb_batch *b) {
     if (b == nullptr) return;
     cudaSetDevice(b->ctx->device);
-    DevBuf *bufs[] = { &b->symX, &b->symY, &b->dAnchors, &b->regions, &b->diags, &b->blocks, &b->totals, &b->lists, &b->counts,
+    DevBuf *bufs[] = { &b->strips, &b->symX, &b->symY, &b->dAnchors, &b->regions, &b->diags, &b->blocks, &b->totals, &b->lists, &b->counts,
                        &b->offsets, &b->masks, &b->tileSums, &b->pairCounts, &b->partials, &b->pairBlockOff, &b->perPair, &b->hmmTotal, &b->forwardOut, &b->out[0], &b->out[1],
                        &b->out[2] };
     for (DevBuf *d : bufs) d->release();
@@ -307,7 +323,7 @@ extern "C" void cpb_batch_destroy(cpb_batch *b) {
 static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
     b->hRegions.clear();
     std::vector<int64_t> split;
-    int64_t diagBase = 0, blockBase = 0;
+    int64_t diagBase = 0, blockBase = 0, stripBase = 0;
     for (int64_t i = 0; i < b->n; i++) {
         const int64_t lX = b->xOff[i + 1] - b->xOff[i], lY = b->yOff[i + 1] - b->yOff[i];
         const int64_t a0 = b->aOff[i], nA = b->aOff[i + 1] - a0;
@@ -353,6 +369,8 @@ static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
             const int64_t N = (int64_t) R.lX + R.lY;
             R.diagBase = diagBase;
             R.blockBase = blockBase;
+            R.stripBase = stripBase;
+            stripBase += (R.lX >> 5) + 1;
             /* consecutive traceback points are at least minDiags - (traceBack+1) diagonals apart (T moves to d - traceBack - 1) */
             R.blockCap = (int32_t) (N / (p->minDiagsBetweenTraceBack - p->traceBackDiagonals - 1) + 2);
             diagBase += N + 2;
@@ -445,6 +463,8 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     if ((rc = b->regions.reserve(nReg * sizeof(RegionDev))) != CPB_OK) return rc;
     if ((rc = b->diags.reserve(nDiagRecs * sizeof(DiagRec))) != CPB_OK) return rc;
     if ((rc = b->blocks.reserve(blockSlots * sizeof(BlockRec))) != CPB_OK) return rc;
+    const int64_t nStripRecs = regs.back().stripBase + (regs.back().lX >> 5) + 1;
+    if ((rc = b->strips.reserve(nStripRecs * sizeof(StripRec))) != CPB_OK) return rc;
     if (mode != CPB_MODE_FORWARD) {
         if ((rc = b->totals.reserve(nDiagRecs * sizeof(double))) != CPB_OK) return rc;
     } else {
@@ -459,6 +479,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         ba.anchors = b->dAnchors.as<int32_t>();
         ba.diags = b->diags.as<DiagRec>();
         ba.blocks = b->blocks.as<BlockRec>();
+        ba.strips = b->strips.as<StripRec>();
         ba.nRegions = (int32_t) nReg;
         ba.expansion = (int32_t) p->diagonalExpansion;
         ba.dynamic = (mode == CPB_MODE_FORWARD) ? 0 : (p->dynamicAnchorExpansion != 0); /* forward prob always uses the static band (:894) */
@@ -488,7 +509,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             finish_events();
             return CPB_ERR_BAND;
         }
-        if (class_of_width(regs[r].maxSpan) >= kNumClasses) {
+        if (!ctx->stripEngine && class_of_width(regs[r].maxSpan) >= kNumClasses) {
             cpb_set_error("pair %d: band is %d cells wide; the widest kernel configuration holds %d", regs[r].pair, regs[r].maxSpan,
                           class_wcap(kNumClasses - 1));
             finish_events();
@@ -567,14 +588,14 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     std::vector<int32_t> lists;
     for (auto &c : chunks) {
         std::vector<std::vector<int32_t>> byClass(kNumClasses);
-        for (int64_t r = c.region0; r < c.region1; r++) byClass[class_of_width(regs[r].maxSpan)].push_back((int32_t) r);
+        for (int64_t r = c.region0; r < c.region1 && !ctx->stripEngine; r++) byClass[class_of_width(regs[r].maxSpan)].push_back((int32_t) r);
         for (int k = 0; k < kNumClasses; k++) {
             c.fwdListOff[k] = (int64_t) lists.size();
             lists.insert(lists.end(), byClass[k].begin(), byClass[k].end());
         }
         c.fwdListOff[kNumClasses] = (int64_t) lists.size();
         for (auto &v : byClass) v.clear();
-        for (int64_t k = c.block0; k < c.block1; k++) byClass[class_of_width(hBlocks[k].maxSpan)].push_back((int32_t) k);
+        for (int64_t k = c.block0; k < c.block1 && !ctx->stripEngine; k++) byClass[class_of_width(hBlocks[k].maxSpan)].push_back((int32_t) k);
         for (int k = 0; k < kNumClasses; k++) {
             c.bwdListOff[k] = (int64_t) lists.size();
             lists.insert(lists.end(), byClass[k].begin(), byClass[k].end());
@@ -582,6 +603,14 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         c.bwdListOff[kNumClasses] = (int64_t) lists.size();
         c.allBlocksOff = (int64_t) lists.size();
         for (int64_t k = c.block0; k < c.block1; k++) lists.push_back((int32_t) k);
+        /* strip engine: one list of regions and one of blocks, most expensive first (work is fetched dynamically) */
+        c.stripFwdOff = (int64_t) lists.size();
+        for (int64_t r = c.region0; r < c.region1; r++) lists.push_back((int32_t) r);
+        std::sort(lists.begin() + c.stripFwdOff, lists.end(), [&](int32_t x, int32_t y) { return regs[x].cells > regs[y].cells; });
+        c.stripBwdOff = (int64_t) lists.size();
+        for (int64_t k = c.block0; k < c.block1; k++) lists.push_back((int32_t) k);
+        auto blockCost = [&](int32_t k) { return (int64_t) (hBlocks[k].top - hBlocks[k].T) * hBlocks[k].maxSpan; };
+        std::sort(lists.begin() + c.stripBwdOff, lists.end(), [&](int32_t x, int32_t y) { return blockCost(x) > blockCost(y); });
     }
     if ((rc = b->lists.reserve(std::max<size_t>(lists.size(), 1) * sizeof(int32_t))) != CPB_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(b->lists.p, lists.data(), lists.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -609,8 +638,31 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         if ((rc = b->pairBlockOff.reserve((size_t) (maxChunkPairs + 2) * sizeof(int64_t))) != CPB_OK) return rc;
     }
 
+    /* strip engine: persistent grid of independent warps, boundary rings, work counters */
+    StripArgs sargs;
+    memset(&sargs, 0, sizeof(sargs));
+    int stripGrid = 1;
+    if (ctx->stripEngine) {
+        int maxRange = 1;
+        for (int64_t r = 0; r < nReg; r++) maxRange = std::max(maxRange, regs[r].maxStripRange);
+        int64_t ring = 64;
+        while (ring < maxRange + 4) ring <<= 1;
+        int occF = 1, occB = 1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occF, k_forward_strip<S, kStripWPC>, 32 * kStripWPC, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, k_backward_strip<S, kStripWPC>, 32 * kStripWPC, 0));
+        stripGrid = ctx->smCount * std::max(1, std::max(occF, occB));
+        const size_t need = (size_t) stripGrid * kStripWPC * 2 * S * ring * sizeof(double);
+        if ((rc = ctx->boundary.reserve(need)) != CPB_OK) return rc;
+        if ((rc = ctx->counters.reserve(2 * chunks.size() * sizeof(unsigned int) + 16)) != CPB_OK) return rc;
+        CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, 2 * chunks.size() * sizeof(unsigned int) + 16, st));
+        sargs.strips = b->strips.as<StripRec>();
+        sargs.boundary = ctx->boundary.as<double>();
+        sargs.bndStride = ring;
+    }
+
     std::vector<int64_t> hPairOff;
     int64_t running[3] = { 0, 0, 0 };
+    int64_t chunkIndex = -1;
 
     for (auto &c : chunks) {
         DpArgs a;
@@ -631,14 +683,25 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         a.forwardOut = mode == CPB_MODE_FORWARD ? b->forwardOut.as<double>() : nullptr;
         const int32_t *dLists = b->lists.as<int32_t>();
 
+        chunkIndex++;
         size_t ev = tic(&stx.msForward);
-        for (int k = 0; k < kNumClasses; k++) {
-            const int64_t cnt = c.fwdListOff[k + 1] - c.fwdListOff[k];
-            if (cnt == 0) continue;
-            a.list = dLists + c.fwdListOff[k];
-            const int warps = g_classWarps[k];
-            kernel_table<S>().fwd[k][warp_index(warps)]<<<(unsigned) cnt, 32 * warps, dp_smem_bytes<S>(class_wcap(k)), st>>>(a, *m);
+        if (ctx->stripEngine) {
+            const int64_t cnt = c.region1 - c.region0;
+            a.list = dLists + c.stripFwdOff;
+            sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex;
+            sargs.nItems = (int32_t) cnt;
+            const int grid = (int) std::min<int64_t>(stripGrid, (cnt + kStripWPC - 1) / kStripWPC);
+            k_forward_strip<S, kStripWPC><<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
             stx.kernelLaunches++;
+        } else {
+            for (int k = 0; k < kNumClasses; k++) {
+                const int64_t cnt = c.fwdListOff[k + 1] - c.fwdListOff[k];
+                if (cnt == 0) continue;
+                a.list = dLists + c.fwdListOff[k];
+                const int warps = g_classWarps[k];
+                kernel_table<S>().fwd[k][warp_index(warps)]<<<(unsigned) cnt, 32 * warps, dp_smem_bytes<S>(class_wcap(k)), st>>>(a, *m);
+                stx.kernelLaunches++;
+            }
         }
         toc(ev);
         if (mode == CPB_MODE_FORWARD) continue;
@@ -646,13 +709,22 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         const int64_t nb = c.block1 - c.block0;
         if (nb == 0) continue;
         ev = tic(&stx.msBackward);
-        for (int k = 0; k < kNumClasses; k++) {
-            const int64_t cnt = c.bwdListOff[k + 1] - c.bwdListOff[k];
-            if (cnt == 0) continue;
-            a.list = dLists + c.bwdListOff[k];
-            const int warps = g_classWarps[k];
-            kernel_table<S>().bwd[k][warp_index(warps)]<<<(unsigned) cnt, 32 * warps, dp_smem_bytes<S>(class_wcap(k)), st>>>(a, *m);
+        if (ctx->stripEngine) {
+            a.list = dLists + c.stripBwdOff;
+            sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex + 1;
+            sargs.nItems = (int32_t) nb;
+            const int grid = (int) std::min<int64_t>(stripGrid, (nb + kStripWPC - 1) / kStripWPC);
+            k_backward_strip<S, kStripWPC><<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
             stx.kernelLaunches++;
+        } else {
+            for (int k = 0; k < kNumClasses; k++) {
+                const int64_t cnt = c.bwdListOff[k + 1] - c.bwdListOff[k];
+                if (cnt == 0) continue;
+                a.list = dLists + c.bwdListOff[k];
+                const int warps = g_classWarps[k];
+                kernel_table<S>().bwd[k][warp_index(warps)]<<<(unsigned) cnt, 32 * warps, dp_smem_bytes<S>(class_wcap(k)), st>>>(a, *m);
+                stx.kernelLaunches++;
+            }
         }
         toc(ev);
 
@@ -837,7 +909,7 @@ extern "C" int cpb_band(cpb_context *ctx, const int64_t *anchors, int64_t nAncho
     if (ctx == nullptr || lX < 0 || lY < 0 || out3 == nullptr) return CPB_ERR_ARGUMENT;
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int64_t N = lX + lY;
-    DevBuf dRegion, dDiags, dBlocks, dAnch;
+    DevBuf dRegion, dDiags, dBlocks, dAnch, dStrips;
     int rc;
     if ((rc = dRegion.reserve(sizeof(RegionDev))) != CPB_OK || (rc = dDiags.reserve((N + 2) * sizeof(DiagRec))) != CPB_OK ||
         (rc = dBlocks.reserve(sizeof(BlockRec))) != CPB_OK || (rc = dAnch.reserve(std::max<int64_t>(nAnchors, 1) * 3 * sizeof(int32_t))) != CPB_OK)
@@ -858,7 +930,9 @@ extern "C" int cpb_band(cpb_context *ctx, const int64_t *anchors, int64_t nAncho
     ba.regions = dRegion.as<RegionDev>();
     ba.anchors = dAnch.as<int32_t>();
     ba.diags = dDiags.as<DiagRec>();
+    if ((rc = dStrips.reserve(((lX >> 5) + 1) * sizeof(StripRec))) != CPB_OK) return rc;
     ba.blocks = dBlocks.as<BlockRec>();
+    ba.strips = dStrips.as<StripRec>();
     ba.nRegions = 1;
     ba.expansion = (int32_t) expansion;
     ba.dynamic = dynamic;
@@ -875,6 +949,7 @@ extern "C" int cpb_band(cpb_context *ctx, const int64_t *anchors, int64_t nAncho
     dDiags.release();
     dBlocks.release();
     dAnch.release();
+    dStrips.release();
     for (int64_t d = 0; d <= N; d++) {
         out3[3 * d] = d;
         out3[3 * d + 1] = recs[d].xmyL;

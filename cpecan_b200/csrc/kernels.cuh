@@ -44,6 +44,7 @@ struct RegionDev {
     int64_t cellBase;      /* chunk-relative first cell (host, after planning) */
     int64_t auxBase;       /* chunk-relative first aux double (host, after planning) */
     int64_t maskBase;      /* chunk-relative first keep-mask word (host, after planning) */
+    int64_t stripBase;     /* first StripRec of the region: (lX>>5)+1 records */
     int64_t cells;         /* out: band cells */
     int64_t auxDoubles;    /* out */
     int32_t lX, lY;
@@ -54,9 +55,14 @@ struct RegionDev {
     int32_t nBlocks;       /* out */
     int32_t maxW;          /* out: widest diagonal */
     int32_t maxSpan;       /* out: window slots needed (see k_band) */
+    int32_t maxStripRange; /* out: longest diagonal range of a 32-row strip */
     int32_t err;           /* out: 0 ok, 1 invalid diagonal, 2 block table overflow */
     uint8_t raggedL, raggedR;
-    uint8_t pad_[2];
+    uint8_t pad_[6];
+};
+
+struct StripRec {
+    int32_t dFirst, dLast; /* diagonals on which any row of the 32-row strip is inside the band (dLast < dFirst: never) */
 };
 
 struct BlockRec {
@@ -833,6 +839,7 @@ struct BandArgs {
     const int32_t *anchors; /* (x,y,expansion) triples, pair coordinates */
     DiagRec *diags;
     BlockRec *blocks;
+    StripRec *strips;
     int32_t nRegions;
     int32_t expansion, dynamic;
     int32_t minDiags, traceBack;
@@ -853,6 +860,13 @@ __global__ void k_band(const BandArgs b) {
     int64_t e = b.dynamic ? 0 : b.expansion;
     int64_t coff = 0;
     int maxW = 0, maxSpan = 1, err = 0;
+    StripRec *st = b.strips + R.stripBase;
+    const int nStrips = (int) (lX >> 5) + 1;
+    for (int k = 0; k < nStrips; k++) {
+        st[k].dFirst = 0x7FFFFFFF;
+        st[k].dLast = -1;
+    }
+    int curLo = 0, curHi = -1; /* strips touched by the previous diagonal */
     int64_t bl1 = 0, br1 = 0, bl2 = 0, br2 = -1; /* bands of the two previous diagonals */
     for (int64_t xay = 0; xay <= N; xay++) {
         int64_t l = xL - yL, rr = xU - yU, v;
@@ -875,6 +889,24 @@ __global__ void k_band(const BandArgs b) {
         dg[xay] = rec;
         coff += w;
         maxW = w > maxW ? w : maxW;
+        {
+            /* row strips touched by this diagonal: rows (xay + l)/2 .. (xay + rr)/2.  Only strips entering or leaving
+             * the touched range are written, so the table costs O(changes), not O(cells / 32). */
+            int sLo = (int) (((xay + l) / 2) >> 5), sHi = (int) (((xay + rr) / 2) >> 5);
+            if (sHi >= nStrips) sHi = nStrips - 1;
+            for (int k = sLo; k <= sHi; k++) {
+                if (k < curLo || k > curHi) {
+                    if (st[k].dFirst > (int) xay) st[k].dFirst = (int) xay;
+                }
+            }
+            for (int k = curLo; k <= curHi; k++) {
+                if (k < sLo || k > sHi) {
+                    if (st[k].dLast < (int) xay - 1) st[k].dLast = (int) xay - 1;
+                }
+            }
+            curLo = sLo;
+            curHi = sHi;
+        }
         {
             /* window slots the kernels need around this diagonal: same parity as xay-2, and xay-1 vs the +-1 neighbourhood */
             int span = w;
@@ -960,6 +992,13 @@ __global__ void k_band(const BandArgs b) {
     R.nBlocks = nBlocks;
     R.maxW = maxW;
     R.maxSpan = maxSpan;
+    for (int k = curLo; k <= curHi; k++) st[k].dLast = (int) N; /* strips still touched by the last diagonal */
+    int msr = 1;
+    for (int k = 0; k < nStrips; k++) {
+        const int rg = st[k].dLast - st[k].dFirst + 1;
+        msr = rg > msr ? rg : msr;
+    }
+    R.maxStripRange = msr;
     R.err = err;
     b.regions[r] = R;
 }

@@ -154,12 +154,14 @@ def test_wide_bands_every_width_class(ctx, oracle):
     check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.threeStateAsymmetric), p, cases[:4], "wide sm3")
 
 
-def test_band_too_wide_fails_loudly(ctx):
+def test_very_wide_band_has_no_limit(ctx, oracle):
+    """a 2.6k x 2.6k matrix without anchors (band 2601 cells wide): the warp-per-region kernels have no width classes"""
+    rng = np.random.default_rng(6)
     p = cp.pairwiseAlignmentBandingParameters_construct()
     p.splitMatrixBiggerThanThis = 1 << 40
-    s = "ACGT" * 700
-    with pytest.raises(cp.CpbError, match="wide"):
-        cp.getAlignedPairsUsingAnchors(cp.stateMachine5_construct(), s, s, [], p, ctx=ctx)
+    sX = synth.random_sequence(rng, 2600, acgt_only=True)
+    sY = sX[:1300] + synth.random_sequence(rng, 7, acgt_only=True) + sX[1300:]
+    check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.fiveState), p, [(sX, sY, np.zeros((0, 3), dtype=np.int64), False, False)], "very wide")
 
 
 def test_edge_cases(ctx, oracle):
