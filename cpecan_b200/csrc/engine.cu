@@ -515,6 +515,11 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             finish_events();
             return CPB_ERR_BAND_TOO_WIDE;
         }
+        if (regs[r].cells >= ((int64_t) 1 << 31)) {
+            cpb_set_error("pair %d: a single region has %lld band cells (limit 2^31)", regs[r].pair, (long long) regs[r].cells);
+            finish_events();
+            return CPB_ERR_ARGUMENT;
+        }
         totalBlocks += regs[r].nBlocks;
         stx.cells += regs[r].cells;
         stx.maxWidth = std::max(stx.maxWidth, regs[r].maxW);
@@ -639,25 +644,33 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     }
 
     /* strip engine: persistent grid of independent warps, boundary rings, work counters */
+    typedef void (*StripKernel)(const DpArgs, const CpbModel, const StripArgs);
+    StripKernel kFwdStrip = nullptr, kBwdStrip = nullptr;
+    switch (nPlanes) {
+    case 0: kFwdStrip = k_forward_strip<S, 0, kStripWPC>; kBwdStrip = k_backward_strip<S, 0, kStripWPC>; break;
+    case 1: kFwdStrip = k_forward_strip<S, 1, kStripWPC>; kBwdStrip = k_backward_strip<S, 1, kStripWPC>; break;
+    case 3: kFwdStrip = k_forward_strip<S, 3, kStripWPC>; kBwdStrip = k_backward_strip<S, 3, kStripWPC>; break;
+    default: kFwdStrip = k_forward_strip<S, S, kStripWPC>; kBwdStrip = k_backward_strip<S, S, kStripWPC>; break;
+    }
     StripArgs sargs;
     memset(&sargs, 0, sizeof(sargs));
     int stripGrid = 1;
     if (ctx->stripEngine) {
         int maxRange = 1;
         for (int64_t r = 0; r < nReg; r++) maxRange = std::max(maxRange, regs[r].maxStripRange);
-        int64_t ring = 64;
+        int ring = 64;
         while (ring < maxRange + 4) ring <<= 1;
         int occF = 1, occB = 1;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occF, k_forward_strip<S, kStripWPC>, 32 * kStripWPC, 0));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, k_backward_strip<S, kStripWPC>, 32 * kStripWPC, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occF, kFwdStrip, 32 * kStripWPC, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, kBwdStrip, 32 * kStripWPC, 0));
         stripGrid = ctx->smCount * std::max(1, std::max(occF, occB));
-        const size_t need = (size_t) stripGrid * kStripWPC * 2 * S * ring * sizeof(double);
+        const size_t need = (size_t) stripGrid * kStripWPC * 2 * ring * BND_REC * sizeof(double);
         if ((rc = ctx->boundary.reserve(need)) != CPB_OK) return rc;
         if ((rc = ctx->counters.reserve(2 * chunks.size() * sizeof(unsigned int) + 16)) != CPB_OK) return rc;
         CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, 2 * chunks.size() * sizeof(unsigned int) + 16, st));
         sargs.strips = b->strips.as<StripRec>();
         sargs.boundary = ctx->boundary.as<double>();
-        sargs.bndStride = ring;
+        sargs.ringSize = ring;
     }
 
     std::vector<int64_t> hPairOff;
@@ -691,7 +704,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex;
             sargs.nItems = (int32_t) cnt;
             const int grid = (int) std::min<int64_t>(stripGrid, (cnt + kStripWPC - 1) / kStripWPC);
-            k_forward_strip<S, kStripWPC><<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
+            kFwdStrip<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
             stx.kernelLaunches++;
         } else {
             for (int k = 0; k < kNumClasses; k++) {
@@ -714,7 +727,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex + 1;
             sargs.nItems = (int32_t) nb;
             const int grid = (int) std::min<int64_t>(stripGrid, (nb + kStripWPC - 1) / kStripWPC);
-            k_backward_strip<S, kStripWPC><<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
+            kBwdStrip<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
             stx.kernelLaunches++;
         } else {
             for (int k = 0; k < kNumClasses; k++) {
