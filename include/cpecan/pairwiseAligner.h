@@ -1,0 +1,147 @@
+/*
+ * cpecan/pairwiseAligner.h -- cPecan's pairwise pair-HMM API (inc/pairwiseAligner.h of the reference) served by
+ * libcpecan.so: plain C host code over the batched CUDA engine of include/cpecan_b200.h.
+ *
+ * Every function below keeps the reference's name, argument order, ownership rules and error convention
+ * (st_errAbort on unusable input; a missing or failing CUDA device is reported the same way -- there is no host
+ * implementation of the DP to fall back to).  Citations are to the reference tree.
+ *
+ * New in this library (the reference handles one pair per call): the *Batch entry points at the end, which run
+ * many independent pairs in one device pass and are what cPecanRealign's per-cigar loop (cPecanRealign.c:509-605)
+ * and multipleAligner's all-pairs loop (impl/multipleAligner.c:668-681) should call.
+ */
+#ifndef CPECAN_PAIRWISEALIGNER_H_
+#define CPECAN_PAIRWISEALIGNER_H_
+
+#include "cpecan/sonLibLite.h"
+#include "cpecan/stateMachine.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+extern const char *PAIRWISE_ALIGNMENT_EXCEPTION_ID; /* inc/pairwiseAligner.h:23 */
+
+#define PAIR_ALIGNMENT_PROB_1 10000000 /* inc/pairwiseAligner.h:26 */
+#define LOG_ZERO (-INFINITY)           /* inc/pairwiseAligner.h:165 */
+#define LOG_ONE 0.0
+
+/* inc/pairwiseAligner.h:28-41, same fields in the same order */
+typedef struct _pairwiseAlignmentBandingParameters {
+    double threshold;
+    int64_t minDiagsBetweenTraceBack;
+    int64_t traceBackDiagonals;
+    int64_t diagonalExpansion;
+    int64_t constraintDiagonalTrim;
+    int64_t anchorMatrixBiggerThanThis;
+    int64_t repeatMaskMatrixBiggerThanThis;
+    int64_t splitMatrixBiggerThanThis;
+    bool alignAmbiguityCharacters;
+    float gapGamma;
+    bool dynamicAnchorExpansion;
+} PairwiseAlignmentParameters;
+
+PairwiseAlignmentParameters *pairwiseAlignmentBandingParameters_construct(void);      /* :43, defaults of impl/pairwiseAligner.c:1334-1348 */
+void pairwiseAlignmentBandingParameters_destruct(PairwiseAlignmentParameters *p);     /* :45 */
+PairwiseAlignmentParameters *pairwiseAlignmentParameters_jsonParse(char *buf, size_t r); /* :51 */
+
+/* :56 -- log P(x, y) by the banded forward algorithm */
+double computeForwardProbability(char *seqX, char *seqY, stList *anchorPairs, PairwiseAlignmentParameters *p, StateMachine *sM,
+                                 bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd);
+
+/*
+ * :62 / :69 -- as the ...UsingAnchors forms with anchors found by the registered anchor provider.  The reference
+ * shells out to LASTZ here (impl/pairwiseAligner.c:1005-1080, only for matrices bigger than
+ * p->anchorMatrixBiggerThanThis); that subprocess is outside this library.  Without a
+ * provider, matrices up to anchorMatrixBiggerThanThis are aligned unanchored exactly as the reference does, and
+ * larger ones abort asking for anchors.
+ */
+stList *getAlignedPairs(StateMachine *sM, const char *string1, const char *string2, PairwiseAlignmentParameters *p,
+                        bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd);
+void getAlignedPairsWithIndels(StateMachine *sM, const char *string1, const char *string2, PairwiseAlignmentParameters *p,
+                               stList **alignedPairs, stList **gapXPairs, stList **gapYPairs, bool alignmentHasRaggedLeftEnd,
+                               bool alignmentHasRaggedRightEnd);
+
+/* :75 -- list of stIntTuple (pInt, x, y), 0-based, unique (x, y), caller frees with stList_destruct */
+stList *getAlignedPairsUsingAnchors(StateMachine *sM, const char *sX, const char *sY, stList *anchorPairs, PairwiseAlignmentParameters *p,
+                                    bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd);
+/* :77 */
+void getAlignedPairsWithIndelsUsingAnchors(StateMachine *sM, const char *sX, const char *sY, stList *anchorPairs,
+                                           PairwiseAlignmentParameters *p, stList **alignedPairs, stList **gapXPairs, stList **gapYPairs,
+                                           bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd);
+/* :105 / :108 -- expected transition / emission counts are added to hmmExpectations */
+void getExpectationsUsingAnchors(StateMachine *sM, Hmm *hmmExpectations, const char *sX, const char *sY, stList *anchorPairs,
+                                 PairwiseAlignmentParameters *p, bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd);
+void getExpectations(StateMachine *sM, Hmm *hmmExpectations, const char *sX, const char *sY, PairwiseAlignmentParameters *p,
+                     bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd);
+
+/* ---- helpers the reference exposes for its tests ---- */
+
+/* :116-138 */
+typedef struct _diagonal {
+    int64_t xay;  /* x + y */
+    int64_t xmyL; /* smallest x - y */
+    int64_t xmyR; /* largest x - y */
+} Diagonal;
+
+Diagonal diagonal_construct(int64_t xay, int64_t xmyL, int64_t xmyR); /* aborts on an invalid diagonal (reference: stThrowNew) */
+int64_t diagonal_getXay(Diagonal diagonal);
+int64_t diagonal_getMinXmy(Diagonal diagonal);
+int64_t diagonal_getMaxXmy(Diagonal diagonal);
+int64_t diagonal_getWidth(Diagonal diagonal);
+int64_t diagonal_getXCoordinate(int64_t xay, int64_t xmy);
+int64_t diagonal_getYCoordinate(int64_t xay, int64_t xmy);
+int64_t diagonal_equals(Diagonal diagonal1, Diagonal diagonal2);
+
+/* :140-161 -- the band comes from the device-side band builder (kernel k_band) */
+typedef struct _band Band;
+typedef struct _bandIterator BandIterator;
+Band *band_construct(stList *anchorPairs, int64_t lX, int64_t lY, int64_t expansion);
+Band *band_constructDynamic(stList *anchorPairs, int64_t lX, int64_t lY);
+void band_destruct(Band *band);
+BandIterator *bandIterator_construct(Band *band);
+void bandIterator_destruct(BandIterator *bandIterator);
+BandIterator *bandIterator_clone(BandIterator *bandIterator);
+Diagonal bandIterator_getNext(BandIterator *bandIterator);
+Diagonal bandIterator_getPrevious(BandIterator *bandIterator);
+
+/* :171-175 */
+Symbol symbol_convertCharToSymbol(char i);
+char symbol_convertSymbolToChar(Symbol i);
+Symbol *symbol_convertStringToSymbols(const char *s, int64_t sL);
+
+/* :261 -- list of stIntTuple (x1, y1, x2, y2) */
+stList *getSplitPoints(stList *anchorPairs, int64_t lX, int64_t lY, int64_t maxMatrixSize, bool alignmentHasRaggedLeftEnd,
+                       bool alignmentHasRaggedRightEnd);
+
+/* ---- batched entry points (not in the reference) ---- */
+
+/* Anchor provider used by getAlignedPairs / getAlignedPairsWithIndels / getExpectations for matrices bigger than
+ * p->anchorMatrixBiggerThanThis: returns a new stList of stIntTuple (x, y, expansion), strictly increasing in x and y. */
+typedef stList *(*CpecanAnchorProvider)(const char *sX, const char *sY, int64_t lX, int64_t lY, PairwiseAlignmentParameters *p, void *extra);
+void cpecan_setAnchorProvider(CpecanAnchorProvider provider, void *extra);
+
+/* CUDA device used by this process (default: $CPECAN_DEVICE or 0).  Must be called before the first alignment. */
+void cpecan_setDevice(int device);
+/* releases the device context (optional; also safe to never call) */
+void cpecan_shutdown(void);
+
+/* n independent problems in one device pass.  anchorPairs[i] may be NULL (no anchors); raggedLeft / raggedRight may
+ * be NULL (all false).  Returns a new array of n lists (free each with stList_destruct, the array with free). */
+stList **getAlignedPairsUsingAnchorsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY,
+                                          stList *const *anchorPairs, PairwiseAlignmentParameters *p, const bool *raggedLeft,
+                                          const bool *raggedRight);
+void getAlignedPairsWithIndelsUsingAnchorsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY,
+                                                stList *const *anchorPairs, PairwiseAlignmentParameters *p, stList ***alignedPairs,
+                                                stList ***gapXPairs, stList ***gapYPairs, const bool *raggedLeft, const bool *raggedRight);
+/* sums the expectations of all n problems into hmmExpectations (+=), as n calls of getExpectationsUsingAnchors would */
+void getExpectationsUsingAnchorsBatch(StateMachine *sM, Hmm *hmmExpectations, int64_t n, const char *const *sX, const char *const *sY,
+                                      stList *const *anchorPairs, PairwiseAlignmentParameters *p, const bool *raggedLeft,
+                                      const bool *raggedRight);
+void computeForwardProbabilityBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY, stList *const *anchorPairs,
+                                    PairwiseAlignmentParameters *p, const bool *raggedLeft, const bool *raggedRight, double *logProbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPECAN_PAIRWISEALIGNER_H_ */

@@ -1,0 +1,157 @@
+"""libcpecan.so -- the reference-named C API (include/cpecan/*.h) in plain C over the engine's C-ABI.
+
+CPU part: the library exports every function the headers declare, and the host-only pieces (containers, Hmm text /
+JSON formats, parameter JSON, split points, diagonals, symbols) pass tests/c/test_cpecan_api.c's `host` suite, which
+restates the reference's own unit tests for them.  GPU part: the `gpu` suite (the reference's known-answer tests) and a
+differential run of the C entry points -- batched and one-pair -- against the oracle.
+"""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+
+ROOT = helpers.ROOT
+LIB_DIR = os.path.join(ROOT, "cpecan_b200", "lib")
+HOST_SO = os.path.join(LIB_DIR, "libcpecan.so")
+BUILD = os.path.join(ROOT, "tests", "c", "_build")
+EXE = os.path.join(BUILD, "test_cpecan_api")
+
+
+def build_exe():
+    src = os.path.join(ROOT, "tests", "c", "test_cpecan_api.c")
+    if not os.path.exists(HOST_SO):
+        subprocess.check_call(["make", "-s", "-f", os.path.join(ROOT, "cpecan_b200", "csrc", "Makefile")])
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(HOST_SO)):
+        os.makedirs(BUILD, exist_ok=True)
+        subprocess.check_call(["gcc", "-std=c99", "-O1", "-D_POSIX_C_SOURCE=200809L", "-I" + os.path.join(ROOT, "include"), src, "-o", EXE,
+                               "-L" + LIB_DIR, "-lcpecan", "-lcpecan_b200", "-Wl,-rpath," + LIB_DIR, "-lm"])
+    return EXE
+
+
+def declared_functions(header):
+    text = open(header).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"typedef[^;]*\(\*\w+\)\([^;]*;", "", text)       # function-pointer typedefs
+    text = re.sub(r"struct\s+\w+\s*\{.*?\};", "", text, flags=re.S)  # struct bodies (callback members)
+    return sorted(set(re.findall(r"\b(\w+)\s*\([^;{}]*\)\s*;", text)) - {"defined"})
+
+
+def test_host_library_exports_every_declared_symbol():
+    build_exe()
+    out = subprocess.check_output(["nm", "-D", "--defined-only", HOST_SO], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    for h in ("sonLibLite.h", "stateMachine.h", "pairwiseAligner.h"):
+        names = declared_functions(os.path.join(ROOT, "include", "cpecan", h))
+        assert len(names) > 10, h
+        missing = [n for n in names if n not in exported]
+        assert not missing, "%s declares functions libcpecan.so does not export: %s" % (h, missing)
+
+
+def test_host_library_has_no_dp_of_its_own():
+    """The C host layer marshals; the recurrence lives only in the CUDA engine (no logAdd / cell update on the host)."""
+    host_dir = os.path.join(ROOT, "cpecan_b200", "csrc", "host")
+    for fn in os.listdir(host_dir):
+        text = open(os.path.join(host_dir, fn)).read()
+        assert "oracle" not in text.lower().replace("oracle/", "") or fn.endswith(".md")
+        assert not re.search(r"\blogAdd\s*\(|\bexp\s*\(|\blog\s*\(", text), fn
+
+
+def test_host_suite_without_a_gpu():
+    out = subprocess.run([build_exe(), "host"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert re.search(r"\d+ checks, 0 failures", out.stdout)
+
+
+def test_alignment_entry_points_abort_loudly_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    out = subprocess.run([build_exe(), "gpu"], capture_output=True, text=True)
+    assert out.returncode != 0
+    assert "no CPU implementation" in out.stderr or "CUDA" in out.stderr
+
+
+@pytest.mark.gpu
+def test_reference_known_answer_tests_through_the_c_api():
+    out = subprocess.run([build_exe(), "gpu"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert re.search(r"\d+ checks, 0 failures", out.stdout)
+
+
+def _parse_list(fields):
+    n = int(fields[0])
+    return np.asarray([int(v) for v in fields[1:1 + 3 * n]], dtype=np.int64).reshape(-1, 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("type_", [0, 1, 2, 3])
+def test_c_api_matches_the_oracle(tmp_path, oracle, type_):
+    import cpecan_b200 as cp
+    from cpecan_b200 import synth
+
+    rng = np.random.default_rng(100 + type_)
+    S = 5 if type_ < 2 else 3
+    spec = helpers.ModelSpec.random(rng, type_) if type_ % 2 else helpers.ModelSpec(type_)
+    hmm_file = "-"
+    if spec.transitions is not None:
+        hmm_file = str(tmp_path / "model.hmm")
+        with open(hmm_file, "w") as f:  # the reference's text format with full precision (%f would round the model)
+            f.write("%d\t%s\t0.0\n" % (type_, "\t".join(repr(float(v)) for v in spec.transitions.ravel())))
+            f.write("\t".join(repr(float(v)) for v in spec.emissions.ravel()) + "\t\n")
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    p.minDiagsBetweenTraceBack = 60
+    p.traceBackDiagonals = 10
+    p.diagonalExpansion = 6
+    p.splitMatrixBiggerThanThis = 400
+    p.threshold = 0.05
+    pj = ('{"threshold": %r, "minDiagsBetweenTraceBack": %d, "traceBackDiagonals": %d, "diagonalExpansion": %d, '
+          '"splitMatrixBiggerThanThis": %d}' % (p.threshold, p.minDiagsBetweenTraceBack, p.traceBackDiagonals, p.diagonalExpansion,
+                                                p.splitMatrixBiggerThanThis))
+    packed = synth.evolved_pairs(6, 180, seed=41 + type_, trim=2, expansion=int(p.diagonalExpansion))
+    cases = []
+    for i in range(6):
+        sx, sy, a = synth.unpack(packed, i)
+        cases.append((sx, sy, np.asarray(a, dtype=np.int64).reshape(-1, 3), bool(i & 1), bool(i & 2)))
+    cases.append(("ACGTN", "", np.zeros((0, 3), dtype=np.int64), False, False))  # an empty sequence
+    cases.append(("acgtnACGT", "ACGTTACGT", np.zeros((0, 3), dtype=np.int64), True, True))
+    inp, outp = tmp_path / "in.txt", tmp_path / "out.txt"
+    with open(inp, "w") as f:
+        f.write("%d %s %s\n%d\n" % (type_, hmm_file, pj, len(cases)))
+        for sx, sy, a, rl, rr in cases:
+            sx = sx if isinstance(sx, str) else bytes(sx).decode()
+            sy = sy if isinstance(sy, str) else bytes(sy).decode()
+            f.write("%d %d %d\n%s\n%s\n%s\n" % (rl, rr, a.shape[0], sx or "-", sy or "-", " ".join(str(int(v)) for v in a.ravel())))
+    out = subprocess.run([build_exe(), "run", str(inp), str(outp)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = open(outp).read().splitlines()
+    om, op = spec.orc(), helpers.orc_params_from(p)
+    total = np.zeros(cp.hmm_len(S))
+    k = 0
+    for i, (sx, sy, a, rl, rr) in enumerate(cases):
+        assert lines[k] == "problem %d" % i
+        got = {}
+        for j in range(1, 9):
+            f = lines[k + j].split()
+            got[f[0]] = f[1:]
+        k += 9
+        want = oracle.aligned_pairs_with_indels(om, op, sx, sy, a, rl, rr)
+        for key, w in zip(("match", "gapX", "gapY"), want):
+            g, w = helpers.sort_triples(_parse_list(got[key])), helpers.sort_triples(w)
+            assert g.shape == w.shape and np.array_equal(g[:, 1:], w[:, 1:]), (i, key)
+            assert g.shape[0] == 0 or np.abs(g[:, 0] - w[:, 0]).max() <= 1
+        for key in ("only", "one"):
+            g = helpers.sort_triples(_parse_list(got[key]))
+            assert np.array_equal(g[:, 1:], helpers.sort_triples(want[0])[:, 1:]), (i, key)
+        fw = oracle.forward_prob(om, op, sx, sy, a, rl, rr)
+        assert float.fromhex(got["forward"][0]) == fw and float.fromhex(got["forward1"][0]) == fw
+        e = oracle.expectations(om, op, sx, sy, a, rl, rr)
+        np.testing.assert_allclose(np.array([float.fromhex(v) for v in got["expectations"]]), e, rtol=1e-9, atol=1e-12)
+        total += e
+    f = lines[k].split()
+    assert f[0] == "total"
+    np.testing.assert_allclose(np.array([float.fromhex(v) for v in f[1:]]), total, rtol=1e-9, atol=1e-12)
