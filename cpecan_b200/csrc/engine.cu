@@ -72,62 +72,6 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-/* ------------------------------------------------------------------------------------------------
- * width classes: window capacity (cells per diagonal) -> warps per CTA
- * ---------------------------------------------------------------------------------------------- */
-static const int kNumClasses = 7; /* 32, 64, 128, 256, 512, 1024, 2048 */
-static int g_classWarps[kNumClasses] = { 1, 1, 2, 4, 8, 8, 8 };
-
-static int class_of_width(int w) {
-    int c = 0, cap = 32;
-    while (cap < w && c < kNumClasses) {
-        cap <<= 1;
-        c++;
-    }
-    return c; /* == kNumClasses when too wide */
-}
-static int class_wcap(int c) { return 32 << c; }
-
-template <int S> static size_t dp_smem_bytes(int wcap) {
-    return ((sizeof(Tables<S>) + 15) & ~size_t(15)) + size_t(2) * S * wcap * sizeof(double);
-}
-
-typedef void (*DpKernel)(const DpArgs, const CpbModel);
-
-static const int kWarpChoices[5] = { 1, 2, 4, 8, 16 };
-static int warp_index(int warps) {
-    for (int i = 0; i < 5; i++) {
-        if (kWarpChoices[i] == warps) return i;
-    }
-    return -1;
-}
-
-/* [class][warp choice] tables of the template instantiations */
-template <int S> struct KernelTable {
-    DpKernel fwd[kNumClasses][5];
-    DpKernel bwd[kNumClasses][5];
-    KernelTable() {
-#define CPB_ROW(C, WCAP)                                                                         \
-        fwd[C][0] = k_forward<S, WCAP, 1>;  bwd[C][0] = k_backward<S, WCAP, 1>;                     \
-        fwd[C][1] = k_forward<S, WCAP, 2>;  bwd[C][1] = k_backward<S, WCAP, 2>;                     \
-        fwd[C][2] = k_forward<S, WCAP, 4>;  bwd[C][2] = k_backward<S, WCAP, 4>;                     \
-        fwd[C][3] = k_forward<S, WCAP, 8>;  bwd[C][3] = k_backward<S, WCAP, 8>;                     \
-        fwd[C][4] = k_forward<S, WCAP, 16>; bwd[C][4] = k_backward<S, WCAP, 16>;
-        CPB_ROW(0, 32)
-        CPB_ROW(1, 64)
-        CPB_ROW(2, 128)
-        CPB_ROW(3, 256)
-        CPB_ROW(4, 512)
-        CPB_ROW(5, 1024)
-        CPB_ROW(6, 2048)
-#undef CPB_ROW
-    }
-};
-template <int S> static const KernelTable<S> &kernel_table() {
-    static const KernelTable<S> t;
-    return t;
-}
-
 /* ------------------------------------------------------------------------------------------------ */
 struct cpb_context {
     int device = 0;
@@ -135,23 +79,15 @@ struct cpb_context {
     bool ownStream = false;
     size_t scratchBudget = 0;
     DevBuf scratch;
-    DevBuf boundary, counters; /* strip engine: per-warp-slot boundary rings, work-fetch counters */
+    DevBuf boundary, counters, negRecord; /* strip engine: per-warp-slot boundary rings, work-fetch counters, one LOG_ZERO ring record */
     int smCount = 148;
-    int stripEngine = 1;       /* 1: barrier-free warp-per-region kernels (default); 0: CTA-per-region kernels (CPB_ENGINE=cta) */
 };
 
 static const int kStripWPC = 4; /* warps per CTA of the strip kernels */
+static const int64_t kSymPad = 64; /* bytes of 'n' before and after the symbol arrays */
 
 static int configure_kernels() {
     const int maxSmem = 227 * 1024;
-    for (int c = 0; c < kNumClasses; c++) {
-        for (int w = 0; w < 5; w++) {
-            CUDA_TRY(cudaFuncSetAttribute((const void *) kernel_table<5>().fwd[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-            CUDA_TRY(cudaFuncSetAttribute((const void *) kernel_table<5>().bwd[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-            CUDA_TRY(cudaFuncSetAttribute((const void *) kernel_table<3>().fwd[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-            CUDA_TRY(cudaFuncSetAttribute((const void *) kernel_table<3>().bwd[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        }
-    }
     CUDA_TRY(cudaFuncSetAttribute((const void *) k_expect<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
     CUDA_TRY(cudaFuncSetAttribute((const void *) k_expect<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
     return CPB_OK;
@@ -185,22 +121,19 @@ extern "C" int cpb_context_create(int device, void *stream, cpb_context **out) {
         }
         ctx->ownStream = true;
     }
-    const char *w = getenv("CPB_CLASS_WARPS"); /* tuning knob: warps per CTA for the 7 width classes, e.g. "1,1,1,2,4,8,8" */
-    if (w != nullptr) {
-        int v[kNumClasses];
-        if (sscanf(w, "%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]) == kNumClasses) {
-            for (int i = 0; i < kNumClasses; i++) {
-                if (warp_index(v[i]) >= 0) g_classWarps[i] = v[i];
-            }
-        }
-    }
     {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->smCount = prop.multiProcessorCount;
-        const char *eng = getenv("CPB_ENGINE");
-        if (eng != nullptr && strcmp(eng, "cta") == 0) ctx->stripEngine = 0;
     }
     int rc = configure_kernels();
+    if (rc == CPB_OK && (rc = ctx->negRecord.reserve(BND_REC * sizeof(double))) == CPB_OK) {
+        double neg[BND_REC];
+        for (int i = 0; i < BND_REC; i++) neg[i] = -INFINITY;
+        if (cudaMemcpy(ctx->negRecord.p, neg, sizeof(neg), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cpb_set_error("cudaMemcpy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = CPB_ERR_CUDA;
+        }
+    }
     if (rc != CPB_OK) {
         if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -215,6 +148,7 @@ extern "C" void cpb_context_destroy(cpb_context *ctx) {
     cudaSetDevice(ctx->device);
     ctx->scratch.release();
     ctx->boundary.release();
+    ctx->negRecord.release();
     ctx->counters.release();
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -230,8 +164,6 @@ struct Chunk {
     int64_t block0, block1;   /* positions in the compact block order */
     int64_t cells, aux, maskWords, decades;
     int64_t stride;
-    int64_t fwdListOff[kNumClasses + 1]; /* offsets into the forward list array */
-    int64_t bwdListOff[kNumClasses + 1];
     int64_t allBlocksOff;                /* offset of the chunk's in-order block list */
     int64_t stripFwdOff, stripBwdOff;    /* strip engine: regions / blocks sorted by cost */
     int64_t pair0, pair1;                /* pairs touched: [pair0, pair1] inclusive */
@@ -281,19 +213,22 @@ extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *se
 
     const int64_t nx = xOff[nPairs], ny = yOff[nPairs];
     int rc = CPB_OK;
-    if ((rc = b->symX.reserve(std::max<int64_t>(nx, 1))) != CPB_OK || (rc = b->symY.reserve(std::max<int64_t>(ny, 1))) != CPB_OK ||
+    /* the strip kernels index symbols up to 32 positions outside a region without bounds tests: pad both ends with 'n' */
+    if ((rc = b->symX.reserve(nx + 2 * kSymPad)) != CPB_OK || (rc = b->symY.reserve(ny + 2 * kSymPad)) != CPB_OK ||
         (rc = b->dAnchors.reserve(std::max<int64_t>(nA, 1) * 3 * sizeof(int32_t))) != CPB_OK) {
         cpb_batch_destroy(b);
         return rc;
     }
     cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMemsetAsync(b->symX.p, 4, nx + 2 * kSymPad, st));
+    CUDA_TRY(cudaMemsetAsync(b->symY.p, 4, ny + 2 * kSymPad, st));
     if (nx > 0) {
-        CUDA_TRY(cudaMemcpyAsync(b->symX.p, seqX, nx, cudaMemcpyHostToDevice, st));
-        k_encode<<<(unsigned) ((nx + 255) / 256), 256, 0, st>>>(b->symX.as<uint8_t>(), nx);
+        CUDA_TRY(cudaMemcpyAsync(b->symX.as<uint8_t>() + kSymPad, seqX, nx, cudaMemcpyHostToDevice, st));
+        k_encode<<<(unsigned) ((nx + 255) / 256), 256, 0, st>>>(b->symX.as<uint8_t>() + kSymPad, nx);
     }
     if (ny > 0) {
-        CUDA_TRY(cudaMemcpyAsync(b->symY.p, seqY, ny, cudaMemcpyHostToDevice, st));
-        k_encode<<<(unsigned) ((ny + 255) / 256), 256, 0, st>>>(b->symY.as<uint8_t>(), ny);
+        CUDA_TRY(cudaMemcpyAsync(b->symY.as<uint8_t>() + kSymPad, seqY, ny, cudaMemcpyHostToDevice, st));
+        k_encode<<<(unsigned) ((ny + 255) / 256), 256, 0, st>>>(b->symY.as<uint8_t>() + kSymPad, ny);
     }
     if (nA > 0) {
         std::vector<int32_t> a32(3 * nA);
@@ -509,12 +444,6 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             finish_events();
             return CPB_ERR_BAND;
         }
-        if (!ctx->stripEngine && class_of_width(regs[r].maxSpan) >= kNumClasses) {
-            cpb_set_error("pair %d: band is %d cells wide; the widest kernel configuration holds %d", regs[r].pair, regs[r].maxSpan,
-                          class_wcap(kNumClasses - 1));
-            finish_events();
-            return CPB_ERR_BAND_TOO_WIDE;
-        }
         if (regs[r].cells >= ((int64_t) 1 << 31)) {
             cpb_set_error("pair %d: a single region has %lld band cells (limit 2^31)", regs[r].pair, (long long) regs[r].cells);
             finish_events();
@@ -592,20 +521,6 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     /* launch lists: forward regions per class, backward blocks per class, all blocks in order */
     std::vector<int32_t> lists;
     for (auto &c : chunks) {
-        std::vector<std::vector<int32_t>> byClass(kNumClasses);
-        for (int64_t r = c.region0; r < c.region1 && !ctx->stripEngine; r++) byClass[class_of_width(regs[r].maxSpan)].push_back((int32_t) r);
-        for (int k = 0; k < kNumClasses; k++) {
-            c.fwdListOff[k] = (int64_t) lists.size();
-            lists.insert(lists.end(), byClass[k].begin(), byClass[k].end());
-        }
-        c.fwdListOff[kNumClasses] = (int64_t) lists.size();
-        for (auto &v : byClass) v.clear();
-        for (int64_t k = c.block0; k < c.block1 && !ctx->stripEngine; k++) byClass[class_of_width(hBlocks[k].maxSpan)].push_back((int32_t) k);
-        for (int k = 0; k < kNumClasses; k++) {
-            c.bwdListOff[k] = (int64_t) lists.size();
-            lists.insert(lists.end(), byClass[k].begin(), byClass[k].end());
-        }
-        c.bwdListOff[kNumClasses] = (int64_t) lists.size();
         c.allBlocksOff = (int64_t) lists.size();
         for (int64_t k = c.block0; k < c.block1; k++) lists.push_back((int32_t) k);
         /* strip engine: one list of regions and one of blocks, most expensive first (work is fetched dynamically) */
@@ -646,16 +561,16 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     /* strip engine: persistent grid of independent warps, boundary rings, work counters */
     typedef void (*StripKernel)(const DpArgs, const CpbModel, const StripArgs);
     StripKernel kFwdStrip = nullptr, kBwdStrip = nullptr;
-    switch (nPlanes) {
-    case 0: kFwdStrip = k_forward_strip<S, 0, kStripWPC>; kBwdStrip = k_backward_strip<S, 0, kStripWPC>; break;
-    case 1: kFwdStrip = k_forward_strip<S, 1, kStripWPC>; kBwdStrip = k_backward_strip<S, 1, kStripWPC>; break;
-    case 3: kFwdStrip = k_forward_strip<S, 3, kStripWPC>; kBwdStrip = k_backward_strip<S, 3, kStripWPC>; break;
-    default: kFwdStrip = k_forward_strip<S, S, kStripWPC>; kBwdStrip = k_backward_strip<S, S, kStripWPC>; break;
+    switch (mode) {
+    case CPB_MODE_FORWARD: kFwdStrip = k_forward_strip<S, 0, kStripWPC>; kBwdStrip = k_backward_strip<S, 0, true, kStripWPC>; break;
+    case CPB_MODE_ALIGNED_PAIRS: kFwdStrip = k_forward_strip<S, 1, kStripWPC>; kBwdStrip = k_backward_strip<S, 1, true, kStripWPC>; break;
+    case CPB_MODE_ALIGNED_PAIRS_INDELS: kFwdStrip = k_forward_strip<S, 3, kStripWPC>; kBwdStrip = k_backward_strip<S, 3, true, kStripWPC>; break;
+    default: kFwdStrip = k_forward_strip<S, S, kStripWPC>; kBwdStrip = k_backward_strip<S, S, false, kStripWPC>; break;
     }
     StripArgs sargs;
     memset(&sargs, 0, sizeof(sargs));
     int stripGrid = 1;
-    if (ctx->stripEngine) {
+    {
         int maxRange = 1;
         for (int64_t r = 0; r < nReg; r++) maxRange = std::max(maxRange, regs[r].maxStripRange);
         int ring = 64;
@@ -670,6 +585,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, 2 * chunks.size() * sizeof(unsigned int) + 16, st));
         sargs.strips = b->strips.as<StripRec>();
         sargs.boundary = ctx->boundary.as<double>();
+        sargs.negRecord = ctx->negRecord.as<double>();
         sargs.ringSize = ring;
     }
 
@@ -683,8 +599,8 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         a.regions = b->regions.as<RegionDev>();
         a.blocks = b->blocks.as<BlockRec>();
         a.diags = b->diags.as<DiagRec>();
-        a.symX = b->symX.as<uint8_t>();
-        a.symY = b->symY.as<uint8_t>();
+        a.symX = b->symX.as<uint8_t>() + kSymPad;
+        a.symY = b->symY.as<uint8_t>() + kSymPad;
         double *scr = ctx->scratch.as<double>();
         a.planesF = scr;
         a.planesB = scr + (int64_t) nPlanes * c.stride;
@@ -698,7 +614,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
 
         chunkIndex++;
         size_t ev = tic(&stx.msForward);
-        if (ctx->stripEngine) {
+        {
             const int64_t cnt = c.region1 - c.region0;
             a.list = dLists + c.stripFwdOff;
             sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex;
@@ -706,15 +622,6 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             const int grid = (int) std::min<int64_t>(stripGrid, (cnt + kStripWPC - 1) / kStripWPC);
             kFwdStrip<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
             stx.kernelLaunches++;
-        } else {
-            for (int k = 0; k < kNumClasses; k++) {
-                const int64_t cnt = c.fwdListOff[k + 1] - c.fwdListOff[k];
-                if (cnt == 0) continue;
-                a.list = dLists + c.fwdListOff[k];
-                const int warps = g_classWarps[k];
-                kernel_table<S>().fwd[k][warp_index(warps)]<<<(unsigned) cnt, 32 * warps, dp_smem_bytes<S>(class_wcap(k)), st>>>(a, *m);
-                stx.kernelLaunches++;
-            }
         }
         toc(ev);
         if (mode == CPB_MODE_FORWARD) continue;
@@ -722,22 +629,13 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         const int64_t nb = c.block1 - c.block0;
         if (nb == 0) continue;
         ev = tic(&stx.msBackward);
-        if (ctx->stripEngine) {
+        {
             a.list = dLists + c.stripBwdOff;
             sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex + 1;
             sargs.nItems = (int32_t) nb;
             const int grid = (int) std::min<int64_t>(stripGrid, (nb + kStripWPC - 1) / kStripWPC);
             kBwdStrip<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
             stx.kernelLaunches++;
-        } else {
-            for (int k = 0; k < kNumClasses; k++) {
-                const int64_t cnt = c.bwdListOff[k + 1] - c.bwdListOff[k];
-                if (cnt == 0) continue;
-                a.list = dLists + c.bwdListOff[k];
-                const int warps = g_classWarps[k];
-                kernel_table<S>().bwd[k][warp_index(warps)]<<<(unsigned) cnt, 32 * warps, dp_smem_bytes<S>(class_wcap(k)), st>>>(a, *m);
-                stx.kernelLaunches++;
-            }
         }
         toc(ev);
 

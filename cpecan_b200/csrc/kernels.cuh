@@ -3,10 +3,10 @@
  *
  * Data flow for one chunk of regions (a region = one split sub-problem, see engine.cu):
  *   k_band      per region : anchors -> per-diagonal band records + traceback-block schedule
- *   k_forward   per region : anti-diagonal wavefront, rolling 2-diagonal window in shared memory,
- *                            selected state planes (and full cells of "total" diagonals) -> HBM
- *   k_backward  per block  : same wavefront downwards in gather form, B planes -> HBM,
- *                            per-cell F.B dot products of the total diagonals -> HBM
+ *   k_forward_strip  per region : anti-diagonal wavefront, one warp per region, lanes = matrix rows (strip_kernels.cuh);
+ *                                 selected state planes (and full cells of "total" diagonals) -> HBM
+ *   k_backward_strip per block  : same wavefront downwards in gather form; F + B planes (posterior modes) or
+ *                                 B planes (expectations) -> HBM, per-cell F.B dot products of the total diagonals -> HBM
  *   k_totals    per decade : the reference's left-to-right logAdd folds that give totalProbability
  *   k_posterior per block  : exp(F+B-total) threshold scan, count pass then compacted write pass
  *   k_expect    per block  : expected transition / emission counts
@@ -95,56 +95,55 @@ struct DpArgs {
 /* ---------------------------------------------------------------------------------------------
  * logAdd, bit-compatible with impl/pairwiseAligner.c:290-307
  * ------------------------------------------------------------------------------------------- */
-/* coefficient table laid out [segment][a,b,c,k]; the literals are floats promoted to double exactly as in C */
+/* the reference's 4-segment cubic, [segment][a,b,c,k]; the literals are floats promoted to double exactly as in C */
 __constant__ double c_coefficients[16] = {
     (double) -0.009350833524763f, (double) 0.130659527668286f, (double) 0.498799810682272f, (double) 0.693203116424741f,
     (double) -0.014532321752540f, (double) 0.139942324101744f, (double) 0.495635523139337f, (double) 0.692140569840976f,
     (double) -0.004605031767994f, (double) 0.063427417320019f, (double) 0.695956496475118f, (double) 0.514272634594009f,
     (double) -0.000458661602210f, (double) 0.009695946122598f, (double) 0.930734667215156f, (double) 0.168037164329057f };
 
-__constant__ float c_coefficients_f32[16] = {
-    -0.009350833524763f, 0.130659527668286f, 0.498799810682272f, 0.693203116424741f,
-    -0.014532321752540f, 0.139942324101744f, 0.495635523139337f, 0.692140569840976f,
-    -0.004605031767994f, 0.063427417320019f, 0.695956496475118f, 0.514272634594009f,
-    -0.000458661602210f, 0.009695946122598f, 0.930734667215156f, 0.168037164329057f };
+/*
+ * Segment selection without FP64 compares.  The segment bounds 1, 2.5, 4.5 and the cut-off 7.5 all have a zero low
+ * word and a high word that is a multiple of 2^17, so for d >= 0:  d > T  <=>  hi32(bits(d) - 1) >= hi32(T), and
+ * r = (hi32(bits(d) - 1) >> 17) - 0x1FF7 counts 2^17-wide buckets above 1.0.  A shared-memory table of LA_ROWS rows
+ * maps the clamped bucket to its coefficients: row 0: d <= 1; rows 1-10: (1, 2.5]; rows 11-17: (2.5, 4.5];
+ * rows 18-24: above 4.5 (the polynomial is discarded from 7.5 on).
+ */
+constexpr int LA_ROWS = 25;
 
-__device__ __forceinline__ void fill_coefficients(double *ctab, int tid) {
-#if CPB_COEF_MODE == 1
-    if (tid < 16) reinterpret_cast<float *>(ctab)[tid] = c_coefficients_f32[tid];
-#else
-    if (tid < 16) ctab[tid] = c_coefficients[tid];
-#endif
+__device__ __forceinline__ void fill_logadd_rows(double *la, int tid, int nthreads) {
+    for (int i = tid; i < LA_ROWS * 4; i += nthreads) {
+        const int r = i >> 2;
+        const int seg = r == 0 ? 0 : (r <= 10 ? 1 : (r <= 17 ? 2 : 3));
+        la[i] = c_coefficients[4 * seg + (i & 3)];
+    }
 }
 
-#ifndef CPB_COEF_MODE
-#define CPB_COEF_MODE 0 /* 0: FP64 table in shared memory; 1: FP32 table in shared memory, widened per use; 2: FP64 table in constant memory */
-#endif
-
-__device__ __forceinline__ double log_add(double x, double y, const double *__restrict__ ctab) {
+__device__ __forceinline__ double log_add(double x, double y, const double *__restrict__ la) {
     const double diff = __dsub_rn(x, y);
-    const bool xSmaller = __double2hiint(diff) < 0; /* sign of x-y; both -inf gives NaN, handled below */
+    const int hi = __double2hiint(diff);
+    const bool xSmaller = hi < 0; /* sign of x-y; both -inf gives NaN, handled below */
     const double big = xSmaller ? y : x;
     const double small = xSmaller ? x : y;
-    const double d = fabs(diff);
-    const int seg = (d > 1.0) + (d > 2.5) + (d > 4.5);
-#if CPB_COEF_MODE == 1
-    /* the reference's coefficients are float literals: fetch 16 bytes and widen exactly */
-    const float4 c4 = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(ctab) + 4 * seg);
-    const double2 ab = make_double2((double) c4.x, (double) c4.y), ck = make_double2((double) c4.z, (double) c4.w);
-#elif CPB_COEF_MODE == 2
-    const double2 ab = *reinterpret_cast<const double2 *>(c_coefficients + 4 * seg);
-    const double2 ck = *reinterpret_cast<const double2 *>(c_coefficients + 4 * seg + 2);
-#else
-    const double2 ab = *reinterpret_cast<const double2 *>(ctab + 4 * seg);
-    const double2 ck = *reinterpret_cast<const double2 *>(ctab + 4 * seg + 2);
-#endif
-    double r = __dadd_rn(__dmul_rn(ab.x, d), ab.y);
-    r = __dadd_rn(__dmul_rn(r, d), ck.x);
-    r = __dadd_rn(__dmul_rn(r, d), ck.y);
-    r = __dadd_rn(r, small);
+    const double d = fabs(diff); /* only feeds the multiplies (a free operand modifier); the bucket comes from the integer view */
+    const int hiAbs = hi & 0x7FFFFFFF;
+    const int hi3 = (int) (((long long) (((unsigned long long) (unsigned) hiAbs << 32) | (unsigned) __double2loint(diff)) - 1LL) >> 32); /* hi32(bits(|diff|) - 1) */
+    const int r = min(max((hi3 >> 17) - 0x1FF7, 0), LA_ROWS - 1);
+    const double2 ab = *reinterpret_cast<const double2 *>(la + 4 * r);
+    const double2 ck = *reinterpret_cast<const double2 *>(la + 4 * r + 2);
+    double p = __dadd_rn(__dmul_rn(ab.x, d), ab.y);
+    p = __dadd_rn(__dmul_rn(p, d), ck.x);
+    p = __dadd_rn(__dmul_rn(p, d), ck.y);
+    p = __dadd_rn(p, small);
     /* d >= 7.5, d = +inf (one side is LOG_ZERO) and d = NaN (both are) all return the larger operand */
-    return (d < 7.5) ? r : big;
+    return hiAbs < 0x401E0000 ? p : big;
 }
+
+#define CPB_NEG_INF (__longlong_as_double(0xFFF0000000000000LL))
+
+#ifndef CPB_STRIP_MIN_BLOCKS
+#define CPB_STRIP_MIN_BLOCKS 4 /* resident CTAs per SM the strip kernels are compiled for (register budget) */
+#endif
 
 /* ---------------------------------------------------------------------------------------------
  * per-CTA tables: eP + tP for every (symbol, transition)
@@ -154,7 +153,6 @@ template <> struct Shape<5> { static constexpr int NL = 4, NM = 5, NU = 4; };
 template <> struct Shape<3> { static constexpr int NL = 3, NM = 3, NU = 3; };
 
 template <int S> struct Tables {
-    double ctab[16];
     double tl[5][Shape<S>::NL];      /* [cX][k]  gap-X emission + lower transition */
     double tm[25][Shape<S>::NM];     /* [cX*5+cY][k] */
     double tu[5][Shape<S>::NU];      /* [cY][k] */
@@ -163,7 +161,6 @@ template <int S> struct Tables {
 };
 
 template <int S> __device__ __forceinline__ void fill_tables(Tables<S> &t, const CpbModel &m, int tid, int nthreads) {
-    fill_coefficients(t.ctab, tid);
     for (int i = tid; i < 5 * Shape<S>::NL; i += nthreads) {
         const int c = i / Shape<S>::NL, k = i % Shape<S>::NL;
         t.tl[c][k] = m.eGapX[c] + m.tLower[k];
@@ -198,305 +195,14 @@ template <int S> __host__ __device__ constexpr int middle_from(int k) { return k
 template <int S> __host__ __device__ constexpr int upper_from(int k) { return S == 5 ? (k == 0 ? 0 : (k == 1 ? 2 : (k == 2 ? 0 : 4))) : (k == 0 ? 0 : (k == 1 ? 2 : 1)); }
 template <int S> __host__ __device__ constexpr int upper_to(int k) { return S == 5 ? (k < 2 ? 2 : 4) : 2; }
 
-template <int WARPS> __device__ __forceinline__ void cta_sync() {
-    if (WARPS == 1) __syncwarp();
-    else __syncthreads();
-}
-
-__device__ __forceinline__ int slot_of(int xmy, int mask) { return ((xmy + XMY_BIAS) >> 1) & mask; }
-
-#define CPB_NEG_INF (__longlong_as_double(0xFFF0000000000000LL))
-
-/* ---------------------------------------------------------------------------------------------
- * cell updates
- * ------------------------------------------------------------------------------------------- */
-/* forward: lo = cell (x-1,y), mid = (x-1,y-1), up = (x,y-1); all S states each (absent => -inf) */
-template <int S>
-__device__ __forceinline__ void cell_forward(double *out, const double *lo, const double *mid, const double *up, const double *tl,
-                                             const double *tm, const double *tu, const double *ctab) {
-    if constexpr (S == 5) {
-        out[1] = log_add(lo[0] + tl[0], lo[1] + tl[1], ctab);
-        out[3] = log_add(lo[0] + tl[2], lo[3] + tl[3], ctab);
-        double m = log_add(mid[0] + tm[0], mid[1] + tm[1], ctab);
-        m = log_add(m, mid[2] + tm[2], ctab);
-        m = log_add(m, mid[3] + tm[3], ctab);
-        out[0] = log_add(m, mid[4] + tm[4], ctab);
-        out[2] = log_add(up[0] + tu[0], up[2] + tu[1], ctab);
-        out[4] = log_add(up[0] + tu[2], up[4] + tu[3], ctab);
-    } else {
-        out[1] = log_add(log_add(lo[0] + tl[0], lo[1] + tl[1], ctab), lo[2] + tl[2], ctab);
-        out[0] = log_add(log_add(mid[0] + tm[0], mid[1] + tm[1], ctab), mid[2] + tm[2], ctab);
-        out[2] = log_add(log_add(up[0] + tu[0], up[2] + tu[1], ctab), up[1] + tu[2], ctab);
-    }
-}
-
-/* backward, gather form.  For the cell (x,y): t2m = B.M of (x+1,y+1); tu_* = states of (x,y+1), whose upper
- * neighbour is this cell; tl_* = states of (x+1,y), whose lower neighbour is this cell.  tm/tu/tl are the term
- * rows of those three "to" cells.  Accumulation order = the order the reference's scatter visits this cell:
- * middle of diagonal d+2, then upper-of (x-y-1) and lower-of (x-y+1) on diagonal d+1. */
-template <int S>
-__device__ __forceinline__ void cell_backward(double *out, double t2m, const double *toU, const double *toL, const double *tm,
-                                              const double *tu, const double *tl, const double *ctab) {
-    if constexpr (S == 5) {
-        double m = log_add(t2m + tm[0], toU[2] + tu[0], ctab);
-        m = log_add(m, toU[4] + tu[2], ctab);
-        m = log_add(m, toL[1] + tl[0], ctab);
-        out[0] = log_add(m, toL[3] + tl[2], ctab);
-        out[1] = log_add(t2m + tm[1], toL[1] + tl[1], ctab);
-        out[2] = log_add(t2m + tm[2], toU[2] + tu[1], ctab);
-        out[3] = log_add(t2m + tm[3], toL[3] + tl[3], ctab);
-        out[4] = log_add(t2m + tm[4], toU[4] + tu[3], ctab);
-    } else {
-        out[0] = log_add(log_add(t2m + tm[0], toU[2] + tu[0], ctab), toL[1] + tl[0], ctab);
-        out[1] = log_add(log_add(t2m + tm[1], toU[2] + tu[2], ctab), toL[1] + tl[1], ctab);
-        out[2] = log_add(log_add(t2m + tm[2], toU[2] + tu[1], ctab), toL[1] + tl[2], ctab);
-    }
-}
-
-/* ---------------------------------------------------------------------------------------------
- * The rolling window.  Two parity buffers of S x WCAP doubles in shared memory, indexed by
- * slot(x-y) = floor((x-y)/2) mod WCAP.  Diagonal d overwrites diagonal d-2 in place (same parity, a
- * cell and its "middle" neighbour share x-y).  Invariant kept by clear_stale(): a buffer holds the
- * cells of its latest diagonal and LOG_ZERO in every other slot, so neighbours outside the band read
- * as LOG_ZERO without any bounds test (the reference skips NULL neighbours; logAdd with LOG_ZERO is
- * the identity, so the results are the same bits).  WCAP >= the region's maxSpan (k_band) guarantees
- * that no two live cells alias.
- * ------------------------------------------------------------------------------------------- */
-template <int S, int WCAP, int NT>
-__device__ __forceinline__ void clear_stale(double *buf, int oldL, int oldR, int newL, int newR, int tid) {
-    /* cells of [oldL, oldR] (step 2) that are not in [newL, newR] */
-    const int leftEnd = min(oldR, newL - 2);
-    const int nLeft = leftEnd >= oldL ? ((leftEnd - oldL) >> 1) + 1 : 0;
-    const int rightStart = max(oldL, newR + 2);
-    const int nRight = oldR >= rightStart ? ((oldR - rightStart) >> 1) + 1 : 0;
-    for (int i = tid; i < nLeft + nRight; i += NT) {
-        const int xmy = i < nLeft ? oldL + 2 * i : rightStart + 2 * (i - nLeft);
-        const int sl = slot_of(xmy, WCAP - 1);
-#pragma unroll
-        for (int s = 0; s < S; s++) buf[s * WCAP + sl] = CPB_NEG_INF;
-    }
-}
-
-/* ---------------------------------------------------------------------------------------------
- * k_forward : one CTA (WARPS warps) per region
- * ------------------------------------------------------------------------------------------- */
-template <int S, int WCAP, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) k_forward(const DpArgs a, const CpbModel model) {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    Tables<S> &tab = *reinterpret_cast<Tables<S> *>(smemRaw);
-    double *win = reinterpret_cast<double *>(smemRaw + ((sizeof(Tables<S>) + 15) & ~size_t(15)));
-    constexpr int NT = 32 * WARPS;
-    constexpr int mask = WCAP - 1;
-    const int tid = threadIdx.x;
-
-    const int regionId = a.list[blockIdx.x];
-    const RegionDev R = a.regions[regionId];
-    fill_tables<S>(tab, model, tid, NT);
-    for (int i = tid; i < 2 * S * WCAP; i += NT) win[i] = CPB_NEG_INF;
-    const int N = R.lX + R.lY;
-    const DiagRec *dg = a.diags + R.diagBase;
-    const uint8_t *sx = a.symX + R.xBase, *sy = a.symY + R.yBase;
-    double *pf = a.planesF + R.cellBase;
-    double *aux = a.aux + R.auxBase;
-    cta_sync<WARPS>();
-
-    /* diagonal 0: the single cell (0,0) holds the start vector (impl/pairwiseAligner.c:776-777) */
-    DiagRec prev1 = dg[0];
-    if (tid == 0) {
-        const double *sv = R.raggedL ? tab.rstartv : tab.startv;
-        const int s0 = slot_of(0, mask);
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-            win[(0 * S + s) * WCAP + s0] = sv[s];
-            if (s < a.nPlanes) pf[(int64_t) s * a.planeStride] = sv[s];
-        }
-    }
-    int l2 = 1, r2 = -1; /* band of diagonal d-2: empty */
-    DiagRec cur = dg[N >= 1 ? 1 : 0];
-    cta_sync<WARPS>();
-
-    for (int d = 1; d <= N; d++) {
-        const DiagRec nxt = dg[d + 1]; /* prefetch (record N+1 is a sentinel) */
-        const int par = d & 1;
-        double *wOwn = win + (par * S) * WCAP;               /* holds diagonal d-2, overwritten in place with d */
-        const double *wPrev = win + ((par ^ 1) * S) * WCAP;  /* diagonal d-1 */
-        const bool fullToAux = a.auxF != 0 && cur.aoff != NO_AUX;
-        const int curR = cur.xmyL + 2 * (cur.width - 1);
-#pragma unroll 1
-        for (int i = tid; i < cur.width; i += NT) {
-            const int xmy = cur.xmyL + 2 * i;
-            const int x = (d + xmy) >> 1, y = (d - xmy) >> 1;
-            const int cX = x > 0 ? sx[x - 1] : 4, cY = y > 0 ? sy[y - 1] : 4;
-            const int own = slot_of(xmy, mask);
-            const int sl = par ? own : ((own - 1) & mask); /* slot of xmy-1 on diagonal d-1 */
-            const int su = par ? ((own + 1) & mask) : own; /* slot of xmy+1 on diagonal d-1 */
-            double lo[S], mid[S], up[S], out[S];
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                lo[s] = wPrev[s * WCAP + sl];
-                up[s] = wPrev[s * WCAP + su];
-                mid[s] = wOwn[s * WCAP + own];
-            }
-            /* eP + tP per transition: one emission load per group, the transition comes from the constant bank */
-            double tl[Shape<S>::NL], tm[Shape<S>::NM], tu[Shape<S>::NU];
-            {
-                const double eX = tab.eGapX[cX], eM = tab.eMatch[cX * 5 + cY], eY = tab.eGapY[cY];
-#pragma unroll
-                for (int k = 0; k < Shape<S>::NL; k++) tl[k] = eX + model.tLower[k];
-#pragma unroll
-                for (int k = 0; k < Shape<S>::NM; k++) tm[k] = eM + model.tMiddle[k];
-#pragma unroll
-                for (int k = 0; k < Shape<S>::NU; k++) tu[k] = eY + model.tUpper[k];
-            }
-            cell_forward<S>(out, lo, mid, up, tl, tm, tu, tab.ctab);
-            const int64_t cell = (int64_t) cur.coff + i;
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                wOwn[s * WCAP + own] = out[s];
-                if (s < a.nPlanes) pf[(int64_t) s * a.planeStride + cell] = out[s];
-            }
-            if (fullToAux) {
-#pragma unroll
-                for (int s = 0; s < S; s++) aux[(int64_t) cur.aoff + (int64_t) s * cur.width + i] = out[s];
-            }
-        }
-        if (l2 < cur.xmyL || r2 > curR) clear_stale<S, WCAP, NT>(wOwn, l2, r2, cur.xmyL, curR, tid);
-        cta_sync<WARPS>();
-        l2 = prev1.xmyL;
-        r2 = prev1.xmyL + 2 * (prev1.width - 1);
-        prev1 = cur;
-        cur = nxt;
-    }
-
-    /* forward-only (computeForwardProbability, impl/pairwiseAligner.c:879-931): dot of the last cell with the end vector */
-    if (a.forwardOut != nullptr && tid == 0) {
-        double v = 0.0; /* LOG_ONE for the empty problem */
-        if (N > 0) {
-            const int own = slot_of(R.lX - R.lY, mask);
-            const double *w = win + ((N & 1) * S) * WCAP;
-            const double *ev = R.raggedR ? tab.rendv : tab.endv;
-            v = w[0 * WCAP + own] + ev[0];
-#pragma unroll
-            for (int s = 1; s < S; s++) v = log_add(v, w[s * WCAP + own] + ev[s], tab.ctab);
-        }
-        a.forwardOut[regionId] = v;
-    }
-}
-
-/* ---------------------------------------------------------------------------------------------
- * k_backward : one CTA per traceback block
- * ------------------------------------------------------------------------------------------- */
-template <int S, int WCAP, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) k_backward(const DpArgs a, const CpbModel model) {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    Tables<S> &tab = *reinterpret_cast<Tables<S> *>(smemRaw);
-    double *win = reinterpret_cast<double *>(smemRaw + ((sizeof(Tables<S>) + 15) & ~size_t(15)));
-    constexpr int NT = 32 * WARPS;
-    constexpr int mask = WCAP - 1;
-    const int tid = threadIdx.x;
-
-    const BlockRec K = a.blocks[a.list[blockIdx.x]];
-    const RegionDev R = a.regions[K.region];
-    fill_tables<S>(tab, model, tid, NT);
-    for (int i = tid; i < 2 * S * WCAP; i += NT) win[i] = CPB_NEG_INF;
-    const DiagRec *dg = a.diags + R.diagBase;
-    const uint8_t *sx = a.symX + R.xBase, *sy = a.symY + R.yBase;
-    const double *pf = a.planesF + R.cellBase;
-    double *pb = a.planesB + R.cellBase;
-    double *aux = a.aux + R.auxBase;
-    const int top = K.top, T = K.T, from = K.from;
-    cta_sync<WARPS>();
-    const double *endVec = (K.atEnd && R.raggedR) ? tab.rendv : tab.endv;
-    const int nF = a.auxF; /* full-F planes stored in aux (0 in expectation mode) */
-
-    int l2 = 1, r2 = -1; /* band of diagonal d+2 */
-    DiagRec prev1 = dg[top];
-    DiagRec cur = prev1;
-    for (int d = top; d > T; d--) {
-        const DiagRec nxt = dg[d - 1]; /* the next diagonal down (d-1 >= T >= 0) */
-        const int par = d & 1;
-        double *wOwn = win + (par * S) * WCAP;               /* holds B[d+2], overwritten in place with B[d] */
-        const double *wNext = win + ((par ^ 1) * S) * WCAP;  /* B[d+1] */
-        const bool owned = d <= from;
-        const bool isTotal = owned && cur.aoff != NO_AUX;
-        const bool feedsTotal = d - 1 > T && d - 1 <= from && nxt.aoff != NO_AUX; /* d-1 is a total diagonal: it needs F.M+B.M of d */
-        const int curR = cur.xmyL + 2 * (cur.width - 1);
-#pragma unroll 1
-        for (int i = tid; i < cur.width; i += NT) {
-            const int xmy = cur.xmyL + 2 * i;
-            const int own = slot_of(xmy, mask);
-            double out[S];
-            if (d == top) {
-#pragma unroll
-                for (int s = 0; s < S; s++) out[s] = endVec[s];
-            } else {
-                const int x = (d + xmy) >> 1, y = (d - xmy) >> 1;
-                const int cX = x < R.lX ? sx[x] : 4, cY = y < R.lY ? sy[y] : 4; /* symbols of row x+1 / column y+1 */
-                const int sU = par ? own : ((own - 1) & mask); /* slot of xmy-1 on diagonal d+1: cell (x,y+1) */
-                const int sL = par ? ((own + 1) & mask) : own; /* slot of xmy+1 on diagonal d+1: cell (x+1,y) */
-                double toU[S], toL[S];
-#pragma unroll
-                for (int s = 0; s < S; s++) {
-                    toU[s] = wNext[s * WCAP + sU];
-                    toL[s] = wNext[s * WCAP + sL];
-                }
-                const double t2m = wOwn[0 * WCAP + own];
-                double tl[Shape<S>::NL], tm[Shape<S>::NM], tu[Shape<S>::NU];
-                {
-                    const double eX = tab.eGapX[cX], eM = tab.eMatch[cX * 5 + cY], eY = tab.eGapY[cY];
-#pragma unroll
-                    for (int k = 0; k < Shape<S>::NL; k++) tl[k] = eX + model.tLower[k];
-#pragma unroll
-                    for (int k = 0; k < Shape<S>::NM; k++) tm[k] = eM + model.tMiddle[k];
-#pragma unroll
-                    for (int k = 0; k < Shape<S>::NU; k++) tu[k] = eY + model.tUpper[k];
-                }
-                cell_backward<S>(out, t2m, toU, toL, tm, tu, tl, tab.ctab);
-            }
-            const int64_t cell = (int64_t) cur.coff + i;
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                wOwn[s * WCAP + own] = out[s];
-                if (owned && s < a.nPlanes) pb[(int64_t) s * a.planeStride + cell] = out[s];
-            }
-            if (isTotal) {
-                /* cell_dotProduct(F[d], B[d]) (impl/pairwiseAligner.c:402-408); the fold over cells happens in k_totals */
-                double f[S];
-                if (nF != 0) {
-#pragma unroll
-                    for (int s = 0; s < S; s++) f[s] = aux[(int64_t) cur.aoff + (int64_t) s * cur.width + i];
-                } else {
-#pragma unroll
-                    for (int s = 0; s < S; s++) f[s] = pf[(int64_t) s * a.planeStride + cell];
-                }
-                double t = f[0] + out[0];
-#pragma unroll
-                for (int s = 1; s < S; s++) t = log_add(t, f[s] + out[s], tab.ctab);
-                aux[(int64_t) cur.aoff + (int64_t) nF * cur.width + i] = t;
-            }
-            if (feedsTotal) {
-                /* match step from F[d-2] into diagonal d dotted with B[d] (impl/pairwiseAligner.c:643-651) == F[d].M + B[d].M */
-                aux[(int64_t) nxt.aoff + (int64_t) (nF + 1) * nxt.width + i] = pf[cell] + out[0];
-            }
-        }
-        if (l2 < cur.xmyL || r2 > curR) clear_stale<S, WCAP, NT>(wOwn, l2, r2, cur.xmyL, curR, tid);
-        cta_sync<WARPS>();
-        l2 = prev1.xmyL;
-        r2 = prev1.xmyL + 2 * (prev1.width - 1);
-        if (d == top) { l2 = 1; r2 = -1; } /* nothing above the top diagonal */
-        prev1 = cur;
-        cur = nxt;
-    }
-}
-
 /* ---------------------------------------------------------------------------------------------
  * k_totals : one warp per block, one lane per decade (10 owned diagonals share one totalProbability,
  * impl/pairwiseAligner.c:830-838).  Each fold is the reference's strictly sequential logAdd over the
  * cells of the diagonal (dpDiagonal_dotProduct, :513-523), so lanes run independent folds in parallel.
  * ------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(128) k_totals(const DpArgs a, int nBlocks) {
-    __shared__ __align__(16) double ctab[16];
-    fill_coefficients(ctab, threadIdx.x);
+    __shared__ __align__(16) double ctab[LA_ROWS * 4];
+    fill_logadd_rows(ctab, threadIdx.x, blockDim.x);
     __syncthreads();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= nBlocks) return;
@@ -587,7 +293,7 @@ __global__ void __launch_bounds__(32 * POST_WARPS) k_posterior(const DpArgs a, c
                         keep = valid && (l == 0 ? (x > 0 && y > 0) : (l == 1 ? x > 0 : y > 0));
                     }
                     if (keep) {
-                        const double z = (a.planesF[(int64_t) l * a.planeStride + cell] + a.planesB[(int64_t) l * a.planeStride + cell]) - total;
+                        const double z = a.planesB[(int64_t) l * a.planeStride + cell] - total; /* the backward sweep stored F + B */
                         keep = false;
                         if (z >= p.logThresholdLo) {
                             double pr = exp(z);

@@ -4,80 +4,128 @@
  *
  * Lane l of the warp owns matrix row x = 32*s + l of the current row strip s and walks the anti-diagonals
  * d that touch the strip (k_band records [dFirst, dLast] per strip).  On diagonal d it computes the cell
- * (x, d-x); everything outside the band is LOG_ZERO (the reference never creates those cells, and logAdd
- * with LOG_ZERO is the identity, so the arithmetic that remains is the reference's, bit for bit):
- *   forward : lower (x-1,y) and middle (x-1,y-1) are lane l-1's outputs one and two steps ago -> one
- *             shuffle-up of the previous output per step; upper (x,y-1) is the lane's own previous output;
- *   backward: (x+1,y) and (x+1,y+1) come from lane l+1 by shuffle-down, (x,y+1) is the lane's own.
- * Strips are processed in row order (forward) / reverse row order (backward); the edge row of a strip is
- * handed to the next strip through a small per-warp ring of 64-byte records indexed by diagonal
- * (L2-resident, read one step ahead).  Warps fetch work items from a global counter, so long and short
- * regions balance across the chip.  The step loop is unrolled by two with ping-pong register sets so no
- * state is copied between steps.
+ * (x, d-x).  Cells outside the band are LOG_ZERO (the reference never creates them, and logAdd with
+ * LOG_ZERO is the identity, so the arithmetic that remains is the reference's, bit for bit).
+ *
+ * Forward.  Of the 13 (9) transitions into a cell (impl/stateMachine.c:454-479, :695-713) the "upper" group
+ * comes from the lane's own previous cell and stays local.  The "lower" and "middle" groups come from row
+ * x-1, i.e. lane l-1: that lane folds them itself -- with the destination cell's emissions, which it knows
+ * (the next row's symbol is fixed per strip, the next column's symbol is the one it fetches anyway) -- in
+ * the reference's order, and hands over only the finished sums: one message of NSH = 3 (2) doubles per
+ * diagonal instead of all S states twice.  A message is {m'(d-1), g'(d)}: the middle fold is held back one
+ * step so that everything in a message belongs to diagonal d+1.
+ * Backward (gather form of the reference's scatter) needs B.M of (x+1,y+1) and
+ * the gap-X states of (x+1,y): the same message shape, shuffled down.
+ *
+ * Strips are processed in row order (forward) / reverse row order (backward); the edge lane writes its
+ * messages to a per-warp ring in global memory (L2 resident), indexed by diagonal, and the first lane of the
+ * next strip prefetches them one step ahead.  Out-of-band masking costs one select per received word: the
+ * lane's own terms are masked through a sixth "symbol" whose emissions are LOG_ZERO.
+ * Warps fetch work items from a global counter, so long and short regions balance across the chip.
  */
 #pragma once
 #include "kernels.cuh"
 
 namespace cpb {
 
-constexpr int BND_REC = 8; /* doubles per boundary record (S <= 5 used, padded to 64 bytes) */
+constexpr int BND_REC = 4; /* doubles per ring record: up to 3 used, 32-byte aligned */
 
 struct StripArgs {
     const StripRec *strips;   /* per region: (lX>>5)+1 records at RegionDev.stripBase */
     double *boundary;         /* per warp slot: 2 rings of ringSize records */
+    const double *negRecord;  /* one record of LOG_ZERO */
     int32_t ringSize;         /* power of two >= longest strip diagonal range + 4 */
     int32_t nItems;
     unsigned int *counter;    /* work-fetch counter (zeroed before the launch) */
 };
 
-struct StripTables {
-    double ctab[16];
-    double eGapX[5], eGapY[5], eMatch[25];
+template <int S> struct Msg;
+template <> struct Msg<5> { static constexpr int N = 3; };
+template <> struct Msg<3> { static constexpr int N = 2; };
+
+/* per-CTA tables; symbol index 5 = "cell outside the band": its emissions are LOG_ZERO */
+template <int S> struct StripTables {
+    double la[LA_ROWS * 4];
+    double tm[36][6];             /* [cX*6+cY][k] eMatch + tMiddle[k] (k < NM) */
+    double tu[6][4];              /* [cY][k]      eGapY + tUpper[k] */
+    double tl[6][4];              /* [cX][k]      eGapX + tLower[k] */
     double startv[5], rstartv[5], endv[5], rendv[5];
 };
 
-__device__ __forceinline__ void fill_strip_tables(StripTables &t, const CpbModel &m, int tid) {
-    fill_coefficients(t.ctab, tid);
-    if (tid < 5) {
-        t.eGapX[tid] = m.eGapX[tid];
-        t.eGapY[tid] = m.eGapY[tid];
+template <int S> __device__ __forceinline__ void fill_strip_tables(StripTables<S> &t, const CpbModel &m, int tid, int nthreads) {
+    fill_logadd_rows(t.la, tid, nthreads);
+    for (int i = tid; i < 36 * 6; i += nthreads) {
+        const int c = i / 6, k = i % 6, cX = c / 6, cY = c % 6;
+        const double e = (cX < 5 && cY < 5) ? m.eMatch[cX * 5 + cY] : CPB_NEG_INF;
+        t.tm[c][k] = k < Shape<S>::NM ? e + m.tMiddle[k] : 0.0;
+    }
+    for (int i = tid; i < 6 * 4; i += nthreads) {
+        const int c = i / 4, k = i % 4;
+        t.tu[c][k] = k < Shape<S>::NU ? (c < 5 ? m.eGapY[c] : CPB_NEG_INF) + m.tUpper[k] : 0.0;
+        t.tl[c][k] = k < Shape<S>::NL ? (c < 5 ? m.eGapX[c] : CPB_NEG_INF) + m.tLower[k] : 0.0;
+    }
+    if (tid < S) {
         t.startv[tid] = m.start[tid];
         t.rstartv[tid] = m.raggedStart[tid];
         t.endv[tid] = m.end[tid];
         t.rendv[tid] = m.raggedEnd[tid];
     }
-    if (tid < 25) t.eMatch[tid] = m.eMatch[tid];
 }
 
 __device__ __forceinline__ double shfl_up_f64(double v) { return __shfl_up_sync(0xFFFFFFFFu, v, 1); }
 __device__ __forceinline__ double shfl_down_f64(double v) { return __shfl_down_sync(0xFFFFFFFFu, v, 1); }
 
-template <int S> __device__ __forceinline__ void load_record(double *v, const double *rec) {
-    /* 64-byte aligned record, L2 only (another lane of this warp wrote it) */
+template <int N> __device__ __forceinline__ void load_record(double *v, const double *rec) {
+    /* 32-byte aligned record, L2 only (another lane of this warp wrote it) */
     const double2 a = __ldcg(reinterpret_cast<const double2 *>(rec));
     v[0] = a.x;
     v[1] = a.y;
-    if (S > 2) {
-        const double2 b = __ldcg(reinterpret_cast<const double2 *>(rec) + 1);
-        v[2] = b.x;
-        if (S > 3) v[3] = b.y;
-    }
-    if (S > 4) v[4] = __ldcg(rec + 4);
+    if (N > 2) v[2] = __ldcg(rec + 2);
 }
-template <int S> __device__ __forceinline__ void store_record(double *rec, const double *v) {
+template <int N> __device__ __forceinline__ void store_record(double *rec, const double *v) {
     __stcg(reinterpret_cast<double2 *>(rec), make_double2(v[0], v[1]));
-    if (S > 2) __stcg(reinterpret_cast<double2 *>(rec) + 1, make_double2(v[2], S > 3 ? v[3] : 0.0));
-    if (S > 4) __stcg(rec + 4, v[4]);
+    if (N > 2) __stcg(rec + 2, v[2]);
+}
+
+template <int N> __device__ __forceinline__ void load_row(double *v, const double *row) {
+    const double2 a = *reinterpret_cast<const double2 *>(row);
+    v[0] = a.x;
+    v[1] = a.y;
+    if (N > 2) {
+        const double2 b = *reinterpret_cast<const double2 *>(row + 2);
+        v[2] = b.x;
+        if (N > 3) v[3] = b.y;
+    }
+    if (N > 4) v[4] = row[4];
+}
+
+/* the folds a source cell performs for the cell below-right (middle group) and below (lower group), in the
+ * reference's transition order; `c` = the source cell's S states */
+template <int S>
+__device__ __forceinline__ void forward_contributions(double &m, double *g, const double *c, const double *tm, const double *tl, const double *la) {
+    if constexpr (S == 5) {
+        double v = log_add(c[0] + tm[0], c[1] + tm[1], la);
+        v = log_add(v, c[2] + tm[2], la);
+        v = log_add(v, c[3] + tm[3], la);
+        m = log_add(v, c[4] + tm[4], la);
+        g[0] = log_add(c[0] + tl[0], c[1] + tl[1], la); /* -> shortGapX */
+        g[1] = log_add(c[0] + tl[2], c[3] + tl[3], la); /* -> longGapX */
+    } else {
+        m = log_add(log_add(c[0] + tm[0], c[1] + tm[1], la), c[2] + tm[2], la);
+        g[0] = log_add(log_add(c[0] + tl[0], c[1] + tl[1], la), c[2] + tl[2], la); /* -> gapX */
+    }
 }
 
 /* ---------------------------------------------------------------------------------------------
  * k_forward_strip<S, NP, WPC>: NP = state planes written to HBM (0 forward-only, 1 match, 3 match+gaps, S all)
  * ------------------------------------------------------------------------------------------- */
 template <int S, int NP, int WPC>
-__global__ void __launch_bounds__(32 * WPC) k_forward_strip(const DpArgs a, const CpbModel model, const StripArgs sa) {
-    __shared__ __align__(16) StripTables tab;
-    fill_strip_tables(tab, model, threadIdx.x);
+__global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_strip(const DpArgs a, const CpbModel model, const StripArgs sa) {
+    __shared__ __align__(16) StripTables<S> tab;
+    fill_strip_tables<S>(tab, model, threadIdx.x, 32 * WPC);
     __syncthreads();
+    constexpr int NSH = Msg<S>::N, NL = Shape<S>::NL, NM = Shape<S>::NM, NU = Shape<S>::NU;
+    const double *la = tab.la;
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * WPC + (threadIdx.x >> 5);
     const int rm = sa.ringSize - 1;
@@ -99,7 +147,7 @@ __global__ void __launch_bounds__(32 * WPC) k_forward_strip(const DpArgs a, cons
         double *aux = a.aux + R.auxBase;
         const StripRec *strips = sa.strips + R.stripBase;
         const int nStrips = (R.lX >> 5) + 1;
-        int prevFirst = 1, prevLast = 0; /* diagonal range the previous strip wrote to its boundary ring */
+        int prevFirst = 1, prevLast = 0; /* ring indices the previous strip wrote */
 
         for (int s = 0; s < nStrips; s++) {
             const StripRec sr = strips[s];
@@ -109,19 +157,19 @@ __global__ void __launch_bounds__(32 * WPC) k_forward_strip(const DpArgs a, cons
                 continue;
             }
             const int x = 32 * s + lane;
-            const int cX5 = ((x > 0 && x <= R.lX) ? sx[x - 1] : 4) * 5;
-            const double eX = tab.eGapX[cX5 / 5];
+            const int cXn6 = (x < R.lX ? sx[x] : 4) * 6; /* symbol of row x+1, the row this lane's messages go to */
+            double tlD[NL];
+            load_row<NL>(tlD, tab.tl[cXn6 / 6]);
+            const uint8_t *ptrY = sy - x; /* ptrY[d] = symbol of column d+1-x (symbol arrays are padded on both sides) */
             double *bOut = (s & 1) ? ring1 : ring0;
             const double *bIn = (s & 1) ? ring0 : ring1;
 
-            /* two register sets, used alternately: own previous output, and lane-1's output received one step ago */
-            double ownA[S], ownB[S], rcvA[S], rcvB[S], bNext[S];
+            double own[S], send[NSH], bNext[NSH], mDelay = CPB_NEG_INF;
 #pragma unroll
-            for (int k = 0; k < S; k++) {
-                ownA[k] = ownB[k] = CPB_NEG_INF;
-                rcvA[k] = rcvB[k] = CPB_NEG_INF;
-                bNext[k] = CPB_NEG_INF;
-            }
+            for (int k = 0; k < S; k++) own[k] = CPB_NEG_INF;
+#pragma unroll
+            for (int k = 0; k < NSH; k++) send[k] = bNext[k] = CPB_NEG_INF;
+
             int d0 = sr.dFirst;
             if (d0 == 0) {
                 /* diagonal 0: the single cell (0,0) holds the start vector (impl/pairwiseAligner.c:776-777) */
@@ -129,100 +177,97 @@ __global__ void __launch_bounds__(32 * WPC) k_forward_strip(const DpArgs a, cons
                     const double *sv = R.raggedL ? tab.rstartv : tab.startv;
 #pragma unroll
                     for (int k = 0; k < S; k++) {
-                        ownA[k] = sv[k];
+                        own[k] = sv[k];
                         if (k < NP) pf[(int64_t) k * a.planeStride] = sv[k];
                     }
                 }
-                if (lane == 31) store_record<S>(bOut, ownA);
+                double tmD[NM], mNew;
+                load_row<NM>(tmD, tab.tm[cXn6 + ptrY[0]]);
+                forward_contributions<S>(mNew, send + 1, own, tmD, tlD, la);
+                send[0] = CPB_NEG_INF;
+                mDelay = mNew;
+                if (lane == 31) store_record<NSH>(bOut, send);
                 d0 = 1;
             } else if (lane == 0) {
-                /* row x-1 of the previous strip: diagonal d0-2 seeds "middle", d0-1 is the first step's "lower" */
-                const int d2 = d0 - 2, d1 = d0 - 1;
-                if (d2 >= prevFirst && d2 <= prevLast) load_record<S>(rcvA, bIn + (size_t) (d2 & rm) * BND_REC);
-                if (d1 >= prevFirst && d1 <= prevLast) load_record<S>(bNext, bIn + (size_t) (d1 & rm) * BND_REC);
+                /* message for diagonal d0 from row x-1 (the previous strip's last lane) */
+                const int t = d0 - 1;
+                const DiagRec r0 = dg[d0 <= N ? d0 : N];
+                const bool ok = t >= prevFirst && t <= prevLast && (unsigned) (x - ((d0 + r0.xmyL) >> 1)) < (unsigned) r0.width;
+                load_record<NSH>(bNext, ok ? bIn + (size_t) (t & rm) * BND_REC : sa.negRecord);
             }
             DiagRec cur = dg[d0 <= N ? d0 : N];
-            int cY = 4;
-            {
-                const int y0 = d0 - x;
-                if (y0 > 0 && y0 <= R.lY) cY = sy[y0 - 1];
-            }
+            int cY = ptrY[d0 - 1]; /* symbol of column d0 - x */
 
-            /* one step: reads (own, rcvOld), writes (ownNew, rcvNew) */
-            auto step = [&](const int d, const double(&own)[S], const double(&rcvOld)[S], double(&ownNew)[S], double(&rcvNew)[S]) {
+#pragma unroll 2
+            for (int d = d0; d <= sr.dLast; d++) {
                 const DiagRec nxt = dg[d + 1]; /* prefetch (record N+1 is a sentinel) */
                 const int cYnow = cY;
-                {
-                    const int y1 = d + 1 - x; /* next step's column symbol */
-                    cY = (y1 > 0 && y1 <= R.lY) ? sy[y1 - 1] : 4;
-                }
+                cY = ptrY[d];
+                const bool inBand = (unsigned) (x - ((d + cur.xmyL) >> 1)) < (unsigned) cur.width;
+                const bool useShfl = inBand && lane != 0;
+                double rcv[NSH];
 #pragma unroll
-                for (int k = 0; k < S; k++) rcvNew[k] = shfl_up_f64(own[k]);
+                for (int k = 0; k < NSH; k++) {
+                    const double v = shfl_up_f64(send[k]);
+                    rcv[k] = useShfl ? v : bNext[k]; /* lanes other than 0 keep LOG_ZERO in bNext: this is also the band mask */
+                }
                 if (lane == 0) {
-#pragma unroll
-                    for (int k = 0; k < S; k++) rcvNew[k] = bNext[k];
+                    /* prefetch the message for diagonal d+1; LOG_ZERO if the previous strip had none or (0, d+1) is outside the band */
+                    const bool ok = d >= prevFirst && d <= prevLast && (unsigned) (x - ((d + 1 + nxt.xmyL) >> 1)) < (unsigned) nxt.width;
+                    load_record<NSH>(bNext, ok ? bIn + (size_t) (d & rm) * BND_REC : sa.negRecord);
                 }
-                {
-                    /* boundary cell of diagonal d feeds step d+1 (lane 0 only; everyone else keeps LOG_ZERO) */
-                    const bool have = lane == 0 && d >= prevFirst && d <= prevLast;
-                    if (have) load_record<S>(bNext, bIn + (size_t) (d & rm) * BND_REC);
-                    else {
-#pragma unroll
-                        for (int k = 0; k < S; k++) bNext[k] = CPB_NEG_INF;
-                    }
+                double tu[NU];
+                load_row<NU>(tu, tab.tu[inBand ? cYnow : 5]);
+                /* the cell: middle and lower folds arrive finished; the upper group uses this lane's previous cell */
+                double out[S];
+                out[0] = rcv[0];
+                out[1] = rcv[1];
+                if constexpr (S == 5) {
+                    out[3] = rcv[2];
+                    out[2] = log_add(own[0] + tu[0], own[2] + tu[1], la);
+                    out[4] = log_add(own[0] + tu[2], own[4] + tu[3], la);
+                } else {
+                    out[2] = log_add(log_add(own[0] + tu[0], own[2] + tu[1], la), own[1] + tu[2], la);
                 }
-                const int xlo = (d + cur.xmyL) >> 1;
-                const int i = x - xlo;
-                const bool inBand = i >= 0 && i < cur.width;
-
-                double tl[Shape<S>::NL], tm[Shape<S>::NM], tu[Shape<S>::NU], out[S];
-                {
-                    const double eM = tab.eMatch[cX5 + cYnow], eY = tab.eGapY[cYnow];
-#pragma unroll
-                    for (int k = 0; k < Shape<S>::NL; k++) tl[k] = eX + model.tLower[k];
-#pragma unroll
-                    for (int k = 0; k < Shape<S>::NM; k++) tm[k] = eM + model.tMiddle[k];
-#pragma unroll
-                    for (int k = 0; k < Shape<S>::NU; k++) tu[k] = eY + model.tUpper[k];
-                }
-                cell_forward<S>(out, rcvNew, rcvOld, own, tl, tm, tu, tab.ctab);
-#pragma unroll
-                for (int k = 0; k < S; k++) ownNew[k] = inBand ? out[k] : CPB_NEG_INF;
-
                 if (inBand) {
-                    const int cell = (int) cur.coff + i; /* < 2^31 cells per region is enforced on the host */
+                    const int cell = (int) cur.coff + (x - ((d + cur.xmyL) >> 1)); /* < 2^31 cells per region is enforced on the host */
 #pragma unroll
                     for (int k = 0; k < NP; k++) pf[(int64_t) k * a.planeStride + cell] = out[k];
                     if (keepFull && cur.aoff != NO_AUX) {
+                        const int i = x - ((d + cur.xmyL) >> 1);
 #pragma unroll
                         for (int k = 0; k < S; k++) aux[(size_t) cur.aoff + (size_t) k * cur.width + i] = out[k];
                     }
                 }
-                if (lane == 31) store_record<S>(bOut + (size_t) (d & rm) * BND_REC, ownNew);
-                cur = nxt;
-            };
-
-            int d = d0;
-            for (; d + 1 <= sr.dLast; d += 2) {
-                step(d, ownA, rcvA, ownB, rcvB);
-                step(d + 1, ownB, rcvB, ownA, rcvA);
-            }
-            if (d <= sr.dLast) {
-                step(d, ownA, rcvA, ownB, rcvB);
+                /* this cell's folds for row x+1 */
+                double tmD[NM], mNew;
+                load_row<NM>(tmD, tab.tm[cXn6 + cY]);
+                send[0] = mDelay;
+                forward_contributions<S>(mNew, send + 1, out, tmD, tlD, la);
+                mDelay = mNew;
+                if (lane == 31) store_record<NSH>(bOut + (size_t) (d & rm) * BND_REC, send);
 #pragma unroll
-                for (int k = 0; k < S; k++) ownA[k] = ownB[k];
+                for (int k = 0; k < S; k++) own[k] = out[k];
+                cur = nxt;
             }
-            /* ownA now holds the outputs of the strip's last diagonal */
+            if (lane == 31) {
+                /* the held-back middle fold of the last step belongs to diagonal dLast + 2 */
+                double last[NSH];
+                last[0] = mDelay;
+#pragma unroll
+                for (int k = 1; k < NSH; k++) last[k] = CPB_NEG_INF;
+                store_record<NSH>(bOut + (size_t) ((sr.dLast + 1) & rm) * BND_REC, last);
+            }
             if (NP == 0 && a.forwardOut != nullptr && s == nStrips - 1 && sr.dLast == N && N > 0 && lane == (R.lX & 31)) {
                 /* computeForwardProbability: the last cell dotted with the end vector (impl/pairwiseAligner.c:910-916) */
                 const double *ev = R.raggedR ? tab.rendv : tab.endv;
-                double v = ownA[0] + ev[0];
+                double v = own[0] + ev[0];
 #pragma unroll
-                for (int k = 1; k < S; k++) v = log_add(v, ownA[k] + ev[k], tab.ctab);
+                for (int k = 1; k < S; k++) v = log_add(v, own[k] + ev[k], la);
                 a.forwardOut[regionId] = v;
             }
             prevFirst = sr.dFirst;
-            prevLast = sr.dLast;
+            prevLast = sr.dLast + 1;
             __syncwarp();
         }
         if (NP == 0 && a.forwardOut != nullptr && N == 0 && lane == 0) a.forwardOut[regionId] = 0.0; /* LOG_ONE for the empty problem */
@@ -230,24 +275,47 @@ __global__ void __launch_bounds__(32 * WPC) k_forward_strip(const DpArgs a, cons
 }
 
 /* ---------------------------------------------------------------------------------------------
- * k_backward_strip<S, NP, WPC> : one warp per traceback block, strips in descending row order
+ * k_backward_strip<S, NP, ZSUM, WPC> : one warp per traceback block, strips in descending row order.
+ * ZSUM: the planes written are F + B per state (what the posterior scan needs); otherwise raw B (expectations).
  * ------------------------------------------------------------------------------------------- */
 template <int S> struct BwdShare; /* states of row x+1 that row x needs: M (for the middle step) and the gap-X states */
 template <> struct BwdShare<5> {
-    static constexpr int N = 3;
     __host__ __device__ static constexpr int state(int k) { return k == 0 ? 0 : (k == 1 ? 1 : 3); }
 };
 template <> struct BwdShare<3> {
-    static constexpr int N = 2;
     __host__ __device__ static constexpr int state(int k) { return k; }
 };
 
-template <int S, int NP, int WPC>
-__global__ void __launch_bounds__(32 * WPC) k_backward_strip(const DpArgs a, const CpbModel model, const StripArgs sa) {
-    __shared__ __align__(16) StripTables tab;
-    fill_strip_tables(tab, model, threadIdx.x);
+/* backward cell, gather form.  For the cell (x,y): t2m = B.M of (x+1,y+1); u = states of (x,y+1), whose upper
+ * neighbour is this cell; l = gap-X states of (x+1,y), whose lower neighbour is this cell.  tm/tu/tl are the term
+ * rows of those three "to" cells.  Accumulation order = the order the reference's scatter visits this cell:
+ * middle of diagonal d+2, then upper-of (x-y-1) and lower-of (x-y+1) on diagonal d+1. */
+template <int S>
+__device__ __forceinline__ void cell_backward(double *out, double t2m, const double *u, const double *l, const double *tm, const double *tu,
+                                              const double *tl, const double *la) {
+    if constexpr (S == 5) {
+        double m = log_add(t2m + tm[0], u[2] + tu[0], la);
+        m = log_add(m, u[4] + tu[2], la);
+        m = log_add(m, l[0] + tl[0], la);
+        out[0] = log_add(m, l[1] + tl[2], la);
+        out[1] = log_add(t2m + tm[1], l[0] + tl[1], la);
+        out[2] = log_add(t2m + tm[2], u[2] + tu[1], la);
+        out[3] = log_add(t2m + tm[3], l[1] + tl[3], la);
+        out[4] = log_add(t2m + tm[4], u[4] + tu[3], la);
+    } else {
+        out[0] = log_add(log_add(t2m + tm[0], u[2] + tu[0], la), l[0] + tl[0], la);
+        out[1] = log_add(log_add(t2m + tm[1], u[2] + tu[2], la), l[0] + tl[1], la);
+        out[2] = log_add(log_add(t2m + tm[2], u[2] + tu[1], la), l[0] + tl[2], la);
+    }
+}
+
+template <int S, int NP, bool ZSUM, int WPC>
+__global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_backward_strip(const DpArgs a, const CpbModel model, const StripArgs sa) {
+    __shared__ __align__(16) StripTables<S> tab;
+    fill_strip_tables<S>(tab, model, threadIdx.x, 32 * WPC);
     __syncthreads();
-    constexpr int NB = BwdShare<S>::N;
+    constexpr int NSH = Msg<S>::N, NL = Shape<S>::NL, NM = Shape<S>::NM, NU = Shape<S>::NU;
+    const double *la = tab.la;
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * WPC + (threadIdx.x >> 5);
     const int rm = sa.ringSize - 1;
@@ -271,7 +339,7 @@ __global__ void __launch_bounds__(32 * WPC) k_backward_strip(const DpArgs a, con
         const int nStrips = (R.lX >> 5) + 1;
         const int top = K.top, T = K.T, from = K.from;
         const double *endVec = (K.atEnd && R.raggedR) ? tab.rendv : tab.endv;
-        int prevHi = 0, prevLo = 1; /* diagonal range the previously processed (higher) strip wrote */
+        int prevHi = 0, prevLo = 1; /* ring indices the previously processed (higher) strip wrote */
 
         for (int s = nStrips - 1; s >= 0; s--) {
             const StripRec sr = strips[s];
@@ -282,124 +350,126 @@ __global__ void __launch_bounds__(32 * WPC) k_backward_strip(const DpArgs a, con
                 continue;
             }
             const int x = 32 * s + lane;
-            const int cX5 = (x < R.lX ? sx[x] : 4) * 5; /* symbol of row x+1 */
-            const double eX = tab.eGapX[cX5 / 5];
+            const int cXn6 = (x < R.lX ? sx[x] : 4) * 6; /* symbol of row x+1 */
+            double tl[NL];
+            load_row<NL>(tl, tab.tl[cXn6 / 6]);
+            const uint8_t *ptrY = sy - x; /* ptrY[d] = symbol of column d-x+1, the column right of this lane's cell on diagonal d */
             double *bOut = (s & 1) ? ring1 : ring0;
             const double *bIn = (s & 1) ? ring0 : ring1;
 
-            double ownA[S], ownB[S], bNext[NB], recvM = CPB_NEG_INF;
+            double own[S], send[NSH], bNext[NSH];
 #pragma unroll
-            for (int k = 0; k < S; k++) ownA[k] = ownB[k] = CPB_NEG_INF;
+            for (int k = 0; k < S; k++) own[k] = CPB_NEG_INF;
 #pragma unroll
-            for (int k = 0; k < NB; k++) bNext[k] = CPB_NEG_INF;
-            if (lane == 31) {
-                /* row x+1 belongs to the strip processed before this one */
-                const int d2 = dHi + 2, d1 = dHi + 1;
-                if (d2 >= prevLo && d2 <= prevHi) recvM = __ldcg(bIn + (size_t) (d2 & rm) * BND_REC);
-                if (d1 >= prevLo && d1 <= prevHi) load_record<NB>(bNext, bIn + (size_t) (d1 & rm) * BND_REC);
-            }
-            DiagRec cur = dg[dHi];
-            int cY = 4;
-            {
-                const int y0 = dHi - x;
-                if (y0 >= 0 && y0 < R.lY) cY = sy[y0]; /* symbol of column y+1 */
-            }
+            for (int k = 0; k < NSH; k++) send[k] = bNext[k] = CPB_NEG_INF;
 
-            auto step = [&](const int d, const double(&own)[S], double(&ownNew)[S]) {
-                const DiagRec nxt = dg[d - 1]; /* d-1 >= T >= 0 */
-                const int cYnow = cY;
-                {
-                    const int y1 = d - 1 - x;
-                    cY = (y1 >= 0 && y1 < R.lY) ? sy[y1] : 4;
-                }
-                double rcv[NB];
+            /* everything a finished cell has to leave in HBM */
+            auto emit = [&](const int d, const DiagRec &cur, const DiagRec &nxt, const bool inBand, const double(&out)[S]) {
+                if (!inBand) return;
+                const int i = x - ((d + cur.xmyL) >> 1);
+                const int cell = (int) cur.coff + i;
+                const bool owned = d <= from;
+                const bool feeds = d - 1 > T && d - 1 <= from && nxt.aoff != NO_AUX; /* d-1 is a total diagonal */
+                double fm = 0.0;
+                if ((ZSUM && owned) || feeds) fm = pf[cell];
+                if (owned) {
 #pragma unroll
-                for (int k = 0; k < NB; k++) rcv[k] = shfl_down_f64(own[BwdShare<S>::state(k)]);
-                if (lane == 31) {
-#pragma unroll
-                    for (int k = 0; k < NB; k++) rcv[k] = bNext[k];
-                }
-                {
-                    const bool have = lane == 31 && d >= prevLo && d <= prevHi;
-                    if (have) load_record<NB>(bNext, bIn + (size_t) (d & rm) * BND_REC);
-                    else {
-#pragma unroll
-                        for (int k = 0; k < NB; k++) bNext[k] = CPB_NEG_INF;
+                    for (int k = 0; k < NP; k++) {
+                        if (ZSUM) pb[(int64_t) k * a.planeStride + cell] = (k == 0 ? fm : pf[(int64_t) k * a.planeStride + cell]) + out[k];
+                        else pb[(int64_t) k * a.planeStride + cell] = out[k];
                     }
-                }
-                const int xlo = (d + cur.xmyL) >> 1;
-                const int i = x - xlo;
-                const bool inBand = i >= 0 && i < cur.width;
-
-                double out[S];
-                {
-                    double tl[Shape<S>::NL], tm[Shape<S>::NM], tu[Shape<S>::NU];
-                    const double eM = tab.eMatch[cX5 + cYnow], eY = tab.eGapY[cYnow];
+                    if (cur.aoff != NO_AUX) {
+                        /* cell_dotProduct(F[d], B[d]) (impl/pairwiseAligner.c:402-408); folded over the cells by k_totals */
+                        double f[S];
+                        if (nF != 0) {
 #pragma unroll
-                    for (int k = 0; k < Shape<S>::NL; k++) tl[k] = eX + model.tLower[k];
+                            for (int k = 0; k < S; k++) f[k] = aux[(size_t) cur.aoff + (size_t) k * cur.width + i];
+                        } else {
 #pragma unroll
-                    for (int k = 0; k < Shape<S>::NM; k++) tm[k] = eM + model.tMiddle[k];
-#pragma unroll
-                    for (int k = 0; k < Shape<S>::NU; k++) tu[k] = eY + model.tUpper[k];
-                    /* cell_backward reads toU[2], toU[4] (own previous output: cell (x,y+1)) and toL[1], toL[3] (row x+1) */
-                    double toL[S];
-#pragma unroll
-                    for (int k = 0; k < S; k++) toL[k] = CPB_NEG_INF;
-#pragma unroll
-                    for (int k = 1; k < NB; k++) toL[BwdShare<S>::state(k)] = rcv[k];
-                    cell_backward<S>(out, recvM, own, toL, tm, tu, tl, tab.ctab);
-                }
-                if (d == top) {
-#pragma unroll
-                    for (int k = 0; k < S; k++) out[k] = endVec[k];
-                }
-#pragma unroll
-                for (int k = 0; k < S; k++) ownNew[k] = inBand ? out[k] : CPB_NEG_INF;
-
-                if (inBand) {
-                    const int cell = (int) cur.coff + i;
-                    if (d <= from) {
-#pragma unroll
-                        for (int k = 0; k < NP; k++) pb[(int64_t) k * a.planeStride + cell] = out[k];
-                        if (cur.aoff != NO_AUX) {
-                            /* cell_dotProduct(F[d], B[d]) (impl/pairwiseAligner.c:402-408); folded over the cells by k_totals */
-                            double f[S];
-                            if (nF != 0) {
-#pragma unroll
-                                for (int k = 0; k < S; k++) f[k] = aux[(size_t) cur.aoff + (size_t) k * cur.width + i];
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < S; k++) f[k] = pf[(int64_t) k * a.planeStride + cell];
-                            }
-                            double t = f[0] + out[0];
-#pragma unroll
-                            for (int k = 1; k < S; k++) t = log_add(t, f[k] + out[k], tab.ctab);
-                            aux[(size_t) cur.aoff + (size_t) nF * cur.width + i] = t;
+                            for (int k = 0; k < S; k++) f[k] = pf[(int64_t) k * a.planeStride + cell];
                         }
-                    }
-                    if (d - 1 > T && d - 1 <= from && nxt.aoff != NO_AUX) {
-                        /* diagonal d-1 is a total diagonal: its second term is the fold of F[d].M + B[d].M (:643-651) */
-                        aux[(size_t) nxt.aoff + (size_t) (nF + 1) * nxt.width + i] = pf[cell] + out[0];
-                    }
-                }
-                if (lane == 0) {
-                    double rec[NB];
+                        double t = f[0] + out[0];
 #pragma unroll
-                    for (int k = 0; k < NB; k++) rec[k] = ownNew[BwdShare<S>::state(k)];
-                    store_record<NB>(bOut + (size_t) (d & rm) * BND_REC, rec);
+                        for (int k = 1; k < S; k++) t = log_add(t, f[k] + out[k], la);
+                        aux[(size_t) cur.aoff + (size_t) nF * cur.width + i] = t;
+                    }
                 }
-                recvM = rcv[0]; /* M of (x+1, .) on diagonal d+1 is the middle neighbour of the next step */
-                cur = nxt;
+                /* diagonal d-1 is a total diagonal: its second term is the fold of F[d].M + B[d].M (:643-651) */
+                if (feeds) aux[(size_t) nxt.aoff + (size_t) (nF + 1) * nxt.width + i] = fm + out[0];
             };
 
             int d = dHi;
-            for (; d - 1 >= dLo; d -= 2) {
-                step(d, ownA, ownB);
-                step(d - 1, ownB, ownA);
+            DiagRec cur = dg[d];
+            if (d == top) {
+                /* the block's top diagonal holds the end vector (impl/pairwiseAligner.c:798-799) */
+                const DiagRec nxt = dg[d - 1];
+                const bool inBand = (unsigned) (x - ((d + cur.xmyL) >> 1)) < (unsigned) cur.width;
+                double out[S];
+#pragma unroll
+                for (int k = 0; k < S; k++) out[k] = inBand ? endVec[k] : CPB_NEG_INF;
+                emit(d, cur, nxt, inBand, out);
+                send[0] = CPB_NEG_INF;
+#pragma unroll
+                for (int k = 1; k < NSH; k++) send[k] = out[BwdShare<S>::state(k)];
+                if (lane == 0) store_record<NSH>(bOut + (size_t) (d & rm) * BND_REC, send);
+                if (lane == 31) {
+                    const bool ok = d >= prevLo && d <= prevHi && (unsigned) (x - ((d - 1 + nxt.xmyL) >> 1)) < (unsigned) nxt.width;
+                    load_record<NSH>(bNext, ok ? bIn + (size_t) (d & rm) * BND_REC : sa.negRecord);
+                }
+#pragma unroll
+                for (int k = 0; k < S; k++) own[k] = out[k];
+                cur = nxt;
+                d--;
+            } else if (lane == 31) {
+                /* message for diagonal dHi from row x+1 (the strip processed before this one) */
+                const int t = d + 1;
+                const bool ok = t >= prevLo && t <= prevHi && (unsigned) (x - ((d + cur.xmyL) >> 1)) < (unsigned) cur.width;
+                load_record<NSH>(bNext, ok ? bIn + (size_t) (t & rm) * BND_REC : sa.negRecord);
             }
-            if (d >= dLo) step(d, ownA, ownB);
+            int cY = d >= dLo ? ptrY[d] : 4;
+
+#pragma unroll 2
+            for (; d >= dLo; d--) {
+                const DiagRec nxt = dg[d - 1]; /* d-1 >= T >= 0 */
+                const int cYnow = cY;
+                cY = ptrY[d - 1];
+                const bool inBand = (unsigned) (x - ((d + cur.xmyL) >> 1)) < (unsigned) cur.width;
+                const bool useShfl = inBand && lane != 31;
+                double rcv[NSH];
+#pragma unroll
+                for (int k = 0; k < NSH; k++) {
+                    const double v = shfl_down_f64(send[k]);
+                    rcv[k] = useShfl ? v : bNext[k];
+                }
+                if (lane == 31) {
+                    const bool ok = d >= prevLo && d <= prevHi && (unsigned) (x - ((d - 1 + nxt.xmyL) >> 1)) < (unsigned) nxt.width;
+                    load_record<NSH>(bNext, ok ? bIn + (size_t) (d & rm) * BND_REC : sa.negRecord);
+                }
+                const int cYeff = inBand ? cYnow : 5;
+                double tm[NM], tu[NU], out[S];
+                load_row<NM>(tm, tab.tm[cXn6 + cYeff]);
+                load_row<NU>(tu, tab.tu[cYeff]);
+                cell_backward<S>(out, rcv[0], own, rcv + 1, tm, tu, tl, la);
+                emit(d, cur, nxt, inBand, out);
+                /* message for diagonal d-1: M of the cell two diagonals up, gap-X states of this one */
+                send[0] = own[0];
+#pragma unroll
+                for (int k = 1; k < NSH; k++) send[k] = out[BwdShare<S>::state(k)];
+                if (lane == 0) store_record<NSH>(bOut + (size_t) (d & rm) * BND_REC, send);
+#pragma unroll
+                for (int k = 0; k < S; k++) own[k] = out[k];
+                cur = nxt;
+            }
+            if (lane == 0) {
+                /* M of the last diagonal is the middle neighbour of diagonal dLo - 2 */
+                double last[NSH];
+                last[0] = own[0];
+#pragma unroll
+                for (int k = 1; k < NSH; k++) last[k] = CPB_NEG_INF;
+                store_record<NSH>(bOut + (size_t) ((dLo - 1) & rm) * BND_REC, last);
+            }
             prevHi = dHi;
-            prevLo = dLo;
+            prevLo = dLo - 1;
             __syncwarp();
         }
     }
