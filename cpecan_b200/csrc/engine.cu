@@ -308,7 +308,7 @@ static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
             stripBase += (R.lX >> 5) + 1;
             /* consecutive traceback points are at least minDiags - (traceBack+1) diagonals apart (T moves to d - traceBack - 1) */
             R.blockCap = (int32_t) (N / (p->minDiagsBetweenTraceBack - p->traceBackDiagonals - 1) + 2);
-            diagBase += N + 2;
+            diagBase += N + 3; /* lX+lY+1 diagonals and two sentinels */
             blockBase += R.blockCap;
             b->hRegions.push_back(R);
         }
@@ -391,9 +391,9 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         CUDA_TRY(cudaStreamSynchronize(st));
         return CPB_OK;
     }
-    const int64_t nDiagRecs = regs.back().diagBase + regs.back().lX + regs.back().lY + 2;
+    const int64_t nDiagRecs = regs.back().diagBase + regs.back().lX + regs.back().lY + 3;
     const int64_t blockSlots = regs.back().blockBase + regs.back().blockCap;
-    stx.diagonals = nDiagRecs - 2 * nReg + nReg; /* lX+lY+1 per region */
+    stx.diagonals = nDiagRecs - 2 * nReg; /* lX+lY+1 per region */
 
     if ((rc = b->regions.reserve(nReg * sizeof(RegionDev))) != CPB_OK) return rc;
     if ((rc = b->diags.reserve(nDiagRecs * sizeof(DiagRec))) != CPB_OK) return rc;
@@ -822,7 +822,7 @@ extern "C" int cpb_band(cpb_context *ctx, const int64_t *anchors, int64_t nAncho
     const int64_t N = lX + lY;
     DevBuf dRegion, dDiags, dBlocks, dAnch, dStrips;
     int rc;
-    if ((rc = dRegion.reserve(sizeof(RegionDev))) != CPB_OK || (rc = dDiags.reserve((N + 2) * sizeof(DiagRec))) != CPB_OK ||
+    if ((rc = dRegion.reserve(sizeof(RegionDev))) != CPB_OK || (rc = dDiags.reserve((N + 3) * sizeof(DiagRec))) != CPB_OK ||
         (rc = dBlocks.reserve(sizeof(BlockRec))) != CPB_OK || (rc = dAnch.reserve(std::max<int64_t>(nAnchors, 1) * 3 * sizeof(int32_t))) != CPB_OK)
         return rc;
     std::vector<int32_t> a32(3 * std::max<int64_t>(nAnchors, 1), 0);

@@ -39,7 +39,7 @@ struct __align__(16) DiagRec {
 struct RegionDev {
     int64_t xBase, yBase;  /* first symbol of the region in the symbol arrays */
     int64_t anchorBase;    /* first anchor triple */
-    int64_t diagBase;      /* first DiagRec; lX+lY+2 records */
+    int64_t diagBase;      /* first DiagRec; lX+lY+3 records (two sentinels) */
     int64_t blockBase;     /* first BlockRec slot */
     int64_t cellBase;      /* chunk-relative first cell (host, after planning) */
     int64_t auxBase;       /* chunk-relative first aux double (host, after planning) */
@@ -103,40 +103,54 @@ __constant__ double c_coefficients[16] = {
     (double) -0.000458661602210f, (double) 0.009695946122598f, (double) 0.930734667215156f, (double) 0.168037164329057f };
 
 /*
- * Segment selection without FP64 compares.  The segment bounds 1, 2.5, 4.5 and the cut-off 7.5 all have a zero low
- * word and a high word that is a multiple of 2^17, so for d >= 0:  d > T  <=>  hi32(bits(d) - 1) >= hi32(T), and
- * r = (hi32(bits(d) - 1) >> 17) - 0x1FF7 counts 2^17-wide buckets above 1.0.  A shared-memory table of LA_ROWS rows
- * maps the clamped bucket to its coefficients: row 0: d <= 1; rows 1-10: (1, 2.5]; rows 11-17: (2.5, 4.5];
- * rows 18-24: above 4.5 (the polynomial is discarded from 7.5 on).
+ * Segment selection by table.  The segment bounds 1, 2.5 and 4.5 have a zero low word and a high word that is a
+ * multiple of 2^17, so for d >= 0:  d > T  <=>  hi32(bits(d) - 1) >= hi32(T), and (hi32(bits(d) - 1) >> 17) - 0x1FF8
+ * counts 2^17-wide buckets above 1.0.  A shared-memory table of LA_ROWS rows
+ * maps the clamped bucket to its coefficients: rows 0-9: (1, 2.5]; rows 10-16: (2.5, 4.5]; rows 17-23: above 4.5 (the
+ * polynomial is discarded from 7.5 on); row 24: d <= 1 (and, harmlessly, everything at or beyond the cut-off).
  */
 constexpr int LA_ROWS = 25;
+/* Shared-memory layout of the table: two planes ({a,b} and {c,k}) of LA_ROWS rows; every row is replicated for the
+ * 8 lanes of a quarter warp (8 x 16 bytes = all 32 banks), so a 128-bit fetch never has a bank conflict whatever
+ * rows the lanes pick. */
+constexpr int LA_ROW_DOUBLES = 16;                        /* 8 lanes x {2 doubles} */
+constexpr int LA_PLANE_DOUBLES = LA_ROWS * LA_ROW_DOUBLES;
+constexpr int LA_TABLE_DOUBLES = 2 * LA_PLANE_DOUBLES;    /* 6400 bytes */
 
 __device__ __forceinline__ void fill_logadd_rows(double *la, int tid, int nthreads) {
-    for (int i = tid; i < LA_ROWS * 4; i += nthreads) {
-        const int r = i >> 2;
-        const int seg = r == 0 ? 0 : (r <= 10 ? 1 : (r <= 17 ? 2 : 3));
-        la[i] = c_coefficients[4 * seg + (i & 3)];
+    for (int i = tid; i < LA_TABLE_DOUBLES; i += nthreads) {
+        const int plane = i / LA_PLANE_DOUBLES, r = (i % LA_PLANE_DOUBLES) / LA_ROW_DOUBLES, e = i & 1;
+        const int seg = r == LA_ROWS - 1 ? 0 : (r <= 9 ? 1 : (r <= 16 ? 2 : 3));
+        la[i] = c_coefficients[4 * seg + 2 * plane + e];
     }
 }
+/* the calling lane's view of the table: the shared-memory byte address of its own 16-byte column */
+typedef unsigned LaTable;
+__device__ __forceinline__ LaTable logadd_lane_table(const double *la) {
+    return (unsigned) __cvta_generic_to_shared(la) + 16u * (threadIdx.x & 7);
+}
 
-__device__ __forceinline__ double log_add(double x, double y, const double *__restrict__ la) {
+__device__ __forceinline__ double log_add(double x, double y, const LaTable la) {
     const double diff = __dsub_rn(x, y);
-    const int hi = __double2hiint(diff);
-    const bool xSmaller = hi < 0; /* sign of x-y; both -inf gives NaN, handled below */
+    const bool xSmaller = __double2hiint(diff) < 0; /* sign of x-y; both -inf gives NaN, handled below */
     const double big = xSmaller ? y : x;
     const double small = xSmaller ? x : y;
-    const double d = fabs(diff); /* only feeds the multiplies (a free operand modifier); the bucket comes from the integer view */
-    const int hiAbs = hi & 0x7FFFFFFF;
-    const int hi3 = (int) (((long long) (((unsigned long long) (unsigned) hiAbs << 32) | (unsigned) __double2loint(diff)) - 1LL) >> 32); /* hi32(bits(|diff|) - 1) */
-    const int r = min(max((hi3 >> 17) - 0x1FF7, 0), LA_ROWS - 1);
-    const double2 ab = *reinterpret_cast<const double2 *>(la + 4 * r);
-    const double2 ck = *reinterpret_cast<const double2 *>(la + 4 * r + 2);
-    double p = __dadd_rn(__dmul_rn(ab.x, d), ab.y);
-    p = __dadd_rn(__dmul_rn(p, d), ck.x);
-    p = __dadd_rn(__dmul_rn(p, d), ck.y);
+    const double d = fabs(diff); /* a free operand modifier */
+    /* bits(d) - 1 in one FP64 instruction: d minus the smallest denormal, rounded down, is the predecessor of d
+     * (d = 0 gives a negative number, which like NaN and +inf ends up in the last row after the unsigned clamp) */
+    const int hi3 = __double2hiint(__dadd_rd(d, -4.9406564584124654e-324));
+    const unsigned r = min((unsigned) ((hi3 >> 17) - 0x1FF8), (unsigned) (LA_ROWS - 1));
+    /* lanes at or beyond the cut-off all land in the last row, so they share one address per bank group */
+    double a, b, c, k;
+    asm("ld.shared.v2.f64 {%0, %1}, [%4];\n\tld.shared.v2.f64 {%2, %3}, [%4+%5];"
+        : "=d"(a), "=d"(b), "=d"(c), "=d"(k)
+        : "r"(la + (unsigned) (LA_ROW_DOUBLES * 8) * r), "n"(LA_PLANE_DOUBLES * 8));
+    double p = __dadd_rn(__dmul_rn(a, d), b);
+    p = __dadd_rn(__dmul_rn(p, d), c);
+    p = __dadd_rn(__dmul_rn(p, d), k);
     p = __dadd_rn(p, small);
     /* d >= 7.5, d = +inf (one side is LOG_ZERO) and d = NaN (both are) all return the larger operand */
-    return hiAbs < 0x401E0000 ? p : big;
+    return d < 7.5 ? p : big;
 }
 
 #define CPB_NEG_INF (__longlong_as_double(0xFFF0000000000000LL))
@@ -201,9 +215,10 @@ template <int S> __host__ __device__ constexpr int upper_to(int k) { return S ==
  * cells of the diagonal (dpDiagonal_dotProduct, :513-523), so lanes run independent folds in parallel.
  * ------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(128) k_totals(const DpArgs a, int nBlocks) {
-    __shared__ __align__(16) double ctab[LA_ROWS * 4];
-    fill_logadd_rows(ctab, threadIdx.x, blockDim.x);
+    __shared__ __align__(16) double laTable[LA_TABLE_DOUBLES];
+    fill_logadd_rows(laTable, threadIdx.x, blockDim.x);
     __syncthreads();
+    const LaTable ctab = logadd_lane_table(laTable);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= nBlocks) return;
     const BlockRec K = a.blocks[a.list[warp]];
@@ -650,6 +665,7 @@ __global__ void k_band(const BandArgs b) {
     sentinel.coff = (uint32_t) coff;
     sentinel.aoff = NO_AUX;
     dg[N + 1] = sentinel;
+    dg[N + 2] = sentinel;
 
     int nBlocks = 0;
     int64_t auxD = 0;

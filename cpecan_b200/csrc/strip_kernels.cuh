@@ -12,8 +12,8 @@
  * x-1, i.e. lane l-1: that lane folds them itself -- with the destination cell's emissions, which it knows
  * (the next row's symbol is fixed per strip, the next column's symbol is the one it fetches anyway) -- in
  * the reference's order, and hands over only the finished sums: one message of NSH = 3 (2) doubles per
- * diagonal instead of all S states twice.  A message is {m'(d-1), g'(d)}: the middle fold is held back one
- * step so that everything in a message belongs to diagonal d+1.
+ * diagonal instead of all S states twice.  A message is {m'(d-1), g'(d)}: everything in it belongs to diagonal d+1,
+ * and the long middle fold of cell d-1 is evaluated during step d, where it overlaps the short folds of cell d.
  * Backward (gather form of the reference's scatter) needs B.M of (x+1,y+1) and
  * the gap-X states of (x+1,y): the same message shape, shuffled down.
  *
@@ -39,29 +39,33 @@ struct StripArgs {
     unsigned int *counter;    /* work-fetch counter (zeroed before the launch) */
 };
 
+/* compile-time flags for the step lambdas */
+struct Yes { static constexpr bool value = true; };
+struct No { static constexpr bool value = false; };
+
 template <int S> struct Msg;
 template <> struct Msg<5> { static constexpr int N = 3; };
 template <> struct Msg<3> { static constexpr int N = 2; };
 
-/* per-CTA tables; symbol index 5 = "cell outside the band": its emissions are LOG_ZERO */
+/* per-CTA tables; symbol index 5 = "cell outside the band": its emissions are LOG_ZERO.  eM / eY are replicated for the
+ * 16 lanes of a half warp (16 x 8 bytes = all 32 banks): 64-bit fetches of different entries never conflict. */
 template <int S> struct StripTables {
-    double la[LA_ROWS * 4];
-    double tm[36][6];             /* [cX*6+cY][k] eMatch + tMiddle[k] (k < NM) */
-    double tu[6][4];              /* [cY][k]      eGapY + tUpper[k] */
-    double tl[6][4];              /* [cX][k]      eGapX + tLower[k] */
+    double la[LA_TABLE_DOUBLES];
+    double eM[36][16];            /* [cX*6+cY][lane&15] match emission */
+    double eY[6][16];             /* [cY][lane&15]      gap-Y emission */
+    double tl[6][4];              /* [cX][k]            eGapX + tLower[k] (fetched once per strip) */
     double startv[5], rstartv[5], endv[5], rendv[5];
 };
 
 template <int S> __device__ __forceinline__ void fill_strip_tables(StripTables<S> &t, const CpbModel &m, int tid, int nthreads) {
     fill_logadd_rows(t.la, tid, nthreads);
-    for (int i = tid; i < 36 * 6; i += nthreads) {
-        const int c = i / 6, k = i % 6, cX = c / 6, cY = c % 6;
-        const double e = (cX < 5 && cY < 5) ? m.eMatch[cX * 5 + cY] : CPB_NEG_INF;
-        t.tm[c][k] = k < Shape<S>::NM ? e + m.tMiddle[k] : 0.0;
+    for (int i = tid; i < 36 * 16; i += nthreads) {
+        const int c = i / 16, cX = c / 6, cY = c % 6;
+        t.eM[c][i % 16] = (cX < 5 && cY < 5) ? m.eMatch[cX * 5 + cY] : CPB_NEG_INF;
     }
+    for (int i = tid; i < 6 * 16; i += nthreads) t.eY[i / 16][i % 16] = i / 16 < 5 ? m.eGapY[i / 16] : CPB_NEG_INF;
     for (int i = tid; i < 6 * 4; i += nthreads) {
         const int c = i / 4, k = i % 4;
-        t.tu[c][k] = k < Shape<S>::NU ? (c < 5 ? m.eGapY[c] : CPB_NEG_INF) + m.tUpper[k] : 0.0;
         t.tl[c][k] = k < Shape<S>::NL ? (c < 5 ? m.eGapX[c] : CPB_NEG_INF) + m.tLower[k] : 0.0;
     }
     if (tid < S) {
@@ -99,19 +103,23 @@ template <int N> __device__ __forceinline__ void load_row(double *v, const doubl
     if (N > 4) v[4] = row[4];
 }
 
-/* the folds a source cell performs for the cell below-right (middle group) and below (lower group), in the
+/* the folds a source cell performs for the cell below-right (middle group: m) and below (lower group: g), in the
  * reference's transition order; `c` = the source cell's S states */
-template <int S>
-__device__ __forceinline__ void forward_contributions(double &m, double *g, const double *c, const double *tm, const double *tl, const double *la) {
+template <int S> __device__ __forceinline__ double middle_fold(const double *c, const double *tm, const LaTable la) {
     if constexpr (S == 5) {
         double v = log_add(c[0] + tm[0], c[1] + tm[1], la);
         v = log_add(v, c[2] + tm[2], la);
         v = log_add(v, c[3] + tm[3], la);
-        m = log_add(v, c[4] + tm[4], la);
+        return log_add(v, c[4] + tm[4], la);
+    } else {
+        return log_add(log_add(c[0] + tm[0], c[1] + tm[1], la), c[2] + tm[2], la);
+    }
+}
+template <int S> __device__ __forceinline__ void lower_folds(double *g, const double *c, const double *tl, const LaTable la) {
+    if constexpr (S == 5) {
         g[0] = log_add(c[0] + tl[0], c[1] + tl[1], la); /* -> shortGapX */
         g[1] = log_add(c[0] + tl[2], c[3] + tl[3], la); /* -> longGapX */
     } else {
-        m = log_add(log_add(c[0] + tm[0], c[1] + tm[1], la), c[2] + tm[2], la);
         g[0] = log_add(log_add(c[0] + tl[0], c[1] + tl[1], la), c[2] + tl[2], la); /* -> gapX */
     }
 }
@@ -125,7 +133,8 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
     fill_strip_tables<S>(tab, model, threadIdx.x, 32 * WPC);
     __syncthreads();
     constexpr int NSH = Msg<S>::N, NL = Shape<S>::NL, NM = Shape<S>::NM, NU = Shape<S>::NU;
-    const double *la = tab.la;
+    const LaTable la = logadd_lane_table(tab.la);
+    const int l16 = threadIdx.x & 15;
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * WPC + (threadIdx.x >> 5);
     const int rm = sa.ringSize - 1;
@@ -164,7 +173,7 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
             double *bOut = (s & 1) ? ring1 : ring0;
             const double *bIn = (s & 1) ? ring0 : ring1;
 
-            double own[S], send[NSH], bNext[NSH], mDelay = CPB_NEG_INF;
+            double own[S], send[NSH], bNext[NSH];
 #pragma unroll
             for (int k = 0; k < S; k++) own[k] = CPB_NEG_INF;
 #pragma unroll
@@ -181,11 +190,8 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
                         if (k < NP) pf[(int64_t) k * a.planeStride] = sv[k];
                     }
                 }
-                double tmD[NM], mNew;
-                load_row<NM>(tmD, tab.tm[cXn6 + ptrY[0]]);
-                forward_contributions<S>(mNew, send + 1, own, tmD, tlD, la);
+                lower_folds<S>(send + 1, own, tlD, la); /* the middle fold of this cell is evaluated by step 1 */
                 send[0] = CPB_NEG_INF;
-                mDelay = mNew;
                 if (lane == 31) store_record<NSH>(bOut, send);
                 d0 = 1;
             } else if (lane == 0) {
@@ -195,15 +201,17 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
                 const bool ok = t >= prevFirst && t <= prevLast && (unsigned) (x - ((d0 + r0.xmyL) >> 1)) < (unsigned) r0.width;
                 load_record<NSH>(bNext, ok ? bIn + (size_t) (t & rm) * BND_REC : sa.negRecord);
             }
-            DiagRec cur = dg[d0 <= N ? d0 : N];
-            int cY = ptrY[d0 - 1]; /* symbol of column d0 - x */
+            /* diagonal records and column symbols are fetched two steps ahead (records N+1, N+2 are sentinels) */
+            DiagRec cur = dg[d0 <= N ? d0 : N], nxt = dg[d0 <= N ? d0 + 1 : N + 1];
+            int cYnow = ptrY[d0 - 1], cYnext = ptrY[d0]; /* symbols of columns d0 - x and d0 + 1 - x */
 
-#pragma unroll 2
-            for (int d = d0; d <= sr.dLast; d++) {
-                const DiagRec nxt = dg[d + 1]; /* prefetch (record N+1 is a sentinel) */
-                const int cYnow = cY;
-                cY = ptrY[d];
-                const bool inBand = (unsigned) (x - ((d + cur.xmyL) >> 1)) < (unsigned) cur.width;
+            /* One diagonal step.  Reads own = cell of d-1, leaves own = cell of d.  Without AUX the body has no branch (the plane
+             * store is predicated), so the two steps of a pair form one scheduling block and the long middle fold of one
+             * overlaps the short critical path of the next.  AUX: d is a "total" diagonal whose full cells are kept. */
+            auto step = [&](auto auxTag, const int d, const DiagRec &cur, const DiagRec &nxt, const int cYnow) {
+                constexpr bool AUX = decltype(auxTag)::value;
+                const int i = x - ((d + cur.xmyL) >> 1);
+                const bool inBand = (unsigned) i < (unsigned) cur.width;
                 const bool useShfl = inBand && lane != 0;
                 double rcv[NSH];
 #pragma unroll
@@ -211,13 +219,22 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
                     const double v = shfl_up_f64(send[k]);
                     rcv[k] = useShfl ? v : bNext[k]; /* lanes other than 0 keep LOG_ZERO in bNext: this is also the band mask */
                 }
-                if (lane == 0) {
-                    /* prefetch the message for diagonal d+1; LOG_ZERO if the previous strip had none or (0, d+1) is outside the band */
+                {
+                    /* lane 0 prefetches the message for diagonal d+1; LOG_ZERO if the previous strip had none or (x, d+1-x) is outside the band */
                     const bool ok = d >= prevFirst && d <= prevLast && (unsigned) (x - ((d + 1 + nxt.xmyL) >> 1)) < (unsigned) nxt.width;
-                    load_record<NSH>(bNext, ok ? bIn + (size_t) (d & rm) * BND_REC : sa.negRecord);
+                    const double *rec = ok ? bIn + (size_t) (d & rm) * BND_REC : sa.negRecord;
+                    if (lane == 0) load_record<NSH>(bNext, rec);
                 }
-                double tu[NU];
-                load_row<NU>(tu, tab.tu[inBand ? cYnow : 5]);
+                /* the middle fold of the previous cell (own) for (x+1, d-x): its column symbol is this step's cYnow */
+                double tmD[NM], tu[NU];
+                {
+                    const double eM = tab.eM[cXn6 + cYnow][l16], eY = tab.eY[inBand ? cYnow : 5][l16];
+#pragma unroll
+                    for (int k = 0; k < NM; k++) tmD[k] = eM + model.tMiddle[k];
+#pragma unroll
+                    for (int k = 0; k < NU; k++) tu[k] = eY + model.tUpper[k];
+                }
+                const double mPrev = middle_fold<S>(own, tmD, la);
                 /* the cell: middle and lower folds arrive finished; the upper group uses this lane's previous cell */
                 double out[S];
                 out[0] = rcv[0];
@@ -230,33 +247,54 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
                     out[2] = log_add(log_add(own[0] + tu[0], own[2] + tu[1], la), own[1] + tu[2], la);
                 }
                 if (inBand) {
-                    const int cell = (int) cur.coff + (x - ((d + cur.xmyL) >> 1)); /* < 2^31 cells per region is enforced on the host */
+                    const int cell = (int) cur.coff + i; /* < 2^31 cells per region is enforced on the host */
 #pragma unroll
                     for (int k = 0; k < NP; k++) pf[(int64_t) k * a.planeStride + cell] = out[k];
-                    if (keepFull && cur.aoff != NO_AUX) {
-                        const int i = x - ((d + cur.xmyL) >> 1);
+                    if (AUX) {
 #pragma unroll
                         for (int k = 0; k < S; k++) aux[(size_t) cur.aoff + (size_t) k * cur.width + i] = out[k];
                     }
                 }
-                /* this cell's folds for row x+1 */
-                double tmD[NM], mNew;
-                load_row<NM>(tmD, tab.tm[cXn6 + cY]);
-                send[0] = mDelay;
-                forward_contributions<S>(mNew, send + 1, out, tmD, tlD, la);
-                mDelay = mNew;
+                /* message for diagonal d+1: middle fold of cell d-1, lower folds of cell d */
+                send[0] = mPrev;
+                lower_folds<S>(send + 1, out, tlD, la);
                 if (lane == 31) store_record<NSH>(bOut + (size_t) (d & rm) * BND_REC, send);
 #pragma unroll
                 for (int k = 0; k < S; k++) own[k] = out[k];
-                cur = nxt;
+            };
+
+            for (int d = d0; d <= sr.dLast;) {
+                const bool auxA = keepFull && cur.aoff != NO_AUX, auxB = keepFull && nxt.aoff != NO_AUX; /* warp-uniform */
+                const DiagRec nxt2 = dg[d + 2];
+                const int cY2 = ptrY[d + 1];
+                if (d + 1 <= sr.dLast && !auxA && !auxB) {
+                    step(No(), d, cur, nxt, cYnow);
+                    step(No(), d + 1, nxt, nxt2, cYnext);
+                    cur = nxt2;
+                    nxt = dg[d + 3];
+                    cYnow = cY2;
+                    cYnext = ptrY[d + 2];
+                    d += 2;
+                } else {
+                    if (auxA) step(Yes(), d, cur, nxt, cYnow);
+                    else step(No(), d, cur, nxt, cYnow);
+                    cur = nxt;
+                    nxt = nxt2;
+                    cYnow = cYnext;
+                    cYnext = cY2;
+                    d++;
+                }
             }
-            if (lane == 31) {
-                /* the held-back middle fold of the last step belongs to diagonal dLast + 2 */
-                double last[NSH];
-                last[0] = mDelay;
+            {
+                /* the middle fold of the last cell belongs to diagonal dLast + 2; cYnow is by now the symbol of column dLast + 1 - x */
+                double tmD[NM], last[NSH];
+                const double eM = tab.eM[cXn6 + cYnow][l16];
+#pragma unroll
+                for (int k = 0; k < NM; k++) tmD[k] = eM + model.tMiddle[k];
+                last[0] = middle_fold<S>(own, tmD, la);
 #pragma unroll
                 for (int k = 1; k < NSH; k++) last[k] = CPB_NEG_INF;
-                store_record<NSH>(bOut + (size_t) ((sr.dLast + 1) & rm) * BND_REC, last);
+                if (lane == 31) store_record<NSH>(bOut + (size_t) ((sr.dLast + 1) & rm) * BND_REC, last);
             }
             if (NP == 0 && a.forwardOut != nullptr && s == nStrips - 1 && sr.dLast == N && N > 0 && lane == (R.lX & 31)) {
                 /* computeForwardProbability: the last cell dotted with the end vector (impl/pairwiseAligner.c:910-916) */
@@ -292,7 +330,7 @@ template <> struct BwdShare<3> {
  * middle of diagonal d+2, then upper-of (x-y-1) and lower-of (x-y+1) on diagonal d+1. */
 template <int S>
 __device__ __forceinline__ void cell_backward(double *out, double t2m, const double *u, const double *l, const double *tm, const double *tu,
-                                              const double *tl, const double *la) {
+                                              const double *tl, const LaTable la) {
     if constexpr (S == 5) {
         double m = log_add(t2m + tm[0], u[2] + tu[0], la);
         m = log_add(m, u[4] + tu[2], la);
@@ -315,7 +353,8 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_backward_str
     fill_strip_tables<S>(tab, model, threadIdx.x, 32 * WPC);
     __syncthreads();
     constexpr int NSH = Msg<S>::N, NL = Shape<S>::NL, NM = Shape<S>::NM, NU = Shape<S>::NU;
-    const double *la = tab.la;
+    const LaTable la = logadd_lane_table(tab.la);
+    const int l16 = threadIdx.x & 15;
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * WPC + (threadIdx.x >> 5);
     const int rm = sa.ringSize - 1;
@@ -363,21 +402,25 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_backward_str
 #pragma unroll
             for (int k = 0; k < NSH; k++) send[k] = bNext[k] = CPB_NEG_INF;
 
-            /* everything a finished cell has to leave in HBM */
-            auto emit = [&](const int d, const DiagRec &cur, const DiagRec &nxt, const bool inBand, const double(&out)[S]) {
+            /* everything a finished cell has to leave in HBM; fm = the F values of the cell (planes 0..NP-1), fetched a step ahead.
+             * PLAIN: an owned diagonal that is neither a total diagonal nor the one above one -- only the plane store remains. */
+            auto emit = [&](auto plainTag, const int d, const DiagRec &cur, const DiagRec &nxt, const bool inBand, const int i, const double(&out)[S],
+                            const double *fm) {
+                constexpr bool PLAIN = decltype(plainTag)::value;
                 if (!inBand) return;
-                const int i = x - ((d + cur.xmyL) >> 1);
                 const int cell = (int) cur.coff + i;
+                if (PLAIN) {
+#pragma unroll
+                    for (int k = 0; k < NP; k++) pb[(int64_t) k * a.planeStride + cell] = ZSUM ? fm[k] + out[k] : out[k];
+                    return;
+                }
                 const bool owned = d <= from;
                 const bool feeds = d - 1 > T && d - 1 <= from && nxt.aoff != NO_AUX; /* d-1 is a total diagonal */
-                double fm = 0.0;
-                if ((ZSUM && owned) || feeds) fm = pf[cell];
+                double f0 = fm[0];
+                if (!ZSUM && feeds) f0 = pf[cell];
                 if (owned) {
 #pragma unroll
-                    for (int k = 0; k < NP; k++) {
-                        if (ZSUM) pb[(int64_t) k * a.planeStride + cell] = (k == 0 ? fm : pf[(int64_t) k * a.planeStride + cell]) + out[k];
-                        else pb[(int64_t) k * a.planeStride + cell] = out[k];
-                    }
+                    for (int k = 0; k < NP; k++) pb[(int64_t) k * a.planeStride + cell] = ZSUM ? fm[k] + out[k] : out[k];
                     if (cur.aoff != NO_AUX) {
                         /* cell_dotProduct(F[d], B[d]) (impl/pairwiseAligner.c:402-408); folded over the cells by k_totals */
                         double f[S];
@@ -395,19 +438,34 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_backward_str
                     }
                 }
                 /* diagonal d-1 is a total diagonal: its second term is the fold of F[d].M + B[d].M (:643-651) */
-                if (feeds) aux[(size_t) nxt.aoff + (size_t) (nF + 1) * nxt.width + i] = fm + out[0];
+                if (feeds) aux[(size_t) nxt.aoff + (size_t) (nF + 1) * nxt.width + i] = f0 + out[0];
+            };
+            /* F of this lane's cell on diagonal `rec` (clamped into the diagonal, so the address is always valid) */
+            constexpr int NFM = ZSUM && NP > 0 ? NP : 1;
+            auto fetch_f = [&](const int dd, const DiagRec &rec, double *fm) {
+                if (ZSUM && NP > 0) {
+                    const int ii = min(max(x - ((dd + rec.xmyL) >> 1), 0), rec.width - 1);
+#pragma unroll
+                    for (int k = 0; k < NFM; k++) fm[k] = pf[(int64_t) k * a.planeStride + (int) rec.coff + ii];
+                }
             };
 
             int d = dHi;
-            DiagRec cur = dg[d];
+            DiagRec cur = dg[d], nxt = dg[d - 1]; /* d - 1 >= T >= 0 */
+            double fNext[NFM];
+#pragma unroll
+            for (int k = 0; k < NFM; k++) fNext[k] = 0.0;
             if (d == top) {
                 /* the block's top diagonal holds the end vector (impl/pairwiseAligner.c:798-799) */
-                const DiagRec nxt = dg[d - 1];
-                const bool inBand = (unsigned) (x - ((d + cur.xmyL) >> 1)) < (unsigned) cur.width;
-                double out[S];
+                const int i = x - ((d + cur.xmyL) >> 1);
+                const bool inBand = (unsigned) i < (unsigned) cur.width;
+                double out[S], fm[NFM];
+#pragma unroll
+                for (int k = 0; k < NFM; k++) fm[k] = 0.0;
+                fetch_f(d, cur, fm);
 #pragma unroll
                 for (int k = 0; k < S; k++) out[k] = inBand ? endVec[k] : CPB_NEG_INF;
-                emit(d, cur, nxt, inBand, out);
+                emit(No(), d, cur, nxt, inBand, i, out, fm);
                 send[0] = CPB_NEG_INF;
 #pragma unroll
                 for (int k = 1; k < NSH; k++) send[k] = out[BwdShare<S>::state(k)];
@@ -420,37 +478,49 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_backward_str
                 for (int k = 0; k < S; k++) own[k] = out[k];
                 cur = nxt;
                 d--;
+                nxt = dg[d > 0 ? d - 1 : 0];
             } else if (lane == 31) {
                 /* message for diagonal dHi from row x+1 (the strip processed before this one) */
                 const int t = d + 1;
                 const bool ok = t >= prevLo && t <= prevHi && (unsigned) (x - ((d + cur.xmyL) >> 1)) < (unsigned) cur.width;
                 load_record<NSH>(bNext, ok ? bIn + (size_t) (t & rm) * BND_REC : sa.negRecord);
             }
-            int cY = d >= dLo ? ptrY[d] : 4;
+            /* column symbols, diagonal records and F values are fetched ahead of the step that uses them */
+            int cYnow = ptrY[d], cYnext = ptrY[d - 1];
+            if (d >= dLo) fetch_f(d, cur, fNext);
 
-#pragma unroll 2
-            for (; d >= dLo; d--) {
-                const DiagRec nxt = dg[d - 1]; /* d-1 >= T >= 0 */
-                const int cYnow = cY;
-                cY = ptrY[d - 1];
-                const bool inBand = (unsigned) (x - ((d + cur.xmyL) >> 1)) < (unsigned) cur.width;
+            /* One diagonal step.  Reads own = cell of d+1, leaves own = cell of d; fetches the F values of the next step's cell.
+             * PLAIN steps have no branch, so the two steps of a pair form one scheduling block. */
+            auto step = [&](auto plainTag, const int d, const DiagRec &cur, const DiagRec &nxt, const int cYnow) {
+                const int i = x - ((d + cur.xmyL) >> 1);
+                const bool inBand = (unsigned) i < (unsigned) cur.width;
                 const bool useShfl = inBand && lane != 31;
+                double fm[NFM];
+#pragma unroll
+                for (int k = 0; k < NFM; k++) fm[k] = fNext[k];
+                fetch_f(d - 1, nxt, fNext);
                 double rcv[NSH];
 #pragma unroll
                 for (int k = 0; k < NSH; k++) {
                     const double v = shfl_down_f64(send[k]);
                     rcv[k] = useShfl ? v : bNext[k];
                 }
-                if (lane == 31) {
+                {
                     const bool ok = d >= prevLo && d <= prevHi && (unsigned) (x - ((d - 1 + nxt.xmyL) >> 1)) < (unsigned) nxt.width;
-                    load_record<NSH>(bNext, ok ? bIn + (size_t) (d & rm) * BND_REC : sa.negRecord);
+                    const double *rec = ok ? bIn + (size_t) (d & rm) * BND_REC : sa.negRecord;
+                    if (lane == 31) load_record<NSH>(bNext, rec);
                 }
                 const int cYeff = inBand ? cYnow : 5;
                 double tm[NM], tu[NU], out[S];
-                load_row<NM>(tm, tab.tm[cXn6 + cYeff]);
-                load_row<NU>(tu, tab.tu[cYeff]);
+                {
+                    const double eM = tab.eM[cXn6 + cYeff][l16], eY = tab.eY[cYeff][l16];
+#pragma unroll
+                    for (int k = 0; k < NM; k++) tm[k] = eM + model.tMiddle[k];
+#pragma unroll
+                    for (int k = 0; k < NU; k++) tu[k] = eY + model.tUpper[k];
+                }
                 cell_backward<S>(out, rcv[0], own, rcv + 1, tm, tu, tl, la);
-                emit(d, cur, nxt, inBand, out);
+                emit(plainTag, d, cur, nxt, inBand, i, out, fm);
                 /* message for diagonal d-1: M of the cell two diagonals up, gap-X states of this one */
                 send[0] = own[0];
 #pragma unroll
@@ -458,7 +528,33 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_backward_str
                 if (lane == 0) store_record<NSH>(bOut + (size_t) (d & rm) * BND_REC, send);
 #pragma unroll
                 for (int k = 0; k < S; k++) own[k] = out[k];
-                cur = nxt;
+            };
+            /* a diagonal is plain if it is owned, not a total diagonal, and the diagonal below it is not one either */
+            auto plain = [&](const int dd, const DiagRec &rec, const DiagRec &below) {
+                return dd <= from && rec.aoff == NO_AUX && !(dd - 1 > T && below.aoff != NO_AUX);
+            };
+
+            while (d >= dLo) {
+                const DiagRec nxt2 = dg[d >= 2 ? d - 2 : 0];
+                const int cY2 = ptrY[d - 2];
+                const bool plainA = plain(d, cur, nxt); /* warp-uniform */
+                if (d - 1 >= dLo && plainA && plain(d - 1, nxt, nxt2)) {
+                    step(Yes(), d, cur, nxt, cYnow);
+                    step(Yes(), d - 1, nxt, nxt2, cYnext);
+                    cur = nxt2;
+                    nxt = dg[d >= 3 ? d - 3 : 0];
+                    cYnow = cY2;
+                    cYnext = ptrY[d - 3];
+                    d -= 2;
+                } else {
+                    if (plainA) step(Yes(), d, cur, nxt, cYnow);
+                    else step(No(), d, cur, nxt, cYnow);
+                    cur = nxt;
+                    nxt = nxt2;
+                    cYnow = cYnext;
+                    cYnext = cY2;
+                    d--;
+                }
             }
             if (lane == 0) {
                 /* M of the last diagonal is the middle neighbour of diagonal dLo - 2 */
