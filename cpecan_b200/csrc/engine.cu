@@ -496,7 +496,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             c.region1 = r;
             c.cells = cells;
             c.aux = aux;
-            c.maskWords = words;
+            c.maskWords = words; /* provisional; final value below once the decades are counted */
             c.stride = (cells + 31) & ~int64_t(31);
             c.block0 = regionBlock0[c.region0];
             c.block1 = regionBlock0[c.region1];
@@ -509,6 +509,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
                 dec += (hBlocks[k].from - hBlocks[k].T + 9) / 10;
             }
             c.decades = dec;
+            c.maskWords = (c.cells >> 5) + dec + 2; /* k_posterior: word of chunk cell C in decade g is (C >> 5) + g */
             chunks.push_back(c);
         }
     }

@@ -245,13 +245,18 @@ __global__ void __launch_bounds__(128) k_totals(const DpArgs a, int nBlocks) {
 
 /* ---------------------------------------------------------------------------------------------
  * k_posterior : one CTA of POST_WARPS warps per block, one warp per decade at a time.
- *   WRITE == false : evaluates exp(F+B-total) >= threshold for every owned cell (addPosteriorProb,
- *                    impl/pairwiseAligner.c:655-664), stores one ballot word per 32 cells and the
- *                    number of kept cells of the decade;
+ * The cells of a decade (10 owned diagonals sharing one totalProbability) are one contiguous range of the F+B
+ * plane, so the scan is a flat, coalesced sweep:
+ *   WRITE == false : evaluates exp(F+B-total) >= threshold for every cell (addPosteriorProb,
+ *                    impl/pairwiseAligner.c:655-664), stores one ballot word per 32 cells and the number of kept
+ *                    cells of the decade; cells on the matrix border (x = 0 / y = 0, which the reference skips,
+ *                    :672, :700-729) are then struck out again -- at most two per diagonal;
  *   (device scan of the decade counts)
- *   WRITE == true  : revisits only the set bits and writes (pInt, x, y) at the decade's offset.
- * Decades are numbered in ascending-diagonal order inside a block, so the output of a region is
- * sorted by (x+y, x).
+ *   WRITE == true  : revisits only the set bits, recovers (x, y) from the diagonal records and writes
+ *                    (pInt, x, y) at the decade's offset.
+ * Decades are numbered in ascending-diagonal order inside a block, so the output of a region is sorted by
+ * (x+y, x).  Mask word of chunk-relative cell C in decade g: (C >> 5) + g -- the "+ g" keeps neighbouring
+ * decades, whose cell ranges may share a 32-cell group, in different words.
  * ------------------------------------------------------------------------------------------- */
 constexpr int POST_WARPS = 8;
 
@@ -268,6 +273,16 @@ struct PostArgs {
     int32_t *out[3];
 };
 
+__device__ __forceinline__ bool posterior_keep(double z, double total, const PostArgs &p, int &pInt) {
+    const double lp = z - total;
+    if (!(lp >= p.logThresholdLo)) return false;
+    double pr = exp(lp);
+    if (!(pr >= p.threshold)) return false;
+    if (pr > 1.0) pr = 1.0;
+    pInt = (int) floor(pr * (double) CPB_PAIR_ALIGNMENT_PROB_1);
+    return true;
+}
+
 template <bool WRITE>
 __global__ void __launch_bounds__(32 * POST_WARPS) k_posterior(const DpArgs a, const PostArgs p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -276,66 +291,92 @@ __global__ void __launch_bounds__(32 * POST_WARPS) k_posterior(const DpArgs a, c
     const DiagRec *dg = a.diags + R.diagBase;
     const double *tot = a.totals + R.diagBase;
     const int nDecades = (K.from - K.T + 9) / 10;
-    const unsigned ltMask = (1u << lane) - 1u;
     for (int j = warp; j < nDecades; j += POST_WARPS) {
         const int dt = K.from - 10 * j;                       /* the decade's total diagonal (its highest) */
         const int64_t g = K.decadeBase + (nDecades - 1 - j);  /* ascending-diagonal numbering */
         const double total = tot[dt];
-        const int dLow = max(dt - 9, K.T + 1);
-        int64_t run[3] = { 0, 0, 0 };
-        if (WRITE) {
-            for (int l = 0; l < p.nLists; l++) run[l] = p.offsets[(int64_t) l * p.nDecades + g];
-        }
-        for (int d = dLow; d <= dt; d++) {
-            const DiagRec rec = dg[d];
-            const int64_t word0 = R.maskBase + (rec.coff >> 5) + d;
-            for (int i0 = 0; i0 < rec.width; i0 += 32) {
-                const int i = i0 + lane;
-                const bool valid = i < rec.width;
-                const int xmy = rec.xmyL + 2 * i;
-                const int x = (d + xmy) >> 1, y = (d - xmy) >> 1;
-                const int64_t cell = R.cellBase + (int64_t) rec.coff + i;
-                const int64_t word = word0 + (i0 >> 5);
-                for (int l = 0; l < p.nLists; l++) {
-                    /* list 0: match (x>0 && y>0); 1: gapX (x>0); 2: gapY (y>0) -- planes 0,1,2 are M, gapX, gapY */
-                    unsigned m;
-                    bool keep = false;
-                    int pInt = 0;
-                    if (WRITE) {
-                        m = p.masks[(int64_t) l * p.maskWords + word];
-                        keep = (m >> lane) & 1u;
-                    } else {
-                        keep = valid && (l == 0 ? (x > 0 && y > 0) : (l == 1 ? x > 0 : y > 0));
+        const int dLow = max(dt - 9, K.T + 1), nd = dt - dLow + 1;
+        /* lane k < nd holds diagonal dLow + k */
+        DiagRec mine;
+        mine.xmyL = 0;
+        mine.width = 0;
+        mine.coff = 0;
+        mine.aoff = 0;
+        if (lane < nd) mine = dg[dLow + lane];
+        const int64_t c0 = R.cellBase + __shfl_sync(0xFFFFFFFFu, mine.coff, 0);
+        const int64_t c1 = R.cellBase + __shfl_sync(0xFFFFFFFFu, mine.coff, nd - 1) + __shfl_sync(0xFFFFFFFFu, mine.width, nd - 1);
+        const int64_t cA = c0 & ~int64_t(31);
+        for (int l = 0; l < p.nLists; l++) {
+            const double *plane = a.planesB + (int64_t) l * a.planeStride;
+            uint32_t *masks = p.masks + (int64_t) l * p.maskWords + g;
+            if (!WRITE) {
+                int cnt = 0;
+                for (int64_t C = cA; C < c1; C += 128) {
+                    double z[4];
+                    bool valid[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int64_t cell = C + 32 * u + lane;
+                        valid[u] = cell >= c0 && cell < c1;
+                        z[u] = valid[u] ? __ldcs(plane + cell) : CPB_NEG_INF;
                     }
-                    if (keep) {
-                        const double z = a.planesB[(int64_t) l * a.planeStride + cell] - total; /* the backward sweep stored F + B */
-                        keep = false;
-                        if (z >= p.logThresholdLo) {
-                            double pr = exp(z);
-                            if (pr >= p.threshold) {
-                                keep = true;
-                                if (pr > 1.0) pr = 1.0;
-                                pInt = (int) floor(pr * (double) CPB_PAIR_ALIGNMENT_PROB_1);
-                            }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        int pInt;
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, valid[u] && posterior_keep(z[u], total, p, pInt));
+                        if (C + 32 * u < c1) {
+                            if (lane == 0) masks[(C >> 5) + u] = m;
+                            cnt += __popc(m);
                         }
                     }
-                    if (WRITE) {
-                        if (keep) {
-                            int32_t *o = p.out[l] + 3 * (run[l] + __popc(m & ltMask));
-                            o[0] = pInt;
-                            o[1] = x - 1 + R.ox;
-                            o[2] = y - 1 + R.oy;
+                }
+                __syncwarp();
+                /* strike out the border cells: list 0 (match) needs x > 0 and y > 0, list 1 (gap X) x > 0, list 2 (gap Y) y > 0 */
+                int struck = 0;
+                if (lane < nd) {
+                    const int d = dLow + lane, xlo = (d + mine.xmyL) >> 1;
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        /* e = 0: the cell with x = 0 (first cell, if the diagonal starts in row 0); e = 1: the cell with y = 0 (x = d) */
+                        const int i = e == 0 ? 0 : d - xlo;
+                        const bool exists = e == 0 ? xlo == 0 : (i >= 0 && i < mine.width);
+                        const bool applies = l == 0 || (l == 1 && e == 0) || (l == 2 && e == 1);
+                        if (exists && applies) {
+                            const int64_t cell = R.cellBase + mine.coff + i;
+                            const uint32_t bit = 1u << (cell & 31);
+                            if (atomicAnd(masks + (cell >> 5), ~bit) & bit) struck++; /* (0,0) may be visited twice: the second visit finds the bit gone */
                         }
-                    } else {
-                        m = __ballot_sync(0xFFFFFFFFu, keep);
-                        if (lane == 0) p.masks[(int64_t) l * p.maskWords + word] = m;
                     }
-                    run[l] += __popc(m);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) struck += __shfl_xor_sync(0xFFFFFFFFu, struck, o);
+                if (lane == 0) p.counts[(int64_t) l * p.nDecades + g] = cnt - struck;
+            } else {
+                int64_t run = p.offsets[(int64_t) l * p.nDecades + g];
+                const unsigned ltMask = (1u << lane) - 1u;
+                for (int64_t C = cA; C < c1; C += 32) {
+                    const unsigned m = masks[C >> 5];
+                    if (m == 0) continue; /* warp-uniform */
+                    const int64_t cell = C + lane;
+                    /* the diagonal of the cell: the last of the decade's diagonals that starts at or before it */
+                    int k = -1;
+                    for (int q = 0; q < nd; q++) k += (cell >= R.cellBase + (int64_t) __shfl_sync(0xFFFFFFFFu, mine.coff, q)) ? 1 : 0;
+                    k = max(k, 0);
+                    const int64_t coffK = R.cellBase + (int64_t) __shfl_sync(0xFFFFFFFFu, mine.coff, k);
+                    const int xmyLK = __shfl_sync(0xFFFFFFFFu, mine.xmyL, k);
+                    if ((m >> lane) & 1u) {
+                        const int d = dLow + k;
+                        const int x = ((d + xmyLK) >> 1) + (int) (cell - coffK), y = d - x;
+                        int pInt = 0;
+                        posterior_keep(plane[cell], total, p, pInt);
+                        int32_t *o = p.out[l] + 3 * (run + __popc(m & ltMask));
+                        o[0] = pInt;
+                        o[1] = x - 1 + R.ox;
+                        o[2] = y - 1 + R.oy;
+                    }
+                    run += __popc(m);
                 }
             }
-        }
-        if (!WRITE && lane == 0) {
-            for (int l = 0; l < p.nLists; l++) p.counts[(int64_t) l * p.nDecades + g] = (int32_t) run[l];
         }
     }
 }
