@@ -46,26 +46,62 @@ extern "C" const char *cpb_version(void) { return "cpecan_b200 0.1 (sm_100a)"; }
         }                                                                                                \
     } while (0)
 
+/* Device allocations released by one batch are kept for the next (cudaMalloc / cudaFree of multi-GB buffers costs
+ * hundreds of milliseconds per batch otherwise).  Best fit within 2x; everything is returned to the driver when the
+ * context is destroyed or an allocation fails. */
+struct DevPool {
+    struct Item {
+        void *p;
+        size_t cap;
+    };
+    std::vector<Item> items;
+    void *take(size_t bytes, size_t *capOut) {
+        int best = -1;
+        for (int i = 0; i < (int) items.size(); i++) {
+            if (items[i].cap >= bytes && items[i].cap <= 2 * bytes + (size_t(1) << 20) && (best < 0 || items[i].cap < items[best].cap)) best = i;
+        }
+        if (best < 0) return nullptr;
+        void *p = items[best].p;
+        *capOut = items[best].cap;
+        items.erase(items.begin() + best);
+        return p;
+    }
+    void give(void *p, size_t cap) { items.push_back({ p, cap }); }
+    void drain() {
+        for (auto &it : items) cudaFree(it.p);
+        items.clear();
+    }
+};
+
 /* grow-only device buffer */
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    DevPool *pool = nullptr;
     int reserve(size_t bytes) {
         if (bytes <= cap) return CPB_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
+        release();
+        if (pool != nullptr && (p = pool->take(bytes, &cap)) != nullptr) return CPB_OK;
         cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess && pool != nullptr) {
+            (void) cudaGetLastError();
+            pool->drain();
+            e = cudaMalloc(&p, bytes);
+        }
         if (e != cudaSuccess) {
             cpb_set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
             (void) cudaGetLastError();
+            p = nullptr;
             return CPB_ERR_MEMORY;
         }
         cap = bytes;
         return CPB_OK;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (pool != nullptr) pool->give(p, cap);
+            else cudaFree(p);
+        }
         p = nullptr;
         cap = 0;
     }
@@ -81,6 +117,7 @@ struct cpb_context {
     DevBuf scratch;
     DevBuf boundary, counters, negRecord; /* strip engine: per-warp-slot boundary rings, work-fetch counters, one LOG_ZERO ring record */
     int smCount = 148;
+    DevPool pool;              /* buffers handed back by destroyed batches */
 };
 
 static const int kStripWPC = 4; /* warps per CTA of the strip kernels */
@@ -149,6 +186,7 @@ extern "C" void cpb_context_destroy(cpb_context *ctx) {
     ctx->scratch.release();
     ctx->boundary.release();
     ctx->negRecord.release();
+    ctx->pool.drain();
     ctx->counters.release();
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -198,6 +236,12 @@ extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *se
     CUDA_TRY(cudaSetDevice(ctx->device));
     cpb_batch *b = new cpb_batch();
     b->ctx = ctx;
+    {
+        DevBuf *all[] = { &b->strips, &b->symX, &b->symY, &b->dAnchors, &b->regions, &b->diags, &b->blocks, &b->totals, &b->lists, &b->counts, &b->offsets,
+                          &b->masks, &b->tileSums, &b->pairCounts, &b->partials, &b->pairBlockOff, &b->perPair, &b->hmmTotal, &b->forwardOut, &b->out[0],
+                          &b->out[1], &b->out[2] };
+        for (DevBuf *d : all) d->pool = &ctx->pool;
+    }
     b->n = nPairs;
     b->xOff.assign(xOff, xOff + nPairs + 1);
     b->yOff.assign(yOff, yOff + nPairs + 1);
@@ -594,7 +638,10 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     int64_t running[3] = { 0, 0, 0 };
     int64_t chunkIndex = -1;
 
+    int64_t totalChunkCells = 0, cellsDone = 0;
+    for (auto &c : chunks) totalChunkCells += c.cells;
     for (auto &c : chunks) {
+        cellsDone += c.cells;
         DpArgs a;
         memset(&a, 0, sizeof(a));
         a.regions = b->regions.as<RegionDev>();
@@ -688,8 +735,11 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
                 const size_t need = (size_t) std::max<int64_t>(newTotals[l], 1) * 3 * sizeof(int32_t);
                 if (need > b->out[l].cap) {
                     /* grow, keeping what earlier chunks wrote */
+                    /* size for the whole batch, extrapolating the yield of the chunks done so far */
                     DevBuf bigger;
-                    if ((rc = bigger.reserve(std::max(need + need / 2, (size_t) 1 << 20))) != CPB_OK) return rc;
+                    bigger.pool = b->out[l].pool;
+                    const double scale = 1.15 * (double) std::max<int64_t>(totalChunkCells, 1) / (double) std::max<int64_t>(cellsDone, 1);
+                    if ((rc = bigger.reserve(std::max((size_t) ((double) need * std::max(scale, 1.0)), (size_t) 1 << 20))) != CPB_OK) return rc;
                     if (b->out[l].p && running[l] > 0)
                         CUDA_TRY(cudaMemcpyAsync(bigger.p, b->out[l].p, (size_t) running[l] * 3 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
                     CUDA_TRY(cudaStreamSynchronize(st));
