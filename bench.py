@@ -31,8 +31,9 @@ import numpy as np  # noqa: E402
 METRIC = "GCUPS (banded fwd-bwd+posterior)"
 UNIT = "GCUPS"
 WORKLOAD = "100k x 1 kb evolved pairs (randomSequences-style, ~10% divergence), StateMachine5, lib-default band (expansion 20, trim 14), threshold 0.01"
-FLOP_PER_CELL = 280.0      # SURVEY.md section 8d, five-state, reference arithmetic
-ALG_BYTES_PER_CELL = 80.0  # 5 states x 8 B written by forward + read by backward
+ALG_BYTES_PER_CELL = 80.0   # 5 states x 8 B written by forward + read by backward
+OPS_PER_CELL = 170.0        # 2 sweeps x (13 adds + 8 logAdds x 8 separately rounded FP64 operations)
+DRAM_BYTES_PER_CELL = 55.4  # measured: dram__bytes_read+write of k_forward_strip + k_backward_strip, profiles/README.md
 
 
 def read_peaks():
@@ -292,8 +293,8 @@ def main():
         k_ms = (phase["forward"] + phase["backward"]) / args.steps
         dom = "k_forward+k_backward"
         achieved_gbs = cells * ALG_BYTES_PER_CELL / (k_ms * 1e-3) / 1e9
-        fp64_peak = 148 * 64 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s non-tensor FP64 at max clock (half the FP32 rate)
-        achieved_tf = cells * FLOP_PER_CELL / (k_ms * 1e-3) / 1e12
+        fp64_peak = 148 * 64 * sm_max * 1e6 / 1e12  # T op/s: 64 FP64 lanes/clk/SM, no FMA (the contract forbids contraction)
+        achieved_tf = cells * OPS_PER_CELL / (k_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -307,10 +308,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "pairs_per_s": pairs_all * e2e_steps / float(tw[0])},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_cell": ALG_BYTES_PER_CELL,
-                         "compute": {"bound": "fp64 CUDA-core issue", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                                     "frac": achieved_tf / fp64_peak, "flop_per_cell": FLOP_PER_CELL}},
+                         "frac": achieved_gbs / hbm_peak, "traffic": DRAM_BYTES_PER_CELL * cells / max(int(st.nChunks), 1),
+                         "traffic_note": "bytes per launch pair (forward+backward of one chunk), ncu dram bytes per cell x cells per chunk",
+                         "peak_source": peak_src, "algorithmic_bytes_per_cell": ALG_BYTES_PER_CELL,
+                         "launches_per_step": 2 * int(st.nChunks),
+                         "compute": {"bound": "FP64 pipe, separately rounded add/mul (no FMA)", "achieved": achieved_tf, "peak": fp64_peak,
+                                     "unit": "Top/s", "frac": achieved_tf / fp64_peak, "ops_per_cell": OPS_PER_CELL}},
         }
         # CPU baseline on a bounded sample of the same workload
         try:

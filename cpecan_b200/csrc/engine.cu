@@ -467,7 +467,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         ba.auxF = auxF;
         ba.scheduleOn = mode != CPB_MODE_FORWARD;
         size_t ev = tic(&stx.msBand);
-        k_band<<<(unsigned) ((nReg + 63) / 64), 64, 0, st>>>(ba);
+        k_band<<<(unsigned) ((nReg + BAND_WARPS - 1) / BAND_WARPS), 32 * BAND_WARPS, 0, st>>>(ba);
         toc(ev);
         stx.kernelLaunches++;
     }
@@ -574,7 +574,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         std::sort(lists.begin() + c.stripFwdOff, lists.end(), [&](int32_t x, int32_t y) { return regs[x].cells > regs[y].cells; });
         c.stripBwdOff = (int64_t) lists.size();
         for (int64_t k = c.block0; k < c.block1; k++) lists.push_back((int32_t) k);
-        auto blockCost = [&](int32_t k) { return (int64_t) (hBlocks[k].top - hBlocks[k].T) * hBlocks[k].maxSpan; };
+        auto blockCost = [&](int32_t k) { return (int64_t) hBlocks[k].cells; };
         std::sort(lists.begin() + c.stripBwdOff, lists.end(), [&](int32_t x, int32_t y) { return blockCost(x) > blockCost(y); });
     }
     if ((rc = b->lists.reserve(std::max<size_t>(lists.size(), 1) * sizeof(int32_t))) != CPB_OK) return rc;
@@ -901,7 +901,7 @@ extern "C" int cpb_band(cpb_context *ctx, const int64_t *anchors, int64_t nAncho
     ba.minDiags = 2;
     ba.traceBack = 1;
     ba.scheduleOn = 0;
-    k_band<<<1, 32, 0, st>>>(ba);
+    k_band<<<1, 32 * BAND_WARPS, 0, st>>>(ba);
     std::vector<DiagRec> recs(N + 2);
     CUDA_TRY(cudaMemcpyAsync(recs.data(), dDiags.p, (N + 2) * sizeof(DiagRec), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(&R, dRegion.p, sizeof(R), cudaMemcpyDeviceToHost, st));

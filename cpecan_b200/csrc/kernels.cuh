@@ -54,7 +54,6 @@ struct RegionDev {
     int32_t blockCap;
     int32_t nBlocks;       /* out */
     int32_t maxW;          /* out: widest diagonal */
-    int32_t maxSpan;       /* out: window slots needed (see k_band) */
     int32_t maxStripRange; /* out: longest diagonal range of a 32-row strip */
     int32_t err;           /* out: 0 ok, 1 invalid diagonal, 2 block table overflow */
     uint8_t raggedL, raggedR;
@@ -70,7 +69,7 @@ struct BlockRec {
     int32_t top;   /* diagonal the traceback starts from */
     int32_t T;     /* tracedBackTo before this block: owned diagonals are (T, from] */
     int32_t from;  /* tracedBackFrom */
-    int32_t maxSpan; /* window slots needed for the diagonals in (T, top] */
+    int32_t cells;   /* band cells on the diagonals (T, top] */
     int32_t atEnd;
     int64_t decadeBase; /* chunk-relative index of the block's first decade (host, after planning) */
 };
@@ -592,9 +591,11 @@ __global__ void k_encode(uint8_t *s, int64_t n) {
 }
 
 /* ---------------------------------------------------------------------------------------------
- * k_band : one thread per region -- the device-side band builder and traceback scheduler.
- *   band:     band_construct / band_constructDynamic, impl/pairwiseAligner.c:94-234
- *   schedule: the traceback trigger of getPosteriorProbsWithBanding, :791-793, :810, :830, :852
+ * k_band : one warp per region -- the device-side band builder and traceback scheduler.
+ *   band:     band_construct / band_constructDynamic, impl/pairwiseAligner.c:94-234.  The reference walks the diagonals
+ *             with a moving (previous anchor, next anchor) pair; here every lane takes one diagonal, finds its anchor
+ *             interval by binary search (anchors are strictly increasing in x+y) and evaluates the same box formula.
+ *   schedule: the traceback trigger of getPosteriorProbsWithBanding, :791-793, :810, :830, :852, found with ballots.
  * ------------------------------------------------------------------------------------------- */
 struct BandArgs {
     RegionDev *regions;
@@ -611,159 +612,201 @@ struct BandArgs {
 
 __device__ __forceinline__ int64_t clamp_coord(int64_t z, int64_t l) { return z < 0 ? 0 : (z > l ? l : z); }
 
-__global__ void k_band(const BandArgs b) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int BAND_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * BAND_WARPS) k_band(const BandArgs b) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * BAND_WARPS + (threadIdx.x >> 5);
     if (r >= b.nRegions) return;
+    const unsigned FULL = 0xFFFFFFFFu;
     RegionDev R = b.regions[r];
     DiagRec *dg = b.diags + R.diagBase;
     const int32_t *an = b.anchors + 3 * R.anchorBase;
+    const int nA = R.nAnchors;
     const int64_t lX = R.lX, lY = R.lY, N = lX + lY;
-    int64_t ai = 0, pxay = 0, pxmy = 0, nxay = 0, nxmy = 0, xL = 0, yL = 0, xU = 0, yU = 0;
-    int64_t e = b.dynamic ? 0 : b.expansion;
-    int64_t coff = 0;
-    int maxW = 0, maxSpan = 1, err = 0;
     StripRec *st = b.strips + R.stripBase;
     const int nStrips = (int) (lX >> 5) + 1;
-    for (int k = 0; k < nStrips; k++) {
+    for (int k = lane; k < nStrips; k += 32) {
         st[k].dFirst = 0x7FFFFFFF;
         st[k].dLast = -1;
     }
-    int curLo = 0, curHi = -1; /* strips touched by the previous diagonal */
-    int64_t bl1 = 0, br1 = 0, bl2 = 0, br2 = -1; /* bands of the two previous diagonals */
-    for (int64_t xay = 0; xay <= N; xay++) {
-        int64_t l = xL - yL, rr = xU - yU, v;
-        if ((xay + l) % 2 != 0) l += 1;
-        if ((xay + rr) % 2 != 0) rr += 1;
-        v = (xay + l) / 2; if (v < xL) l += 2 * (xL - v);
-        v = (xay - l) / 2; if (yL < v) l += 2 * (v - yL);
-        v = (xay + rr) / 2; if (xU < v) rr -= 2 * (v - xU);
-        v = (xay - rr) / 2; if (v < yU) rr -= 2 * (yU - v);
-        if ((xay + l) % 2 != 0 || (xay + rr) % 2 != 0 || l > rr) {
-            err = 1;
-            rr = l; /* keep the tables well-formed; the host reports the error */
-        }
-        const int w = (int) ((rr - l) / 2 + 1);
-        DiagRec rec;
-        rec.xmyL = (int32_t) l;
-        rec.width = w;
-        rec.coff = (uint32_t) coff;
-        rec.aoff = NO_AUX;
-        dg[xay] = rec;
-        coff += w;
-        maxW = w > maxW ? w : maxW;
-        {
-            /* row strips touched by this diagonal: rows (xay + l)/2 .. (xay + rr)/2.  Only strips entering or leaving
-             * the touched range are written, so the table costs O(changes), not O(cells / 32). */
-            int sLo = (int) (((xay + l) / 2) >> 5), sHi = (int) (((xay + rr) / 2) >> 5);
-            if (sHi >= nStrips) sHi = nStrips - 1;
-            for (int k = sLo; k <= sHi; k++) {
-                if (k < curLo || k > curHi) {
-                    if (st[k].dFirst > (int) xay) st[k].dFirst = (int) xay;
-                }
-            }
-            for (int k = curLo; k <= curHi; k++) {
-                if (k < sLo || k > sHi) {
-                    if (st[k].dLast < (int) xay - 1) st[k].dLast = (int) xay - 1;
-                }
-            }
-            curLo = sLo;
-            curHi = sHi;
-        }
-        {
-            /* window slots the kernels need around this diagonal: same parity as xay-2, and xay-1 vs the +-1 neighbourhood */
-            int span = w;
-            if (xay >= 2 && br2 >= bl2) span = (int) (((rr > br2 ? rr : br2) - (l < bl2 ? l : bl2)) / 2 + 1);
-            if (xay >= 1) {
-                const int64_t hi = br1 > rr + 1 ? br1 : rr + 1, lo = bl1 < l - 1 ? bl1 : l - 1;
-                const int sb = (int) ((hi - lo) / 2 + 1);
-                span = sb > span ? sb : span;
-            }
-            dg[xay].aoff = (uint32_t) span; /* parked here until the schedule pass below consumes it */
-            maxSpan = span > maxSpan ? span : maxSpan;
-            bl2 = bl1; br2 = br1; bl1 = l; br1 = rr;
-        }
-        if (nxay == xay) {
-            pxay = nxay;
-            pxmy = nxmy;
-            int64_t x = lX, y = lY;
-            if (ai < R.nAnchors) {
-                x = (int64_t) an[3 * ai] - R.ox + 1;
-                y = (int64_t) an[3 * ai + 1] - R.oy + 1;
-                if (b.dynamic) e = an[3 * ai + 2];
-                ai++;
-            }
-            nxay = x + y;
-            nxmy = x - y;
-            xL = clamp_coord((pxay + (pxmy - e)) / 2, lX);
-            yL = clamp_coord((nxay - (nxmy - e)) / 2, lY);
-            xU = clamp_coord((nxay + (nxmy + e)) / 2, lX);
-            yU = clamp_coord((pxay - (pxmy + e)) / 2, lY);
-        }
-    }
-    DiagRec sentinel;
-    sentinel.xmyL = 0;
-    sentinel.width = 0;
-    sentinel.coff = (uint32_t) coff;
-    sentinel.aoff = NO_AUX;
-    dg[N + 1] = sentinel;
-    dg[N + 2] = sentinel;
+    __syncwarp();
+    /* anchor i in matrix coordinates of the region */
+    auto axay = [&](int i) { return (int64_t) an[3 * i] - R.ox + 1 + (int64_t) an[3 * i + 1] - R.oy + 1; };
 
+    int err = 0, maxW = 0;
+    int64_t cellsBefore = 0;       /* cells of all diagonals before this chunk */
+    int aLo = 0;                   /* first anchor whose x+y is >= the chunk's first diagonal */
+    int carryLo = 0, carryHi = -1; /* strips touched by the last diagonal of the previous chunk */
+    for (int64_t base = 0; base <= N; base += 32) {
+        const int64_t xay = base + lane;
+        const bool live = xay <= N;
+        int64_t l = 0, rr = 0;
+        int n = aLo;
+        if (live && xay > 0) {
+            /* n = first anchor with x+y >= xay: at most 16 anchors (x+y grows by >= 2) lie inside the chunk */
+            int lo = aLo, hi = min(nA, aLo + 17);
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (axay(mid) < xay) lo = mid + 1;
+                else hi = mid;
+            }
+            n = lo;
+            int64_t px = 0, py = 0, nx = lX, ny = lY, e = b.dynamic ? 0 : b.expansion;
+            if (n > 0) {
+                px = (int64_t) an[3 * (n - 1)] - R.ox + 1;
+                py = (int64_t) an[3 * (n - 1) + 1] - R.oy + 1;
+            }
+            if (n < nA) {
+                nx = (int64_t) an[3 * n] - R.ox + 1;
+                ny = (int64_t) an[3 * n + 1] - R.oy + 1;
+                if (b.dynamic) e = an[3 * n + 2];
+            } else if (b.dynamic && nA > 0) {
+                e = an[3 * (nA - 1) + 2]; /* past the last anchor the reference keeps that anchor's expansion */
+            }
+            const int64_t pxay = px + py, pxmy = px - py, nxay = nx + ny, nxmy = nx - ny;
+            const int64_t xL = clamp_coord((pxay + (pxmy - e)) / 2, lX), yL = clamp_coord((nxay - (nxmy - e)) / 2, lY);
+            const int64_t xU = clamp_coord((nxay + (nxmy + e)) / 2, lX), yU = clamp_coord((pxay - (pxmy + e)) / 2, lY);
+            int64_t v;
+            l = xL - yL;
+            rr = xU - yU;
+            if ((xay + l) % 2 != 0) l += 1;
+            if ((xay + rr) % 2 != 0) rr += 1;
+            v = (xay + l) / 2; if (v < xL) l += 2 * (xL - v);
+            v = (xay - l) / 2; if (yL < v) l += 2 * (v - yL);
+            v = (xay + rr) / 2; if (xU < v) rr -= 2 * (v - xU);
+            v = (xay - rr) / 2; if (v < yU) rr -= 2 * (yU - v);
+            if ((xay + l) % 2 != 0 || (xay + rr) % 2 != 0 || l > rr) {
+                err = 1;
+                rr = l; /* keep the tables well-formed; the host reports the error */
+            }
+        }
+        const int w = live ? (int) ((rr - l) / 2 + 1) : 0;
+        /* cell offsets: exclusive prefix sum of the widths */
+        int incl = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (live) {
+            DiagRec rec;
+            rec.xmyL = (int32_t) l;
+            rec.width = w;
+            rec.coff = (uint32_t) (cellsBefore + incl - w);
+            rec.aoff = NO_AUX;
+            dg[xay] = rec;
+        }
+        cellsBefore += __shfl_sync(FULL, incl, 31);
+        maxW = max(maxW, w);
+        /* 32-row strips touched by this diagonal: rows (xay + l)/2 .. (xay + rr)/2; record where strips enter and leave */
+        int sLo = live ? (int) (((xay + l) / 2) >> 5) : 0, sHi = live ? min((int) (((xay + rr) / 2) >> 5), nStrips - 1) : -1;
+        int pLo = __shfl_up_sync(FULL, sLo, 1), pHi = __shfl_up_sync(FULL, sHi, 1);
+        if (lane == 0) {
+            pLo = carryLo;
+            pHi = carryHi;
+        }
+        if (live) {
+            for (int k = sLo; k <= sHi; k++) {
+                if (k < pLo || k > pHi) atomicMin(&st[k].dFirst, (int) xay);
+            }
+            for (int k = pLo; k <= pHi; k++) {
+                if (k < sLo || k > sHi) atomicMax(&st[k].dLast, (int) xay - 1);
+            }
+        }
+        /* carry the state of the chunk's last live diagonal */
+        const int lastLive = N - base < 31 ? (int) (N - base) : 31;
+        carryLo = __shfl_sync(FULL, sLo, lastLive);
+        carryHi = __shfl_sync(FULL, sHi, lastLive);
+        aLo = __shfl_sync(FULL, n, lastLive);
+        /* the next chunk starts one diagonal later: its first anchor is the first with x+y >= base+32, i.e. n of the last lane, unless that anchor lies exactly on it */
+        if (aLo < nA && axay(aLo) < base + 32) aLo++;
+    }
+    for (int k = carryLo + lane; k <= carryHi; k += 32) atomicMax(&st[k].dLast, (int) N); /* strips still touched by the last diagonal */
+    if (lane == 0) {
+        DiagRec sentinel;
+        sentinel.xmyL = 0;
+        sentinel.width = 0;
+        sentinel.coff = (uint32_t) cellsBefore;
+        sentinel.aoff = NO_AUX;
+        dg[N + 1] = sentinel;
+        dg[N + 2] = sentinel;
+    }
+    __syncwarp();
+
+    /* ---- traceback schedule ---- */
     int nBlocks = 0;
     int64_t auxD = 0;
-    /* the per-diagonal spans were parked in aoff; blocks take their maximum, then aoff gets its real meaning */
     if (b.scheduleOn && N > 0) {
         BlockRec *bl = b.blocks + R.blockBase;
+        const int thresholdW = 2 * b.expansion + 1;
         int64_t T = 0;
-        for (int64_t d = 1; d <= N; d++) {
-            const bool atEnd = d == N;
-            const bool tb = d >= T + b.minDiags && dg[d].width <= 2 * b.expansion + 1;
-            if (!(atEnd || tb)) continue;
-            const int64_t from = d - (atEnd ? 0 : b.traceBack + 1);
-            int mw = 0;
-            for (int64_t k = T + 1; k <= d; k++) {
-                const int sp = (int) dg[k].aoff; /* still the parked span: diagonals above T have no owner yet */
-                mw = sp > mw ? sp : mw;
-                if (k <= from) dg[k].aoff = NO_AUX;
+        for (;;) {
+            /* the next traceback point: the first diagonal >= T + minDiags that is narrow enough, or N */
+            int64_t d = N;
+            for (int64_t q = T + b.minDiags; q < N; q += 32) {
+                const int64_t k = q + lane;
+                const bool hit = k < N && dg[k].width <= thresholdW;
+                const unsigned m = __ballot_sync(FULL, hit);
+                if (m != 0) {
+                    d = q + __ffs(m) - 1;
+                    break;
+                }
             }
-            if (nBlocks < R.blockCap) {
-                BlockRec K;
-                K.region = r;
-                K.top = (int32_t) d;
-                K.T = (int32_t) T;
-                K.from = (int32_t) from;
-                K.maxSpan = mw;
-                K.atEnd = atEnd;
-                K.decadeBase = 0;
-                bl[nBlocks] = K;
-            } else {
-                err = 2;
+            const bool atEnd = d == N;
+            const int64_t from = d - (atEnd ? 0 : b.traceBack + 1);
+            if (lane == 0) {
+                if (nBlocks < R.blockCap) {
+                    BlockRec K;
+                    K.region = r;
+                    K.top = (int32_t) d;
+                    K.T = (int32_t) T;
+                    K.from = (int32_t) from;
+                    K.cells = (int32_t) ((int64_t) dg[d + 1].coff - (int64_t) dg[T + 1].coff);
+                    K.atEnd = atEnd;
+                    K.decadeBase = 0;
+                    bl[nBlocks] = K;
+                } else {
+                    err = 2;
+                }
             }
             nBlocks++;
-            for (int64_t dt = from; dt > T; dt -= 10) {
-                const int w = dg[dt].width;
-                dg[dt].aoff = (uint32_t) auxD;
-                auxD += (int64_t) (b.auxF + 1) * w + (dt + 1 <= d ? dg[dt + 1].width : 0);
+            /* total diagonals from, from-10, ... > T get their aux records, in that order */
+            const int64_t nDec = (from - T + 9) / 10;
+            for (int64_t j0 = 0; j0 < nDec; j0 += 32) {
+                const int64_t j = j0 + lane;
+                const int64_t dt = from - 10 * j;
+                int64_t size = 0;
+                if (j < nDec) size = (int64_t) (b.auxF + 1) * dg[dt].width + (dt + 1 <= d ? dg[dt + 1].width : 0);
+                int64_t incl = size;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int64_t t = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (j < nDec) dg[dt].aoff = (uint32_t) (auxD + incl - size);
+                auxD += __shfl_sync(FULL, incl, 31);
             }
+            __syncwarp();
             T = from;
+            if (atEnd) break;
         }
-        dg[0].aoff = NO_AUX;
-    } else {
-        for (int64_t k = 0; k <= N; k++) dg[k].aoff = NO_AUX;
     }
-    R.cells = coff;
-    R.auxDoubles = auxD;
-    R.nBlocks = nBlocks;
-    R.maxW = maxW;
-    R.maxSpan = maxSpan;
-    for (int k = curLo; k <= curHi; k++) st[k].dLast = (int) N; /* strips still touched by the last diagonal */
+    err = __reduce_max_sync(FULL, err);
+    maxW = __reduce_max_sync(FULL, maxW);
     int msr = 1;
-    for (int k = 0; k < nStrips; k++) {
-        const int rg = st[k].dLast - st[k].dFirst + 1;
-        msr = rg > msr ? rg : msr;
+    __syncwarp();
+    for (int k = lane; k < nStrips; k += 32) msr = max(msr, st[k].dLast - st[k].dFirst + 1);
+    msr = __reduce_max_sync(FULL, msr);
+    if (lane == 0) {
+        R.cells = cellsBefore;
+        R.auxDoubles = auxD;
+        R.nBlocks = nBlocks;
+        R.maxW = maxW;
+        R.maxStripRange = msr;
+        R.err = err;
+        b.regions[r] = R;
     }
-    R.maxStripRange = msr;
-    R.err = err;
-    b.regions[r] = R;
 }
 
 } /* namespace cpb */

@@ -154,3 +154,43 @@ def random_anchor_pairs(rng, lX, lY):
             break
         out.append((x, y, e))
     return np.asarray(out, dtype=np.int64).reshape(-1, 3)
+
+
+# ---- families of sequences evolved from one ancestor (the all-pairs shape of makeAllPairwiseAlignments) ----
+def evolve_with_alignment(rng, ancestor, sub_rate=0.04, indel_rate=0.01, max_indel=4):
+    """-> (sequence str, pos int64[len(ancestor)]): pos[i] = index of ancestor base i in the sequence, or -1 if deleted."""
+    anc = ancestor.decode() if isinstance(ancestor, (bytes, bytearray)) else ancestor
+    out, pos = [], np.full(len(anc), -1, dtype=np.int64)
+    i = 0
+    while i < len(anc):
+        r = rng.random()
+        if r < indel_rate / 2:
+            i += int(rng.integers(1, max_indel + 1))  # deletion
+            continue
+        pos[i] = len(out)
+        out.append("ACGT"[rng.integers(0, 4)] if rng.random() < sub_rate else anc[i])
+        if r > 1.0 - indel_rate / 2:
+            out.extend("ACGT"[k] for k in rng.integers(0, 4, size=int(rng.integers(1, max_indel + 1))))  # insertion
+        i += 1
+    return "".join(out), pos
+
+
+def anchors_between(m1, m2, trim=14, expansion=20):
+    """Anchor triples a lastz-style chain would give for two family members: maximal runs of ancestor columns present in
+    both, consecutive in both and identical, trimmed by `trim` on each side (impl/pairwiseAligner.c:979-1003)."""
+    (s1, p1), (s2, p2) = m1, m2
+    a1 = np.frombuffer(s1.encode(), dtype=np.uint8)
+    a2 = np.frombuffer(s2.encode(), dtype=np.uint8)
+    both = (p1 >= 0) & (p2 >= 0)
+    same = np.zeros(p1.size, dtype=bool)
+    same[both] = a1[p1[both]] == a2[p2[both]]
+    out, run = [], []
+    for i in range(p1.size + 1):
+        ok = i < p1.size and same[i]
+        if ok and run and p1[i] == p1[run[-1]] + 1 and p2[i] == p2[run[-1]] + 1:
+            run.append(i)
+            continue
+        if len(run) > 2 * trim:
+            out.extend((int(p1[k]), int(p2[k]), expansion) for k in run[trim:len(run) - trim])
+        run = [i] if ok else []
+    return np.asarray(out, dtype=np.int64).reshape(-1, 3)

@@ -326,3 +326,48 @@ def test_roundtrip_properties_at_bench_scale(ctx):
     off2, tri2 = b.fetch_pairs(0)
     assert np.array_equal(off, off2) and np.array_equal(tri, tri2)
     b.close()
+
+
+def test_100kb_pair_with_anchor_banding_and_splits(ctx, oracle):
+    """BASELINE config 3 shape: one 100 kb evolved pair, lastz-style anchors, library defaults (~180 traceback blocks,
+    forward values down to -1.4e5), plus a copy with a 4 kb unalignable insert so that getSplitPoints cuts the matrix"""
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    packed = synth.evolved_pairs(1, 100000, seed=3, trim=int(p.constraintDiagonalTrim), expansion=int(p.diagonalExpansion))
+    sx, sy, a = synth.unpack(packed, 0)
+    cases = [(sx, sy, a, False, False)]
+    # second case: an insert in Y in the middle; anchors right of it shift by its length => a > 3000 x 3000 anchor gap
+    rng = np.random.default_rng(4)
+    half = 20000
+    ins = synth.random_sequence(rng, 4000, acgt_only=True)
+    sx2, sy2 = bytes(sx[:40000]).decode(), bytes(sy[:40000]).decode()
+    a2 = np.asarray(a, dtype=np.int64).reshape(-1, 3)
+    a2 = a2[(a2[:, 0] < 39000) & (a2[:, 1] < 39000)]
+    cut_y = int(a2[a2[:, 0] < half][-1, 1]) + 1
+    left = a2[a2[:, 0] < half - 2000]
+    right = a2[a2[:, 0] >= half + 2000].copy()
+    right[:, 1] += len(ins)
+    sy2 = sy2[:cut_y] + ins + sy2[cut_y:]
+    cases.append((sx2, sy2, np.concatenate([left, right]), False, False))
+    n = check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.fiveState), p, cases, "100kb")
+    assert n > 100000
+    b = run_batch(ctx, helpers.ModelSpec(cp.fiveState), p, cases[1:], cp.MODE_ALIGNED_PAIRS)
+    assert b.stats().nRegions >= 2  # the insert really split the matrix
+    b.close()
+
+
+def test_all_pairs_of_10kb_sequences(ctx, oracle):
+    """BASELINE config 5 shape (makeAllPairwiseAlignments, impl/multipleAligner.c:668-681): every pair of a small family of
+    10 kb sequences evolved from one ancestor, aligned in one batch"""
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    fam = synth.evolved_pairs(4, 10000, seed=8, trim=int(p.constraintDiagonalTrim), expansion=int(p.diagonalExpansion))
+    # members: the Y sequences of four pairs that share... each pair has its own ancestor, so build the family from one X
+    anc, _, _ = synth.unpack(fam, 0)
+    rng = np.random.default_rng(9)
+    members = [synth.evolve_with_alignment(rng, anc) for _ in range(4)]
+    cases = []
+    for i in range(4):
+        for j in range(i + 1, 4):
+            a = synth.anchors_between(members[i], members[j], trim=int(p.constraintDiagonalTrim), expansion=int(p.diagonalExpansion))
+            cases.append((members[i][0], members[j][0], a, False, False))
+    n = check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.fiveState), p, cases, "all pairs 10kb")
+    assert n > 6 * 8000
