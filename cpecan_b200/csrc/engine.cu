@@ -115,7 +115,7 @@ struct cpb_context {
     bool ownStream = false;
     size_t scratchBudget = 0;
     DevBuf scratch;
-    DevBuf boundary, counters, negRecord; /* strip engine: per-warp-slot boundary rings, work-fetch counters, one LOG_ZERO ring record */
+    DevBuf boundary, counters, negRecord, progress; /* strip engine: per-warp-slot boundary rings, work-fetch counters, one LOG_ZERO ring record */
     int smCount = 148;
     DevPool pool;              /* buffers handed back by destroyed batches */
 };
@@ -186,6 +186,7 @@ extern "C" void cpb_context_destroy(cpb_context *ctx) {
     ctx->scratch.release();
     ctx->boundary.release();
     ctx->negRecord.release();
+    ctx->progress.release();
     ctx->pool.drain();
     ctx->counters.release();
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
@@ -605,25 +606,45 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
 
     /* strip engine: persistent grid of independent warps, boundary rings, work counters */
     typedef void (*StripKernel)(const DpArgs, const CpbModel, const StripArgs);
-    StripKernel kFwdStrip = nullptr, kBwdStrip = nullptr;
+    StripKernel kFwdStrip = nullptr, kFwdTeam = nullptr, kBwdStrip = nullptr;
     switch (mode) {
-    case CPB_MODE_FORWARD: kFwdStrip = k_forward_strip<S, 0, kStripWPC>; kBwdStrip = k_backward_strip<S, 0, true, kStripWPC>; break;
-    case CPB_MODE_ALIGNED_PAIRS: kFwdStrip = k_forward_strip<S, 1, kStripWPC>; kBwdStrip = k_backward_strip<S, 1, true, kStripWPC>; break;
-    case CPB_MODE_ALIGNED_PAIRS_INDELS: kFwdStrip = k_forward_strip<S, 3, kStripWPC>; kBwdStrip = k_backward_strip<S, 3, true, kStripWPC>; break;
-    default: kFwdStrip = k_forward_strip<S, S, kStripWPC>; kBwdStrip = k_backward_strip<S, S, false, kStripWPC>; break;
+    case CPB_MODE_FORWARD:
+        kFwdStrip = k_forward_strip<S, 0, kStripWPC, false>;
+        kFwdTeam = k_forward_strip<S, 0, kStripWPC, true>;
+        kBwdStrip = k_backward_strip<S, 0, true, kStripWPC>;
+        break;
+    case CPB_MODE_ALIGNED_PAIRS:
+        kFwdStrip = k_forward_strip<S, 1, kStripWPC, false>;
+        kFwdTeam = k_forward_strip<S, 1, kStripWPC, true>;
+        kBwdStrip = k_backward_strip<S, 1, true, kStripWPC>;
+        break;
+    case CPB_MODE_ALIGNED_PAIRS_INDELS:
+        kFwdStrip = k_forward_strip<S, 3, kStripWPC, false>;
+        kFwdTeam = k_forward_strip<S, 3, kStripWPC, true>;
+        kBwdStrip = k_backward_strip<S, 3, true, kStripWPC>;
+        break;
+    default:
+        kFwdStrip = k_forward_strip<S, S, kStripWPC, false>;
+        kFwdTeam = k_forward_strip<S, S, kStripWPC, true>;
+        kBwdStrip = k_backward_strip<S, S, false, kStripWPC>;
+        break;
     }
     StripArgs sargs;
     memset(&sargs, 0, sizeof(sargs));
-    int stripGrid = 1;
+    int stripGrid = 1, teamGrid = 1;
     {
         int maxRange = 1;
         for (int64_t r = 0; r < nReg; r++) maxRange = std::max(maxRange, regs[r].maxStripRange);
         int ring = 64;
         while (ring < maxRange + 4) ring <<= 1;
-        int occF = 1, occB = 1;
+        int occF = 1, occB = 1, occT = 1;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occF, kFwdStrip, 32 * kStripWPC, 0));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, kBwdStrip, 32 * kStripWPC, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, kFwdTeam, 32 * kStripWPC, 0));
         stripGrid = ctx->smCount * std::max(1, std::max(occF, occB));
+        teamGrid = ctx->smCount * std::max(1, std::min(occT, std::max(occF, occB))); /* every team CTA must be resident: teams spin on each other */
+        if ((rc = ctx->progress.reserve((size_t) stripGrid * kStripWPC * sizeof(unsigned long long))) != CPB_OK) return rc;
+        sargs.progress = ctx->progress.as<unsigned long long>();
         const size_t need = (size_t) stripGrid * kStripWPC * 2 * ring * BND_REC * sizeof(double);
         if ((rc = ctx->boundary.reserve(need)) != CPB_OK) return rc;
         if ((rc = ctx->counters.reserve(2 * chunks.size() * sizeof(unsigned int) + 16)) != CPB_OK) return rc;
@@ -667,9 +688,44 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             a.list = dLists + c.stripFwdOff;
             sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex;
             sargs.nItems = (int32_t) cnt;
-            const int grid = (int) std::min<int64_t>(stripGrid, (cnt + kStripWPC - 1) / kStripWPC);
-            kFwdStrip<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
+            /* few regions for the machine: let teams of warps pipeline the strips of one region (largest power of two that still
+             * keeps every warp slot busy, at most 16: a strip lags its predecessor by ~64 diagonals) */
+            int team = 1;
+            int64_t chunkCells = 0;
+            for (int64_t r = c.region0; r < c.region1; r++) chunkCells += regs[r].cells;
+            if (chunkCells / cnt >= (int64_t) 1 << 20) { /* only long regions: a hand-over between warps costs more than a short strip */
+                while (team < 16 && cnt * team * 2 <= (int64_t) teamGrid * kStripWPC) team *= 2;
+            }
+            if (getenv("CPB_TEAM") != nullptr) team = std::max(1, atoi(getenv("CPB_TEAM")));
+            if (team > 1 || getenv("CPB_TEAM_KERNEL") != nullptr) {
+                const int grid = (int) std::min<int64_t>(teamGrid, (cnt * team + kStripWPC - 1) / kStripWPC);
+                sargs.teamSize = team;
+                CUDA_TRY(cudaMemsetAsync(ctx->progress.p, 0, (size_t) grid * kStripWPC * sizeof(unsigned long long), st));
+                kFwdTeam<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
+            } else {
+                const int grid = (int) std::min<int64_t>(stripGrid, (cnt + kStripWPC - 1) / kStripWPC);
+                sargs.teamSize = 1;
+                kFwdStrip<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
+            }
             stx.kernelLaunches++;
+#ifdef CPB_TEAM_DEBUG
+            if (team > 1) {
+                unsigned long long dbg[8] = { 0 }, zero[8] = { 0 };
+                cudaStreamSynchronize(st);
+                cudaMemcpyFromSymbol(dbg, g_teamDebug, sizeof(dbg));
+                cudaMemcpyToSymbol(g_teamDebug, zero, sizeof(zero));
+                if (getenv("CPB_TEAM_TRACE") != nullptr) {
+                    unsigned long long tr[64 * 4];
+                    cudaMemcpyFromSymbol(tr, g_teamTrace, sizeof(tr));
+                    unsigned long long stt[256];
+                    cudaMemcpyFromSymbol(stt, g_stepTrace, sizeof(stt));
+                    for (int q = 0; q < 256; q++) fprintf(stderr, "step strip %d +%d: %.1f\n", 1 + q / 128, q % 128, stt[q] > tr[1] ? (stt[q] - tr[1]) / 1e3 : -1.0);
+                    for (int q = 0; q < 34; q++) fprintf(stderr, "  strip %2d slot %llu start %8.1f loop %8.1f end %8.1f us\n", q, tr[4 * q], (tr[4 * q + 1] - tr[1]) / 1e3, (tr[4 * q + 2] - tr[1]) / 1e3, (tr[4 * q + 3] - tr[1]) / 1e3);
+                }
+                fprintf(stderr, "team %d: %llu wait calls, %llu spun, %llu spin iterations, %.3f ms waiting; %llu publishes, %.3f ms publishing (summed over warps)\n",
+                        team, dbg[3], dbg[1], dbg[2], (double) dbg[0] / 1.965e6, dbg[5], (double) dbg[4] / 1.965e6);
+            }
+#endif
         }
         toc(ev);
         if (mode == CPB_MODE_FORWARD) continue;

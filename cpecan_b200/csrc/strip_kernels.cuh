@@ -37,7 +37,64 @@ struct StripArgs {
     int32_t ringSize;         /* power of two >= longest strip diagonal range + 4 */
     int32_t nItems;
     unsigned int *counter;    /* work-fetch counter (zeroed before the launch) */
+    unsigned long long *progress; /* forward teams: per warp slot, (strip serial << 32) | (last published message index + 2) */
+    int32_t teamSize;         /* forward teams: warps that share one region (power of two, 1 = no teams) */
+    int32_t pad_;
 };
+
+/* ---- forward teams: a region's strips are dealt round-robin to the K warps of a team, and strip s consumes the messages
+ * of strip s-1 while that strip is still running on the neighbouring warp.  Progress words are monotone per slot. ---- */
+__device__ __forceinline__ unsigned long long strip_serial(int iter, int s) { return ((unsigned long long) (iter + 1) << 20) | (unsigned) s; }
+constexpr unsigned PROGRESS_DONE = 0x7FFFFFF0u;
+#ifndef CPB_TEAM_SLEEP_NS
+#define CPB_TEAM_SLEEP_NS 20
+#endif
+#ifndef CPB_TEAM_PUBLISH_MASK
+#define CPB_TEAM_PUBLISH_MASK 7 /* a strip publishes its progress every (mask + 1) diagonals */
+#endif
+/* Progress words and ring records both live in L2 (records are written with st.cg and read with ld.cg), the point of
+ * coherence between SMs.  The producer's release store orders its earlier record stores before the progress word; the
+ * consumer polls with relaxed loads and only then issues its (L2) record loads.  No L1 invalidation is needed or wanted:
+ * __threadfence() would cost a CCTL.IVALL per call and wipe the L1 lines every other warp of the SM is working from. */
+#ifdef CPB_TEAM_DEBUG
+__device__ unsigned long long g_teamTrace[64 * 4];
+__device__ unsigned long long g_stepTrace[256]; /* strip 1 and 2 of the first region: time of every step */ /* per strip (first region only): slot, start, loop start, end (ns) */
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ unsigned long long g_teamDebug[8]; /* wait cycles, waits that spun, spin iterations, wait calls, publish cycles, publishes */
+#endif
+__device__ __forceinline__ void team_publish(unsigned long long *slotWord, unsigned long long serial, unsigned upTo) {
+#ifdef CPB_TEAM_DEBUG
+    const long long t0 = clock64();
+#endif
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(slotWord), "l"((serial << 32) | upTo) : "memory");
+#ifdef CPB_TEAM_DEBUG
+    atomicAdd(&g_teamDebug[4], (unsigned long long) (clock64() - t0));
+    atomicAdd(&g_teamDebug[5], 1ull);
+#endif
+}
+__device__ __forceinline__ unsigned long long team_peek(const unsigned long long *slotWord) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(slotWord) : "memory");
+    return v;
+}
+__device__ __forceinline__ void team_wait(const unsigned long long *slotWord, unsigned long long serial, unsigned upTo) {
+    const unsigned long long want = (serial << 32) | upTo;
+#ifdef CPB_TEAM_DEBUG
+    const long long t0 = clock64();
+    unsigned long long spins = 0;
+    while (team_peek(slotWord) < want) spins++;
+    atomicAdd(&g_teamDebug[0], (unsigned long long) (clock64() - t0));
+    atomicAdd(&g_teamDebug[1], spins > 0 ? 1ull : 0ull);
+    atomicAdd(&g_teamDebug[2], spins);
+    atomicAdd(&g_teamDebug[3], 1ull);
+    return;
+#endif
+    while (team_peek(slotWord) < want) {
+#if CPB_TEAM_SLEEP_NS > 0
+        __nanosleep(CPB_TEAM_SLEEP_NS);
+#endif
+    }
+}
 
 /* compile-time flags for the step lambdas */
 struct Yes { static constexpr bool value = true; };
@@ -125,9 +182,12 @@ template <int S> __device__ __forceinline__ void lower_folds(double *g, const do
 }
 
 /* ---------------------------------------------------------------------------------------------
- * k_forward_strip<S, NP, WPC>: NP = state planes written to HBM (0 forward-only, 1 match, 3 match+gaps, S all)
+ * k_forward_strip<S, NP, WPC, TEAM>: NP = state planes written to HBM (0 forward-only, 1 match, 3 match+gaps, S all).
+ * TEAM = false: every warp fetches whole regions from the work counter (many regions per launch).
+ * TEAM = true : sa.teamSize consecutive warp slots share a region (few, long regions): strips are dealt round-robin and
+ *               pipelined through the rings, regions are dealt round-robin to the teams.
  * ------------------------------------------------------------------------------------------- */
-template <int S, int NP, int WPC>
+template <int S, int NP, int WPC, bool TEAM>
 __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_strip(const DpArgs a, const CpbModel model, const StripArgs sa) {
     __shared__ __align__(16) StripTables<S> tab;
     fill_strip_tables<S>(tab, model, threadIdx.x, 32 * WPC);
@@ -136,17 +196,33 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
     const LaTable la = logadd_lane_table(tab.la);
     const int l16 = threadIdx.x & 15;
     const int lane = threadIdx.x & 31;
+#ifdef CPB_TEAM_SPREAD
+    const int slot = TEAM ? (int) ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) : (int) (blockIdx.x * WPC + (threadIdx.x >> 5)); /* consecutive slots on different SMs */
+#else
     const int slot = blockIdx.x * WPC + (threadIdx.x >> 5);
+#endif
     const int rm = sa.ringSize - 1;
-    double *ring0 = sa.boundary + (size_t) slot * 2 * sa.ringSize * BND_REC;
-    double *ring1 = ring0 + (size_t) sa.ringSize * BND_REC;
+    const size_t ringDoubles = (size_t) sa.ringSize * BND_REC; /* a slot owns two rings */
     const bool keepFull = a.auxF != 0; /* full cells of total diagonals go to the aux records (posterior modes) */
+    const int K = TEAM ? sa.teamSize : 1;
+    const int member = slot & (K - 1), teamBase = slot - member;
+    const int nTeams = (int) ((gridDim.x * WPC) / K);
 
-    for (;;) {
+    for (int iter = 0;; iter++) {
         unsigned item = 0;
-        if (lane == 0) item = atomicAdd(sa.counter, 1u);
-        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (TEAM) {
+            item = (unsigned) (teamBase / K + iter * nTeams);
+            if (teamBase / K >= nTeams) break; /* warps beyond the last whole team idle */
+        } else {
+            if (lane == 0) item = atomicAdd(sa.counter, 1u);
+            item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        }
         if (item >= (unsigned) sa.nItems) break;
+        if (TEAM && iter > 0) {
+            /* the rings are reused: nobody starts a region before the whole team has finished the previous one */
+            if (lane < K) team_wait(sa.progress + teamBase + lane, strip_serial(iter - 1, 0xFFFFF), PROGRESS_DONE);
+            __syncwarp();
+        }
         const int regionId = a.list[item];
         const RegionDev R = a.regions[regionId];
         const int N = R.lX + R.lY;
@@ -156,22 +232,50 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
         double *aux = a.aux + R.auxBase;
         const StripRec *strips = sa.strips + R.stripBase;
         const int nStrips = (R.lX >> 5) + 1;
-        int prevFirst = 1, prevLast = 0; /* ring indices the previous strip wrote */
 
-        for (int s = 0; s < nStrips; s++) {
+        for (int s = member; s < nStrips; s += K) {
             const StripRec sr = strips[s];
+            /* ring indices the previous strip writes: its diagonals and one flush record */
+            int prevFirst = 1, prevLast = 0;
+            if (s > 0) {
+                const StripRec sp = strips[s - 1];
+                if (sp.dLast >= sp.dFirst) {
+                    prevFirst = sp.dFirst;
+                    prevLast = sp.dLast + 1;
+                }
+            }
+#ifdef CPB_TEAM_DEBUG
+            if (TEAM && lane == 0 && item == 0 && s < 64) { g_teamTrace[4 * s] = slot; g_teamTrace[4 * s + 1] = gtime(); }
+#endif
+            const int producer = teamBase + ((s - 1) & (K - 1));
+            const unsigned long long mySerial = strip_serial(iter, s), prodSerial = strip_serial(iter, s - 1);
+            unsigned long long *myWord = sa.progress + slot;
+            const unsigned long long *prodWord = sa.progress + producer;
             if (sr.dLast < sr.dFirst) {
-                prevFirst = 1;
-                prevLast = 0;
+                if (TEAM && lane == 31) team_publish(myWord, mySerial, PROGRESS_DONE);
                 continue;
             }
+            if (TEAM && s >= 2 * K && lane == 0) {
+                /* this strip overwrites the ring of strip s-2K, whose reader is strip s-2K+1 on the next warp of the team */
+                team_wait(sa.progress + teamBase + ((s + 1) & (K - 1)), strip_serial(iter, s - 2 * K + 1), PROGRESS_DONE);
+            }
+            __syncwarp();
+            double *bOut = sa.boundary + ((size_t) slot * 2 + ((s / K) & 1)) * ringDoubles;
+            const double *bIn = sa.boundary + ((size_t) producer * 2 + (((s - 1) / K) & 1)) * ringDoubles;
+            unsigned published = 0; /* lane 0: how far the producer is known to have got (message index + 2) */
+            /* lane 0 only: make sure message t of the previous strip has been published */
+            auto await = [&](const int t) {
+                if (TEAM && (unsigned) (t + 2) > published) {
+                    team_wait(prodWord, prodSerial, (unsigned) (t + 2));
+                    const unsigned long long w = team_peek(prodWord);
+                    published = (w >> 32) == prodSerial ? (unsigned) w : PROGRESS_DONE; /* a later serial: that strip is finished */
+                }
+            };
             const int x = 32 * s + lane;
             const int cXn6 = (x < R.lX ? sx[x] : 4) * 6; /* symbol of row x+1, the row this lane's messages go to */
             double tlD[NL];
             load_row<NL>(tlD, tab.tl[cXn6 / 6]);
             const uint8_t *ptrY = sy - x; /* ptrY[d] = symbol of column d+1-x (symbol arrays are padded on both sides) */
-            double *bOut = (s & 1) ? ring1 : ring0;
-            const double *bIn = (s & 1) ? ring0 : ring1;
 
             double own[S], send[NSH], bNext[NSH];
 #pragma unroll
@@ -199,6 +303,7 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
                 const int t = d0 - 1;
                 const DiagRec r0 = dg[d0 <= N ? d0 : N];
                 const bool ok = t >= prevFirst && t <= prevLast && (unsigned) (x - ((d0 + r0.xmyL) >> 1)) < (unsigned) r0.width;
+                if (ok) await(t);
                 load_record<NSH>(bNext, ok ? bIn + (size_t) (t & rm) * BND_REC : sa.negRecord);
             }
             /* diagonal records and column symbols are fetched two steps ahead (records N+1, N+2 are sentinels) */
@@ -223,7 +328,10 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
                     /* lane 0 prefetches the message for diagonal d+1; LOG_ZERO if the previous strip had none or (x, d+1-x) is outside the band */
                     const bool ok = d >= prevFirst && d <= prevLast && (unsigned) (x - ((d + 1 + nxt.xmyL) >> 1)) < (unsigned) nxt.width;
                     const double *rec = ok ? bIn + (size_t) (d & rm) * BND_REC : sa.negRecord;
-                    if (lane == 0) load_record<NSH>(bNext, rec);
+                    if (lane == 0) {
+                        if (TEAM && ok) await(d);
+                        load_record<NSH>(bNext, rec);
+                    }
                 }
                 /* the middle fold of the previous cell (own) for (x+1, d-x): its column symbol is this step's cYnow */
                 double tmD[NM], tu[NU];
@@ -258,12 +366,21 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
                 /* message for diagonal d+1: middle fold of cell d-1, lower folds of cell d */
                 send[0] = mPrev;
                 lower_folds<S>(send + 1, out, tlD, la);
-                if (lane == 31) store_record<NSH>(bOut + (size_t) (d & rm) * BND_REC, send);
+                if (lane == 31) {
+                    store_record<NSH>(bOut + (size_t) (d & rm) * BND_REC, send);
+                    if (TEAM && (d & CPB_TEAM_PUBLISH_MASK) == CPB_TEAM_PUBLISH_MASK) team_publish(myWord, mySerial, (unsigned) (d + 2)); /* messages up to d are out */
+                }
 #pragma unroll
                 for (int k = 0; k < S; k++) own[k] = out[k];
             };
 
+#ifdef CPB_TEAM_DEBUG
+            if (TEAM && lane == 0 && item == 0 && s < 64) g_teamTrace[4 * s + 2] = gtime();
+#endif
             for (int d = d0; d <= sr.dLast;) {
+#ifdef CPB_TEAM_DEBUG
+                if (TEAM && lane == 0 && item == 0 && (s == 1 || s == 2) && d - d0 < 128) g_stepTrace[(s - 1) * 128 + d - d0] = gtime();
+#endif
                 const bool auxA = keepFull && cur.aoff != NO_AUX, auxB = keepFull && nxt.aoff != NO_AUX; /* warp-uniform */
                 const DiagRec nxt2 = dg[d + 2];
                 const int cY2 = ptrY[d + 1];
@@ -294,7 +411,13 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
                 last[0] = middle_fold<S>(own, tmD, la);
 #pragma unroll
                 for (int k = 1; k < NSH; k++) last[k] = CPB_NEG_INF;
-                if (lane == 31) store_record<NSH>(bOut + (size_t) ((sr.dLast + 1) & rm) * BND_REC, last);
+                if (lane == 31) {
+                    store_record<NSH>(bOut + (size_t) ((sr.dLast + 1) & rm) * BND_REC, last);
+                    if (TEAM) team_publish(myWord, mySerial, PROGRESS_DONE);
+                }
+#ifdef CPB_TEAM_DEBUG
+                if (TEAM && lane == 0 && item == 0 && s < 64) g_teamTrace[4 * s + 3] = gtime();
+#endif
             }
             if (NP == 0 && a.forwardOut != nullptr && s == nStrips - 1 && sr.dLast == N && N > 0 && lane == (R.lX & 31)) {
                 /* computeForwardProbability: the last cell dotted with the end vector (impl/pairwiseAligner.c:910-916) */
@@ -304,11 +427,10 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
                 for (int k = 1; k < S; k++) v = log_add(v, own[k] + ev[k], la);
                 a.forwardOut[regionId] = v;
             }
-            prevFirst = sr.dFirst;
-            prevLast = sr.dLast + 1;
             __syncwarp();
         }
-        if (NP == 0 && a.forwardOut != nullptr && N == 0 && lane == 0) a.forwardOut[regionId] = 0.0; /* LOG_ONE for the empty problem */
+        if (NP == 0 && a.forwardOut != nullptr && N == 0 && lane == 0 && member == 0) a.forwardOut[regionId] = 0.0; /* LOG_ONE for the empty problem */
+        if (TEAM && lane == 31) team_publish(sa.progress + slot, strip_serial(iter, 0xFFFFF), PROGRESS_DONE); /* this warp is done with the region */
     }
 }
 
