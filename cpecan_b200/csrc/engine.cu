@@ -838,6 +838,15 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
+#ifdef CPB_LA_STATS
+    {
+        unsigned long long ls[4] = { 0, 0, 0, 0 }, zero[4] = { 0, 0, 0, 0 };
+        cudaMemcpyFromSymbol(ls, g_laStats, sizeof(ls));
+        cudaMemcpyToSymbol(g_laStats, zero, sizeof(zero));
+        fprintf(stderr, "logAdd: %llu warp calls, %.1f%% with every lane beyond the cut-off; %llu lane calls, %.1f%% beyond the cut-off\n", ls[0],
+                100.0 * ls[1] / (ls[0] ? ls[0] : 1), ls[2], 100.0 * ls[3] / (ls[2] ? ls[2] : 1));
+    }
+#endif
     finish_events();
     for (int l = 0; l < nLists; l++) {
         b->outCount[l] = running[l];

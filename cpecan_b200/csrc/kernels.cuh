@@ -129,8 +129,24 @@ __device__ __forceinline__ LaTable logadd_lane_table(const double *la) {
     return (unsigned) __cvta_generic_to_shared(la) + 16u * (threadIdx.x & 7);
 }
 
+#ifdef CPB_LA_STATS
+__device__ unsigned long long g_laStats[4]; /* warp-level calls, calls where every active lane is at or beyond the cut-off, lane calls, lane cut-offs */
+#endif
 __device__ __forceinline__ double log_add(double x, double y, const LaTable la) {
     const double diff = __dsub_rn(x, y);
+#ifdef CPB_LA_STATS
+    {
+        const unsigned am = __activemask();
+        const bool far = !(fabs(diff) < 7.5);
+        const unsigned fm = __ballot_sync(am, far);
+        if ((threadIdx.x & 31) == __ffs(am) - 1) {
+            atomicAdd(&g_laStats[0], 1ull);
+            if (fm == am) atomicAdd(&g_laStats[1], 1ull);
+            atomicAdd(&g_laStats[2], (unsigned long long) __popc(am));
+            atomicAdd(&g_laStats[3], (unsigned long long) __popc(fm));
+        }
+    }
+#endif
     const bool xSmaller = __double2hiint(diff) < 0; /* sign of x-y; both -inf gives NaN, handled below */
     const double big = xSmaller ? y : x;
     const double small = xSmaller ? x : y;

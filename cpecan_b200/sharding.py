@@ -80,6 +80,20 @@ def allreduce_expectations(local, group=None, device_tensor=None):
     return t.cpu().numpy()
 
 
+class _DeviceDoubles:
+    """A raw device pointer to n doubles as something torch.as_tensor understands (no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def device_vector(ptr, n):
+    """torch float64 CUDA tensor aliasing n doubles at the device address ptr (e.g. Batch.device_expectation_total_ptr())."""
+    import torch
+
+    return torch.as_tensor(_DeviceDoubles(ptr, n), device="cuda")
+
+
 def normalise_hmm(vec, S):
     """hmm_normalise (impl/stateMachine.c:88-112) on the flat vector: rows of the transition matrix and each state's
     emission matrix sum to one; the likelihood entry is left alone."""
