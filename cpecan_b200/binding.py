@@ -109,6 +109,7 @@ def _load():
     L.cpb_batch_result_count.restype = C.c_int64
     L.cpb_batch_result_count.argtypes = [C.c_void_p, C.c_int]
     L.cpb_batch_fetch_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.cpb_batch_fetch_pairs_reference_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.cpb_batch_device_triples.restype = C.c_void_p
     L.cpb_batch_device_triples.argtypes = [C.c_void_p, C.c_int]
     L.cpb_batch_fetch_expectations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -271,12 +272,14 @@ class Batch:
     def result_count(self, which=0):
         return int(lib.cpb_batch_result_count(self.h, which))
 
-    def fetch_pairs(self, which=0, out=None):
-        """-> (offsets[n+1], triples[count,3] int32 (pInt, x, y))"""
+    def fetch_pairs(self, which=0, out=None, reference_order=False):
+        """-> (offsets[n+1], triples[count,3] int32 (pInt, x, y)); per pair sorted by (x+y, x), or with reference_order in the
+        order the reference's own lists have (what libcpecan.so returns)"""
         cnt = self.result_count(which)
         off = np.zeros(self.n + 1, dtype=np.int64)
         tri = out if out is not None else np.zeros((max(cnt, 1), 3), dtype=np.int32)
-        _check(lib.cpb_batch_fetch_pairs(self.h, which, C.c_void_p(off.ctypes.data), C.c_void_p(tri.ctypes.data)))
+        fetch = lib.cpb_batch_fetch_pairs_reference_order if reference_order else lib.cpb_batch_fetch_pairs
+        _check(fetch(self.h, which, C.c_void_p(off.ctypes.data), C.c_void_p(tri.ctypes.data)))
         return off, tri[:cnt]
 
     def fetch_expectations(self, per_pair=True):

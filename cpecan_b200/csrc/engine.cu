@@ -898,6 +898,56 @@ extern "C" int cpb_batch_fetch_pairs(cpb_batch *b, int list, int64_t *offsets, i
     return CPB_OK;
 }
 
+/* The reference hands its lists back in the order its traceback produced them, reversed per region (impl/pairwiseAligner.c:1411-1418 pops
+ * the region's list): regions ascending; inside a region the traceback blocks from last to first; inside a block the diagonals
+ * ascending; along a diagonal x descending.  Order-sensitive callers (getMaximalExpectedAccuracyPairwiseAlignment walks the list
+ * backwards and stops early) see the same list from us.  The device output is sorted by (x + y, x) per pair, and regions and blocks own
+ * consecutive ranges of x + y, so this is a permutation of consecutive runs done on the host after the copy. */
+extern "C" int cpb_batch_fetch_pairs_reference_order(cpb_batch *b, int list, int64_t *offsets, int32_t *triples) {
+    const int rc = cpb_batch_fetch_pairs(b, list, offsets, triples);
+    if (rc != CPB_OK || triples == nullptr) return rc;
+    const std::vector<int64_t> &off = b->pairOff[list];
+    std::vector<int32_t> tmp;
+    std::vector<std::pair<int64_t, int64_t>> runs; /* [first, last) triple of every block of the region */
+    size_t k = 0;                                  /* position in the compact block order */
+    int64_t cur = 0;                               /* regions come in pair order and own ascending ranges of x + y: one sweep */
+    int32_t pair = -1;
+    for (size_t r = 0; r < b->hRegions.size(); r++) {
+        const RegionDev &R = b->hRegions[r];
+        const int64_t pairEnd = off[R.pair + 1];
+        if (R.pair != pair) {
+            pair = R.pair;
+            cur = off[pair];
+        }
+        const int64_t shift = (int64_t) R.ox + R.oy - 2; /* matrix diagonal d holds the sequence coordinates with x + y = d + shift */
+        runs.clear();
+        const int64_t regionFirst = cur;
+        for (int j = 0; j < R.nBlocks; j++, k++) {
+            const int64_t hi = (int64_t) b->hBlocks[k].from + shift;
+            const int64_t first = cur;
+            while (cur < pairEnd && (int64_t) triples[3 * cur + 1] + triples[3 * cur + 2] <= hi) cur++;
+            runs.emplace_back(first, cur);
+        }
+        if (cur == regionFirst) continue;
+        tmp.resize((size_t) (cur - regionFirst) * 3);
+        int64_t w = 0;
+        for (size_t j = runs.size(); j-- > 0;) {
+            for (int64_t g0 = runs[j].first; g0 < runs[j].second;) {
+                const int64_t sum = (int64_t) triples[3 * g0 + 1] + triples[3 * g0 + 2];
+                int64_t g1 = g0 + 1;
+                while (g1 < runs[j].second && (int64_t) triples[3 * g1 + 1] + triples[3 * g1 + 2] == sum) g1++;
+                for (int64_t t = g1; t-- > g0;) {
+                    memcpy(&tmp[3 * w], &triples[3 * t], 3 * sizeof(int32_t));
+                    w++;
+                }
+                g0 = g1;
+            }
+        }
+        memcpy(&triples[3 * regionFirst], tmp.data(), tmp.size() * sizeof(int32_t));
+    }
+    return CPB_OK;
+}
+
 extern "C" int cpb_batch_fetch_expectations(cpb_batch *b, double *perPair, double *total) {
     if (b == nullptr || b->lastMode != CPB_MODE_EXPECTATIONS) {
         cpb_set_error("cpb_batch_fetch_expectations: last run was not in expectation mode");

@@ -1,0 +1,571 @@
+/*
+ * cPecanRealign -- realigns pairwise alignments (cigars on stdin) with the pair-HMM and writes them back (stdout), or
+ * accumulates EM expectations over them.  Same command line, file formats and per-alignment processing as the reference's
+ * cPecanRealign.c (options :374-473, coordinate handling :509-523, post-processing :546-599, expectations :530-535 and :608-614).
+ *
+ * What is different is the shape of the loop.  The reference runs one alignment at a time through the CPU DP
+ * (cPecanRealign.c:509-605).  Here the cigars are read in batches, every batch goes through ONE device pass
+ * (getAlignedPairsUsingAnchorsBatch / getExpectationsUsingAnchorsBatch of libcpecan.so), and the host only does the list work
+ * either side of it; output order is input order.  There is no host DP: without a CUDA device the program aborts with the
+ * engine's message.
+ */
+#include <ctype.h>
+#include <getopt.h>
+#include <inttypes.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "cpecan/multipleAligner.h"
+#include "cpecan/pairwiseAligner.h"
+#include "cpecan/pairwiseAlignment.h"
+
+/* ---- logging: -a INFO / DEBUG prints progress to stderr, as sonLib's st_logInfo would ---- */
+
+static int logLevel = 0; /* 0 off, 1 info, 2 debug */
+
+static void set_log_level(const char *s) {
+    if (s == NULL) return;
+    char u[16];
+    size_t n = 0;
+    for (; s[n] != '\0' && n + 1 < sizeof(u); n++) u[n] = (char) toupper((unsigned char) s[n]);
+    u[n] = '\0';
+    if (strcmp(u, "INFO") == 0) logLevel = 1;
+    else if (strcmp(u, "DEBUG") == 0) logLevel = 2;
+    else logLevel = 0;
+}
+
+static void log_info(const char *format, ...) {
+    if (logLevel < 1) return;
+    va_list ap;
+    va_start(ap, format);
+    vfprintf(stderr, format, ap);
+    va_end(ap);
+}
+
+static void *xmalloc(size_t bytes) {
+    void *p = malloc(bytes ? bytes : 1);
+    if (p == NULL) st_errAbort("cPecanRealign: out of memory allocating %zu bytes", bytes);
+    return p;
+}
+
+static void usage(void) {
+    fprintf(stderr, "cPecanRelign [options] seq1[fasta] seq2[fasta], version 0.2 (B200 batched engine)\n");
+    fprintf(stderr, "Realigns a set of pairwise alignments, as cigars, read from the command line and written back to the command line\n");
+    fprintf(stderr, "-a --logLevel : Set the log level\n");
+    fprintf(stderr, "-l --gapGamma : (float >= 0) The gap gamma (as in the AMAP function)\n");
+    fprintf(stderr, "-L --matchGamma : (float [0, 1]) The match gamma (the avg. weight or greater to be allowed in the alignment)\n");
+    fprintf(stderr, "-o --splitMatrixBiggerThanThis : (int >= 0)  No dp matrix bigger than this number squared will be computed.\n");
+    fprintf(stderr, "-r --diagonalExpansion : (int >= 0 and even) Number of x-y diagonals to expand around anchors\n");
+    fprintf(stderr, "-t --constraintDiagonalTrim : (int >= 0) Amount to trim from ends of each anchor\n");
+    fprintf(stderr, "-w --alignAmbiguityCharacters : Align ambiguity characters (anything not ACTGactg) as a wildcard\n");
+    fprintf(stderr, "-x --rescoreOriginalAlignment : Rescore the original alignment. The output cigar is the same alignment.\n");
+    fprintf(stderr, "-i --rescoreByIdentity : Set score equal to alignment identity, treating indels as mismatches.\n");
+    fprintf(stderr, "-j --rescoreByPosteriorProb : Set score equal to avg. posterior match probability, treating indels as residues with 0 match probability.\n");
+    fprintf(stderr, "-k --rescoreByIdentityIgnoringGaps : Set score equal to alignment identity, ignoring indels.\n");
+    fprintf(stderr, "-m --rescoreByPosteriorProbIgnoringGaps : Set score equal to avg. posterior match probability, ignoring gaps.\n");
+    fprintf(stderr, "-h --help : Print this help screen\n");
+    fprintf(stderr, "-s --splitIndelsLongerThanThis : Split alignments with consecutive runs of indels that are longer than this.\n");
+    fprintf(stderr, "-u --outputPosteriorProbs [FILE] : Outputs the posterior match probs of positions in the alignment to the given tab separated file, each line being X-coordinate, Y-coordinate, posterior-match prob.\n");
+    fprintf(stderr, "-z --outputAllPosteriorProbs [FILE] : As --outputPosteriorProbs, but for all pairs in the banded alignment\n");
+    fprintf(stderr, "-v --outputExpectations [FILE] : Instead of realigning, switches to calculating expectations, dumping out expectations as matrix in the given file.\n");
+    fprintf(stderr, "-y --loadHmm [FILE] : Loads HMM from given file.\n");
+    fprintf(stderr, "-b --batchBases : (int > 0) Bases of sequence per device pass (default 200000000; not in the reference)\n");
+}
+
+/* ---- sequences by the first word of their FASTA header (cPecanRealign.c:242-274) ---- */
+
+typedef struct {
+    char *name, *seq;
+    int64_t length;
+} NamedSeq;
+static NamedSeq *seqs = NULL; /* open-addressing table, capSeqs a power of two, name == NULL: free slot */
+static int64_t nSeqs = 0, capSeqs = 0;
+
+static uint64_t name_hash(const char *s) {
+    uint64_t h = 1469598103934665603ULL; /* FNV-1a */
+    for (; *s != '\0'; s++) h = (h ^ (unsigned char) *s) * 1099511628211ULL;
+    return h;
+}
+
+/* the slot holding `name`, or the free slot where it would go */
+static NamedSeq *sequence_slot(NamedSeq *table, int64_t cap, const char *name) {
+    for (uint64_t i = name_hash(name) & (uint64_t) (cap - 1);; i = (i + 1) & (uint64_t) (cap - 1)) {
+        if (table[i].name == NULL || strcmp(table[i].name, name) == 0) return &table[i];
+    }
+}
+
+static NamedSeq *find_sequence(const char *name) {
+    if (capSeqs == 0) return NULL;
+    NamedSeq *slot = sequence_slot(seqs, capSeqs, name);
+    return slot->name != NULL ? slot : NULL;
+}
+
+static void add_sequence(const char *header, const char *sequence, int64_t length) {
+    size_t n = 0;
+    while (header[n] != '\0' && !isspace((unsigned char) header[n])) n++;
+    char *name = stString_getSubString(header, 0, (int64_t) n);
+    NamedSeq *old = find_sequence(name);
+    if (old != NULL) {
+        log_info("Got a repeat header: %s with sequence length: %" PRIi64 " vs. the existing sequence of length: %" PRIi64 ", complete header: %s\n", name,
+                 length, old->length, header);
+        if (length > old->length) { /* a more complete version of the same sequence (overlapping fragments) */
+            log_info("Replacing sequence\n");
+            free(old->seq);
+            old->seq = stString_copy(sequence);
+            old->length = length;
+        }
+        free(name);
+        return;
+    }
+    log_info("Adding sequence for header: %s, with length %" PRIi64 ", complete header: %s\n", name, length, header);
+    if (2 * (nSeqs + 1) > capSeqs) {
+        const int64_t cap = capSeqs ? 2 * capSeqs : 1024;
+        NamedSeq *table = xmalloc((size_t) cap * sizeof(NamedSeq));
+        memset(table, 0, (size_t) cap * sizeof(NamedSeq));
+        for (int64_t i = 0; i < capSeqs; i++) {
+            if (seqs[i].name != NULL) *sequence_slot(table, cap, seqs[i].name) = seqs[i];
+        }
+        free(seqs);
+        seqs = table;
+        capSeqs = cap;
+    }
+    NamedSeq *slot = sequence_slot(seqs, capSeqs, name);
+    slot->name = name;
+    slot->seq = stString_copy(sequence);
+    slot->length = length;
+    nSeqs++;
+}
+
+/* ---- coordinates (cPecanRealign.c:220-240, :292-298) ---- */
+
+static void rebase(int64_t *start, int64_t *end, int64_t *strand, int64_t shift, bool flip) {
+    *start += shift;
+    *end += shift;
+    if (flip) {
+        *strand = *strand ? 0 : 1;
+        const int64_t t = *end;
+        *end = *start;
+        *start = t;
+    }
+}
+
+static char *sub_sequence(const char *seq, int64_t start, int64_t end, bool strand) {
+    if (strand) return stString_getSubString(seq, start, end - start);
+    char *fwd = stString_getSubString(seq, end, start - end);
+    char *rc = stString_reverseComplementString(fwd);
+    free(fwd);
+    return rc;
+}
+
+static int64_t transform_coordinate(int64_t c, int64_t shift, bool flip, int64_t seqLength) { return shift + (flip ? seqLength - 1 - c : c); }
+
+static void write_posterior_probs(const char *file, stList *pairs, int64_t shift1, bool flip1, int64_t len1, int64_t shift2, bool flip2, int64_t len2) {
+    FILE *f = fopen(file, "w");
+    if (f == NULL) st_errAbort("cPecanRealign: cannot write %s", file);
+    for (int64_t i = 0; i < stList_length(pairs); i++) {
+        stIntTuple *t = stList_get(pairs, i);
+        fprintf(f, "%" PRIi64 "\t%" PRIi64 "\t%f\n", transform_coordinate(stIntTuple_get(t, 1), shift1, flip1, len1),
+                transform_coordinate(stIntTuple_get(t, 2), shift2, flip2, len2), ((double) stIntTuple_get(t, 0)) / PAIR_ALIGNMENT_PROB_1);
+    }
+    fclose(f);
+}
+
+/* ---- the original alignment's columns with their posterior weights (cPecanRealign.c:322-353) ---- */
+
+static int by_xy(const void *a, const void *b) {
+    const int64_t *p = a, *q = b;
+    if (p[0] != q[0]) return p[0] < q[0] ? -1 : 1;
+    return p[1] < q[1] ? -1 : (p[1] > q[1] ? 1 : 0);
+}
+
+static stList *score_anchor_pairs(stList *anchorPairs, stList *alignedPairs) {
+    const int64_t n = stList_length(anchorPairs);
+    int64_t *a = xmalloc((size_t) n * 3 * sizeof(int64_t)); /* (x, y, weight or -1 = not seen) */
+    for (int64_t i = 0; i < n; i++) {
+        stIntTuple *t = stList_get(anchorPairs, i);
+        a[3 * i] = stIntTuple_get(t, 0);
+        a[3 * i + 1] = stIntTuple_get(t, 1);
+        a[3 * i + 2] = -1;
+    }
+    qsort(a, (size_t) n, 3 * sizeof(int64_t), by_xy);
+    stList *scored = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    for (int64_t i = 0; i < stList_length(alignedPairs); i++) {
+        stIntTuple *t = stList_get(alignedPairs, i);
+        int64_t key[3] = { stIntTuple_get(t, 1), stIntTuple_get(t, 2), 0 };
+        int64_t *hit = bsearch(key, a, (size_t) n, 3 * sizeof(int64_t), by_xy);
+        if (hit != NULL && hit[2] < 0) {
+            hit[2] = stIntTuple_get(t, 0);
+            stList_append(scored, stIntTuple_construct3(hit[2], hit[0], hit[1]));
+        }
+    }
+    /* columns of the original alignment below the posterior threshold get weight 0 */
+    for (int64_t i = 0; i < n; i++) {
+        if (a[3 * i + 2] < 0) stList_append(scored, stIntTuple_construct3(0, a[3 * i], a[3 * i + 1]));
+    }
+    free(a);
+    return scored;
+}
+
+/* ---- aligned pairs -> cigar (cPecanRealign.c:50-92) ---- */
+
+static void add_op(struct List *ops, int64_t type, int64_t length) { listAppend(ops, constructAlignmentOperation(type, length, 0)); }
+
+/* xy: (x, y) tuples sorted ascending */
+static struct PairwiseAlignment *pairs_to_alignment(const char *name1, const char *name2, double score, int64_t length1, int64_t length2,
+                                                    stList *xy) {
+    struct List *ops = constructEmptyList(0, (void (*)(void *)) destructAlignmentOperation);
+    int64_t pX = -1, pY = -1, run = 0;
+    const int64_t n = stList_length(xy);
+    for (int64_t i = 0; i <= n; i++) { /* a closing pair at (length1, length2) produces the trailing indels */
+        const int64_t x = i < n ? stIntTuple_get(stList_get(xy, i), 0) : length1;
+        const int64_t y = i < n ? stIntTuple_get(stList_get(xy, i), 1) : length2;
+        if (x - pX > 0 && y - pY > 0) { /* pairs that do not advance both sequences are dropped */
+            if (x - pX > 1) {
+                if (run > 0) add_op(ops, PAIRWISE_MATCH, run);
+                run = 0;
+                add_op(ops, PAIRWISE_INDEL_X, x - pX - 1);
+            }
+            if (y - pY > 1) {
+                if (run > 0) add_op(ops, PAIRWISE_MATCH, run);
+                run = 0;
+                add_op(ops, PAIRWISE_INDEL_Y, y - pY - 1);
+            }
+            run++;
+            pX = x;
+            pY = y;
+        }
+    }
+    if (run > 1) add_op(ops, PAIRWISE_MATCH, run - 1); /* the closing pair itself is not a column */
+    return constructPairwiseAlignment(name1, 0, length1, 1, name2, 0, length2, 1, score, ops);
+}
+
+/* ---- splitting at long indel runs (cPecanRealign.c:94-218) ---- */
+
+static void flush_piece(stList *pieces, const struct PairwiseAlignment *pA, struct List **ops, int64_t start1, int64_t end1, int64_t start2, int64_t end2) {
+    if ((*ops)->length != 0) {
+        stList_append(pieces, constructPairwiseAlignment(pA->contig1, start1, end1, pA->strand1, pA->contig2, start2, end2, pA->strand2, pA->score, *ops));
+    } else {
+        destructList(*ops);
+    }
+    *ops = constructEmptyList(0, (void (*)(void *)) destructAlignmentOperation);
+}
+
+static stList *split_alignment(const struct PairwiseAlignment *pA, int64_t maxIndelLength) {
+    stList *pieces = stList_construct3(0, (void (*)(void *)) destructPairwiseAlignment);
+    struct List *ops = constructEmptyList(0, (void (*)(void *)) destructAlignmentOperation);
+    struct List *pending = constructEmptyList(0, NULL); /* the indel run since the last match: kept only if a match follows */
+    int64_t pos1 = pA->start1, pos2 = pA->start2, start1 = pos1, start2 = pos2, end1 = 0, end2 = 0, indelRun = 0;
+    const int64_t step1 = pA->strand1 ? 1 : -1, step2 = pA->strand2 ? 1 : -1;
+    for (int64_t i = 0; i < pA->operationList->length; i++) {
+        const struct AlignmentOperation *op = pA->operationList->list[i];
+        if (op->opType == PAIRWISE_MATCH) {
+            if ((indelRun > maxIndelLength && ops->length != 0) || ops->length == 0) {
+                /* an over-long run ends the piece before it; a run at the very start is dropped as well */
+                if (ops->length != 0) flush_piece(pieces, pA, &ops, start1, end1, start2, end2);
+                for (int64_t j = 0; j < pending->length; j++) destructAlignmentOperation(pending->list[j]);
+                pending->length = 0;
+                start1 = end1 = pos1;
+                start2 = end2 = pos2;
+            }
+            indelRun = 0;
+            for (int64_t j = 0; j < pending->length; j++) listAppend(ops, pending->list[j]);
+            pending->length = 0;
+            pos1 += step1 * op->length;
+            pos2 += step2 * op->length;
+            end1 = pos1;
+            end2 = pos2;
+            listAppend(ops, constructAlignmentOperation(op->opType, op->length, op->score));
+        } else {
+            indelRun += op->length;
+            if (op->opType == PAIRWISE_INDEL_X) pos1 += step1 * op->length;
+            else pos2 += step2 * op->length;
+            listAppend(pending, constructAlignmentOperation(op->opType, op->length, op->score));
+        }
+    }
+    flush_piece(pieces, pA, &ops, start1, end1, start2, end2);
+    destructList(ops);
+    for (int64_t j = 0; j < pending->length; j++) destructAlignmentOperation(pending->list[j]);
+    destructList(pending);
+    for (int64_t i = 0; i < stList_length(pieces); i++) checkPairwiseAlignment(stList_get(pieces, i));
+    return pieces;
+}
+
+/* ---- one input alignment, prepared for the device pass ---- */
+
+typedef struct {
+    struct PairwiseAlignment *pA; /* rebased to the forward strand, starting at 0 */
+    char *subX, *subY;
+    bool flip1, flip2;
+    int64_t shift1, shift2;
+    stList *anchors;  /* every column of the input alignment (after trim) */
+    stList *filtered; /* those whose two bases agree (and are not N): what constrains the band */
+} Job;
+
+static bool columns_match(const Job *j, stIntTuple *t) {
+    const int x = toupper((unsigned char) j->subX[stIntTuple_get(t, 0)]), y = toupper((unsigned char) j->subY[stIntTuple_get(t, 1)]);
+    return x == y && x != 'N';
+}
+
+static void job_prepare(Job *j, struct PairwiseAlignment *pA, const PairwiseAlignmentParameters *p) {
+    log_info("Processing alignment for sequences: %s and %s\n", pA->contig1, pA->contig2);
+    const NamedSeq *sX = find_sequence(pA->contig1), *sY = find_sequence(pA->contig2);
+    if (sX == NULL || sY == NULL) st_errAbort("cPecanRealign: no sequence named %s in the input files", sX == NULL ? pA->contig1 : pA->contig2);
+    const int64_t hi1 = pA->strand1 ? pA->end1 : pA->start1, hi2 = pA->strand2 ? pA->end2 : pA->start2;
+    if (hi1 > sX->length || hi2 > sY->length || pA->start1 < 0 || pA->end1 < 0 || pA->start2 < 0 || pA->end2 < 0) {
+        st_errAbort("cPecanRealign: alignment of %s and %s reaches beyond the end of a sequence", pA->contig1, pA->contig2);
+    }
+    j->pA = pA;
+    j->flip1 = !pA->strand1;
+    j->flip2 = !pA->strand2;
+    j->shift1 = pA->strand1 ? pA->start1 : pA->end1;
+    j->shift2 = pA->strand2 ? pA->start2 : pA->end2;
+    j->subX = sub_sequence(sX->seq, pA->start1, pA->end1, pA->strand1 != 0);
+    j->subY = sub_sequence(sY->seq, pA->start2, pA->end2, pA->strand2 != 0);
+    rebase(&pA->start1, &pA->end1, &pA->strand1, -j->shift1, j->flip1);
+    rebase(&pA->start2, &pA->end2, &pA->strand2, -j->shift2, j->flip2);
+    checkPairwiseAlignment(pA);
+    j->anchors = convertPairwiseForwardStrandAlignmentToAnchorPairs(pA, p->constraintDiagonalTrim, p->diagonalExpansion);
+    j->filtered = stList_construct(); /* borrows the tuples of j->anchors */
+    for (int64_t i = 0; i < stList_length(j->anchors); i++) {
+        stIntTuple *t = stList_get(j->anchors, i);
+        if (columns_match(j, t)) stList_append(j->filtered, t);
+    }
+}
+
+static void job_release(Job *j) {
+    destructPairwiseAlignment(j->pA);
+    stList_destruct(j->filtered);
+    stList_destruct(j->anchors);
+    free(j->subX);
+    free(j->subY);
+}
+
+typedef struct {
+    float matchGamma;
+    bool rescoreOriginalAlignment, rescoreByIdentity, rescoreByPosteriorProbability, rescoreByIdentityIgnoringGaps,
+        rescoreByPosteriorProbabilityIgnoringGaps;
+    int64_t splitIndelsLongerThanThis; /* -1 = never */
+    const char *posteriorProbsFile, *allPosteriorProbsFile;
+} Options;
+
+/* everything after the device pass for one alignment (cPecanRealign.c:540-599); consumes alignedPairs */
+static void job_finish(Job *j, stList *alignedPairs, const Options *o, const PairwiseAlignmentParameters *p, FILE *out) {
+    struct PairwiseAlignment *pA = j->pA;
+    const int64_t lX = (int64_t) strlen(j->subX), lY = (int64_t) strlen(j->subY);
+    if (o->allPosteriorProbsFile != NULL) {
+        write_posterior_probs(o->allPosteriorProbsFile, alignedPairs, j->shift1, j->flip1, pA->end1 - pA->start1, j->shift2, j->flip2, pA->end2 - pA->start2);
+    }
+    if (o->rescoreOriginalAlignment) {
+        stList *rescored = score_anchor_pairs(j->anchors, alignedPairs);
+        stList_destruct(alignedPairs);
+        alignedPairs = rescored;
+    } else {
+        alignedPairs = reweightAlignedPairs2(alignedPairs, lX, lY, p->gapGamma);
+        alignedPairs = filterPairwiseAlignmentToMakePairsOrdered(alignedPairs, j->subX, j->subY, o->matchGamma);
+    }
+    if (o->rescoreByPosteriorProbability) pA->score = scoreByPosteriorProbability(lX, lY, alignedPairs);
+    else if (o->rescoreByPosteriorProbabilityIgnoringGaps) pA->score = scoreByPosteriorProbabilityIgnoringGaps(alignedPairs);
+    else if (o->rescoreByIdentity) pA->score = scoreByIdentity(j->subX, j->subY, lX, lY, alignedPairs);
+    else if (o->rescoreByIdentityIgnoringGaps) pA->score = scoreByIdentityIgnoringGaps(j->subX, j->subY, alignedPairs);
+    if (o->posteriorProbsFile != NULL) {
+        write_posterior_probs(o->posteriorProbsFile, alignedPairs, j->shift1, j->flip1, pA->end1 - pA->start1, j->shift2, j->flip2, pA->end2 - pA->start2);
+    }
+    /* (weight, x, y) -> (x, y), ascending */
+    stList *xy = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    for (int64_t i = 0; i < stList_length(alignedPairs); i++) {
+        stIntTuple *t = stList_get(alignedPairs, i);
+        stList_append(xy, stIntTuple_construct2(stIntTuple_get(t, 1), stIntTuple_get(t, 2)));
+    }
+    stList_destruct(alignedPairs);
+    stList_sort(xy, stIntTuple_cmpFn);
+    struct PairwiseAlignment *rPA = pairs_to_alignment(pA->contig1, pA->contig2, pA->score, pA->end1, pA->end2, xy);
+    rebase(&rPA->start1, &rPA->end1, &rPA->strand1, j->shift1, j->flip1);
+    rebase(&rPA->start2, &rPA->end2, &rPA->strand2, j->shift2, j->flip2);
+    checkPairwiseAlignment(rPA);
+    if (o->splitIndelsLongerThanThis != -1) {
+        stList *pieces = split_alignment(rPA, o->splitIndelsLongerThanThis);
+        for (int64_t i = 0; i < stList_length(pieces); i++) cigarWrite(out, stList_get(pieces, i), 0);
+        stList_destruct(pieces);
+    } else {
+        cigarWrite(out, rPA, 0);
+    }
+    stList_destruct(xy);
+    destructPairwiseAlignment(rPA);
+}
+
+static int64_t parse_int(const char *arg, const char *what) {
+    char *end;
+    const long long v = strtoll(arg, &end, 10);
+    if (end == arg || *end != '\0' || v < 0) st_errAbort("cPecanRealign: %s needs a non-negative integer, got '%s'", what, arg);
+    return (int64_t) v;
+}
+
+static float parse_float(const char *arg, const char *what) {
+    char *end;
+    const float v = strtof(arg, &end);
+    if (end == arg || *end != '\0' || !(v >= 0.0f)) st_errAbort("cPecanRealign: %s needs a non-negative number, got '%s'", what, arg);
+    return v;
+}
+
+int main(int argc, char *argv[]) {
+    PairwiseAlignmentParameters *p = pairwiseAlignmentBandingParameters_construct();
+    p->constraintDiagonalTrim = 0; /* the CLI's own defaults (cPecanRealign.c:359-361) */
+    p->splitMatrixBiggerThanThis = 10;
+    p->diagonalExpansion = 4;
+    Options o;
+    memset(&o, 0, sizeof(o));
+    o.matchGamma = 0.85f;
+    o.splitIndelsLongerThanThis = -1;
+    const char *expectationsFile = NULL, *hmmFile = NULL;
+    int64_t batchBases = 200000000;
+
+    static struct option longOptions[] = { { "logLevel", required_argument, 0, 'a' },
+                                           { "help", no_argument, 0, 'h' },
+                                           { "gapGamma", required_argument, 0, 'l' },
+                                           { "matchGamma", required_argument, 0, 'L' },
+                                           { "splitMatrixBiggerThanThis", required_argument, 0, 'o' },
+                                           { "diagonalExpansion", required_argument, 0, 'r' },
+                                           { "constraintDiagonalTrim", required_argument, 0, 't' },
+                                           { "alignAmbiguityCharacters", no_argument, 0, 'w' },
+                                           { "rescoreOriginalAlignment", no_argument, 0, 'x' },
+                                           { "rescoreByIdentity", no_argument, 0, 'i' },
+                                           { "rescoreByPosteriorProb", no_argument, 0, 'j' },
+                                           { "rescoreByPosteriorProbIgnoringGaps", no_argument, 0, 'm' },
+                                           { "rescoreByIdentityIgnoringGaps", no_argument, 0, 'k' },
+                                           { "splitIndelsLongerThanThis", required_argument, 0, 's' },
+                                           { "outputPosteriorProbs", required_argument, 0, 'u' },
+                                           { "outputAllPosteriorProbs", required_argument, 0, 'z' },
+                                           { "outputExpectations", required_argument, 0, 'v' },
+                                           { "loadHmm", required_argument, 0, 'y' },
+                                           { "batchBases", required_argument, 0, 'b' },
+                                           { 0, 0, 0, 0 } };
+    for (;;) {
+        int index = 0;
+        const int key = getopt_long(argc, argv, "a:hl:o:r:t:s:wxijkmu:v:y:z:L:b:", longOptions, &index);
+        if (key == -1) break;
+        switch (key) {
+        case 'a': set_log_level(optarg); break;
+        case 'h': usage(); return 0;
+        case 'l': p->gapGamma = parse_float(optarg, "--gapGamma"); break;
+        case 'L': o.matchGamma = parse_float(optarg, "--matchGamma"); break;
+        case 'o': {
+            const int64_t side = parse_int(optarg, "--splitMatrixBiggerThanThis");
+            p->splitMatrixBiggerThanThis = side * side;
+            break;
+        }
+        case 'r':
+            p->diagonalExpansion = parse_int(optarg, "--diagonalExpansion");
+            if (p->diagonalExpansion % 2 != 0) st_errAbort("cPecanRealign: --diagonalExpansion must be even");
+            break;
+        case 't': p->constraintDiagonalTrim = parse_int(optarg, "--constraintDiagonalTrim"); break;
+        case 'w': p->alignAmbiguityCharacters = 1; break;
+        case 'x': o.rescoreOriginalAlignment = 1; break;
+        case 'i': o.rescoreByIdentity = 1; break;
+        case 'j': o.rescoreByPosteriorProbability = 1; break;
+        case 'k': o.rescoreByIdentityIgnoringGaps = 1; break;
+        case 'm': o.rescoreByPosteriorProbabilityIgnoringGaps = 1; break;
+        case 's': o.splitIndelsLongerThanThis = parse_int(optarg, "--splitIndelsLongerThanThis"); break;
+        case 'u': o.posteriorProbsFile = optarg; break;
+        case 'v': expectationsFile = optarg; break;
+        case 'y': hmmFile = optarg; break;
+        case 'z': o.allPosteriorProbsFile = optarg; break;
+        case 'b':
+            batchBases = parse_int(optarg, "--batchBases");
+            if (batchBases == 0) st_errAbort("cPecanRealign: --batchBases must be positive");
+            break;
+        default: usage(); return 1;
+        }
+    }
+    log_info("Starting realigning pairwise alignments\n");
+
+    StateMachine *sM;
+    if (hmmFile != NULL) {
+        log_info("Loading the hmm from file %s\n", hmmFile);
+        Hmm *hmm = hmm_loadFromFile(hmmFile);
+        sM = hmm_getStateMachine(hmm);
+        hmm_destruct(hmm);
+    } else {
+        sM = stateMachine5_construct(fiveState);
+    }
+    Hmm *hmmExpectations = expectationsFile != NULL ? hmm_constructEmpty(0.000000000001, sM->type) : NULL; /* the tiny pseudo-count prevents overflow */
+
+    if (optind >= argc) {
+        usage();
+        return 1;
+    }
+    while (optind < argc) {
+        FILE *f = fopen(argv[optind], "r");
+        if (f == NULL) st_errAbort("cPecanRealign: cannot read %s", argv[optind]);
+        fastaReadToFunction(f, add_sequence);
+        fclose(f);
+        optind++;
+    }
+
+    /* read a batch of cigars, one device pass, finish and write them in order; repeat */
+    Job *jobs = NULL;
+    int64_t capJobs = 0;
+    bool more = true;
+    while (more) {
+        int64_t n = 0, bases = 0;
+        while (bases < batchBases) {
+            struct PairwiseAlignment *pA = cigarRead(stdin);
+            if (pA == NULL) {
+                more = false;
+                break;
+            }
+            if (n == capJobs) {
+                capJobs = capJobs ? 2 * capJobs : 1024;
+                jobs = realloc(jobs, (size_t) capJobs * sizeof(Job));
+                if (jobs == NULL) st_errAbort("cPecanRealign: out of memory");
+            }
+            job_prepare(&jobs[n], pA, p);
+            bases += pA->end1 + pA->end2;
+            n++;
+        }
+        if (n == 0) break;
+        const char **sX = xmalloc((size_t) n * sizeof(char *)), **sY = xmalloc((size_t) n * sizeof(char *));
+        stList **anchors = xmalloc((size_t) n * sizeof(stList *));
+        bool *ragged = xmalloc((size_t) n * sizeof(bool));
+        for (int64_t i = 0; i < n; i++) {
+            sX[i] = jobs[i].subX;
+            sY[i] = jobs[i].subY;
+            anchors[i] = jobs[i].filtered;
+            ragged[i] = 1; /* both ends of a local alignment are ragged (cPecanRealign.c:532, :537) */
+        }
+        log_info("Device pass over %" PRIi64 " alignments, %" PRIi64 " bases\n", n, bases);
+        if (hmmExpectations != NULL) {
+            getExpectationsUsingAnchorsBatch(sM, hmmExpectations, n, sX, sY, anchors, p, ragged, ragged);
+        } else {
+            stList **pairs = getAlignedPairsUsingAnchorsBatch(sM, n, sX, sY, anchors, p, ragged, ragged);
+            for (int64_t i = 0; i < n; i++) job_finish(&jobs[i], pairs[i], &o, p, stdout);
+            free(pairs);
+        }
+        for (int64_t i = 0; i < n; i++) job_release(&jobs[i]);
+        free(sX);
+        free(sY);
+        free(anchors);
+        free(ragged);
+    }
+    free(jobs);
+
+    if (hmmExpectations != NULL) {
+        log_info("Writing out expectations to file %s\n", expectationsFile);
+        FILE *f = fopen(expectationsFile, "w");
+        if (f == NULL) st_errAbort("cPecanRealign: cannot write %s", expectationsFile);
+        hmm_write(hmmExpectations, f);
+        fclose(f);
+        hmm_destruct(hmmExpectations);
+    }
+    for (int64_t i = 0; i < capSeqs; i++) {
+        free(seqs[i].name);
+        free(seqs[i].seq);
+    }
+    free(seqs);
+    stateMachine_destruct(sM);
+    pairwiseAlignmentBandingParameters_destruct(p);
+    cpecan_shutdown();
+    log_info("Finished realigning pairwise alignments, exiting.\n");
+    return 0;
+}

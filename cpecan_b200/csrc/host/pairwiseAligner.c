@@ -219,7 +219,8 @@ static stList **fetch_lists(cpb_batch *b, int64_t n, int which) {
     const int64_t total = cpb_batch_result_count(b, which);
     int64_t *off = cpecan_malloc((size_t) (n + 1) * sizeof(int64_t));
     int32_t *tri = cpecan_malloc((size_t) (3 * total + 3) * sizeof(int32_t));
-    if (cpb_batch_fetch_pairs(b, which, off, tri) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
+    /* same list order as the reference's own lists (its callers may depend on it, e.g. the MEA walk-back) */
+    if (cpb_batch_fetch_pairs_reference_order(b, which, off, tri) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
     stList **lists = cpecan_malloc((size_t) (n > 0 ? n : 1) * sizeof(stList *));
     for (int64_t i = 0; i < n; i++) {
         lists[i] = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);

@@ -114,6 +114,29 @@ Symbol *symbol_convertStringToSymbols(const char *s, int64_t sL);
 stList *getSplitPoints(stList *anchorPairs, int64_t lX, int64_t lY, int64_t maxMatrixSize, bool alignmentHasRaggedLeftEnd,
                        bool alignmentHasRaggedRightEnd);
 
+/* ---- after the device pass: host-side list work on the compacted output (cpecan_b200/csrc/host/realign.c) ---- */
+
+struct PairwiseAlignment; /* cpecan/pairwiseAlignment.h */
+
+/* :73 -- (x, y, diagonalExpansion) for every column of every match run of a forward-strand cigar, `trim` columns dropped at both ends */
+stList *convertPairwiseForwardStrandAlignmentToAnchorPairs(struct PairwiseAlignment *pA, int64_t trim, int64_t diagonalExpansion);
+/* :85-99 -- maximal expected accuracy subset of alignedPairs, its left shift, and both after an alignment */
+stList *getMaximalExpectedAccuracyPairwiseAlignment(stList *alignedPairs, stList *gapXPairs, stList *gapYPairs, int64_t seqXLength,
+                                                    int64_t seqYLength, double *alignmentScore, PairwiseAlignmentParameters *p);
+stList *leftShiftAlignment(stList *alignedPairs, char *seqX, char *seqY);
+stList *getShiftedMEAAlignment(char *seqX, char *seqY, stList *anchorAlignment, PairwiseAlignmentParameters *p, StateMachine *sM,
+                               bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd, double *alignmentScore);
+/* :272-278 -- probability of each position being aligned to a gap, and weights reduced by gapGamma times it (consumes alignedPairs) */
+int64_t *getIndelProbabilities(stList *alignedPairs, int64_t seqLength, bool xIfTrueElseY);
+stList *reweightAlignedPairs(stList *alignedPairs, int64_t *indelProbsX, int64_t *indelProbsY, double gapGamma);
+stList *reweightAlignedPairs2(stList *alignedPairs, int64_t seqLengthX, int64_t seqLengthY, double gapGamma);
+/* :287-307 */
+int64_t getNumberOfMatchingAlignedPairs(char *subSeqX, char *subSeqY, stList *alignedPairs);
+double scoreByIdentity(char *subSeqX, char *subSeqY, int64_t lX, int64_t lY, stList *alignedPairs);
+double scoreByIdentityIgnoringGaps(char *subSeqX, char *subSeqY, stList *alignedPairs);
+double scoreByPosteriorProbability(int64_t lX, int64_t lY, stList *alignedPairs);
+double scoreByPosteriorProbabilityIgnoringGaps(stList *alignedPairs);
+
 /* ---- batched entry points (not in the reference) ---- */
 
 /* Anchor provider used by getAlignedPairs / getAlignedPairsWithIndels / getExpectations for matrices bigger than

@@ -145,6 +145,10 @@ void cpb_batch_stats(const cpb_batch *b, CpbRunStats *out);
  * coordinates, grouped by pair in input order; within a pair: region, block, diagonal (x+y) and x ascending. */
 int64_t cpb_batch_result_count(const cpb_batch *b, int list);
 int cpb_batch_fetch_pairs(cpb_batch *b, int list, int64_t *offsets, int32_t *triples);
+/* As cpb_batch_fetch_pairs, with every pair's triples in the order the reference's own lists have (regions ascending; inside a region
+ * the traceback blocks last to first; inside a block x+y ascending and x descending): what libcpecan.so returns, so that callers whose
+ * result depends on list order (impl/pairwiseAligner.c:1603-1724) behave as with the reference. */
+int cpb_batch_fetch_pairs_reference_order(cpb_batch *b, int list, int64_t *offsets, int32_t *triples);
 /* device pointers of the same (valid until the next run / destroy) */
 const int32_t *cpb_batch_device_triples(const cpb_batch *b, int list);
 /* EXPECTATIONS mode: perPair (may be NULL) receives n * CPB_HMM_LEN(S) doubles, total receives CPB_HMM_LEN(S) doubles

@@ -275,3 +275,66 @@ void orc_batch(const OrcModel *m, const OrcParams *o, int64_t nPairs, const char
     free(args);
     free(th);
 }
+
+/* ---- the reference's list post-processing (impl/pairwiseAligner.c:979-1003, :1519-1792), for tests of cpecan_b200/csrc/host/realign.c ---- */
+
+int64_t orc_cigar_anchors(const int64_t *ops, int64_t nOps, int64_t start1, int64_t start2, int64_t trim, int64_t expansion, int64_t *out,
+        int64_t cap) {
+    /* ops: (type, length) with type 0 = match, 1 = indel X, 2 = indel Y */
+    struct List opList;
+    struct AlignmentOperation *store = st_malloc(sizeof(struct AlignmentOperation) * (nOps + 1));
+    void **ptrs = st_malloc(sizeof(void *) * (nOps + 1));
+    struct PairwiseAlignment pA;
+    memset(&pA, 0, sizeof(pA));
+    pA.start1 = pA.end1 = start1;
+    pA.start2 = pA.end2 = start2;
+    pA.strand1 = pA.strand2 = 1;
+    for (int64_t i = 0; i < nOps; i++) {
+        store[i].opType = ops[2 * i] == 0 ? PAIRWISE_MATCH : (ops[2 * i] == 1 ? PAIRWISE_INDEL_X : PAIRWISE_INDEL_Y);
+        store[i].length = ops[2 * i + 1];
+        store[i].score = 0;
+        ptrs[i] = &store[i];
+        if (ops[2 * i] != 2) pA.end1 += ops[2 * i + 1];
+        if (ops[2 * i] != 1) pA.end2 += ops[2 * i + 1];
+    }
+    opList.list = ptrs;
+    opList.length = nOps;
+    pA.operationList = &opList;
+    int64_t n = drain(convertPairwiseForwardStrandAlignmentToAnchorPairs(&pA, trim, expansion), out, cap);
+    free(store);
+    free(ptrs);
+    return n;
+}
+
+int64_t orc_reweight(const int64_t *pairs, int64_t n, int64_t lX, int64_t lY, double gapGamma, int64_t *out) {
+    return drain(reweightAlignedPairs2(toAnchors(pairs, n), lX, lY, gapGamma), out, n);
+}
+
+void orc_scores(const char *sX, const char *sY, const int64_t *pairs, int64_t n, double *out4) {
+    stList *l = toAnchors(pairs, n);
+    out4[0] = scoreByIdentity((char *) sX, (char *) sY, strlen(sX), strlen(sY), l);
+    out4[1] = scoreByIdentityIgnoringGaps((char *) sX, (char *) sY, l);
+    out4[2] = scoreByPosteriorProbability(strlen(sX), strlen(sY), l);
+    out4[3] = scoreByPosteriorProbabilityIgnoringGaps(l);
+    stList_destruct(l);
+}
+
+int64_t orc_mea(const int64_t *pairs, int64_t n, const int64_t *gapX, int64_t nX, const int64_t *gapY, int64_t nY, int64_t lX, int64_t lY,
+        double gapGamma, int64_t *out, double *score) {
+    PairwiseAlignmentParameters *p = pairwiseAlignmentBandingParameters_construct();
+    p->gapGamma = gapGamma;
+    stList *a = toAnchors(pairs, n), *x = toAnchors(gapX, nX), *y = toAnchors(gapY, nY);
+    int64_t k = drain(getMaximalExpectedAccuracyPairwiseAlignment(a, x, y, lX, lY, score, p), out, n);
+    stList_destruct(a);
+    stList_destruct(x);
+    stList_destruct(y);
+    pairwiseAlignmentBandingParameters_destruct(p);
+    return k;
+}
+
+int64_t orc_left_shift(const int64_t *pairs, int64_t n, const char *sX, const char *sY, int64_t *out, int64_t cap) {
+    stList *a = toAnchors(pairs, n);
+    int64_t k = drain(leftShiftAlignment(a, (char *) sX, (char *) sY), out, cap);
+    stList_destruct(a);
+    return k;
+}

@@ -38,6 +38,8 @@ def run_batch(ctx, spec, p, cases, mode):
 def check_aligned_pairs(ctx, oracle, spec, p, cases, what):
     b = run_batch(ctx, spec, p, cases, cp.MODE_ALIGNED_PAIRS)
     off, tri = b.fetch_pairs(0)
+    off2, tri2 = b.fetch_pairs(0, reference_order=True)
+    assert np.array_equal(off, off2)
     op = helpers.orc_params_from(p)
     om = spec.orc()
     nd = 0
@@ -46,6 +48,8 @@ def check_aligned_pairs(ctx, oracle, spec, p, cases, what):
         want = oracle.aligned_pairs(om, op, c[0], c[1], c[2], c[3], c[4])
         got = tri[off[i]:off[i + 1]]
         nd += compare_triples(got, want, "%s case %d (lX %d lY %d)" % (what, i, len(c[0]), len(c[1])))
+        # the reference-order fetch reproduces the reference's list element for element (impl/pairwiseAligner.c:1411-1418)
+        assert np.array_equal(tri2[off[i]:off[i + 1], 1:], want[:, 1:]), "%s case %d: list order differs from the reference's" % (what, i)
         total += want.shape[0]
     b.close()
     # last-bit exp() differences must be vanishingly rare
@@ -215,11 +219,13 @@ def test_indel_posteriors(ctx, oracle, type_):
     cases = small_cases(rng, 30, 150, ragged=True)
     b = run_batch(ctx, spec, p, cases, cp.MODE_ALIGNED_PAIRS_INDELS)
     res = [b.fetch_pairs(k) for k in range(3)]
+    res2 = [b.fetch_pairs(k, reference_order=True) for k in range(3)]
     for i, c in enumerate(cases):
         want = oracle.aligned_pairs_with_indels(spec.orc(), helpers.orc_params_from(p), c[0], c[1], c[2], c[3], c[4])
         for k in range(3):
             off, tri = res[k]
             compare_triples(tri[off[i]:off[i + 1]], want[k], "indel list %d case %d" % (k, i))
+            assert np.array_equal(res2[k][1][off[i]:off[i + 1], 1:], want[k][:, 1:]), "indel list %d case %d: list order" % (k, i)
     b.close()
 
 

@@ -44,9 +44,9 @@ def test_host_library_exports_every_declared_symbol():
     build_exe()
     out = subprocess.check_output(["nm", "-D", "--defined-only", HOST_SO], text=True)
     exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
-    for h in ("sonLibLite.h", "stateMachine.h", "pairwiseAligner.h"):
+    for h in ("sonLibLite.h", "stateMachine.h", "pairwiseAligner.h", "pairwiseAlignment.h", "multipleAligner.h"):
         names = declared_functions(os.path.join(ROOT, "include", "cpecan", h))
-        assert len(names) > 10, h
+        assert len(names) > (0 if h == "multipleAligner.h" else 10), h
         missing = [n for n in names if n not in exported]
         assert not missing, "%s declares functions libcpecan.so does not export: %s" % (h, missing)
 

@@ -52,6 +52,27 @@ template <int MODE> __global__ void thr(double *out, double a, double b) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// pipe overlap: does an SMSP issue FP64 (DADD), ALU (SEL) and FMA-pipe (IMAD) instructions concurrently, or do the
+// 16-lane pipes serialise at the dispatch port?  Each mode runs 8 independent chains per op class per iteration.
+template <int MODE> __global__ void mix(double *out, double a, double b, int sel) {
+    double x[8];
+    int u[8], v[8];
+    for (int k = 0; k < 8; k++) { x[k] = a + threadIdx.x * 1e-6 + k; u[k] = threadIdx.x + k; v[k] = sel + k + 3 * threadIdx.x; }
+#pragma unroll 4
+    for (int i = 0; i < ITER; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (MODE & 1) x[k] = __dadd_rn(x[k], b);
+            if (MODE & 2) asm volatile("{ .reg .pred p; setp.lt.s32 p, %1, %2; selp.b32 %0, %0, %3, p; }" : "+r"(u[k]) : "r"(sel), "r"(0), "r"(v[k]));
+            if (MODE & 4) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(v[k]) : "r"(sel), "r"(3));
+        }
+    }
+    double s = 0;
+    for (int k = 0; k < 8; k++) s += x[k] + u[k] + v[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main() {
     double *out;
     long long *cyc, h[16] = {0};
@@ -91,6 +112,30 @@ int main() {
             }
             const double ops = (double) blocks * threads * ITER * 8;
             printf("throughput %-30s warps/SM %2d: %.1f lane-ops/clk/SM (at 1.965 GHz)\n", tn[m], warps, ops / (ms * 1e-3) / 148 / 1.965e9);
+        }
+    }
+
+    const char *mn[] = { "", "DADD", "SEL", "DADD+SEL", "IMAD", "DADD+IMAD", "SEL+IMAD", "DADD+SEL+IMAD" };
+    for (int warps = 4; warps <= 16; warps *= 2) {
+        for (int m = 1; m < 8; m++) {
+            const int blocks = 148 * 4, threads = 32 * warps / 4;
+            float ms = 0;
+            for (int rep = 0; rep < 2; rep++) {
+                cudaEventRecord(e0);
+                if (m == 1) mix<1><<<blocks, threads>>>(out, 1.0, 1e-9, 5);
+                if (m == 2) mix<2><<<blocks, threads>>>(out, 1.0, 1e-9, 5);
+                if (m == 3) mix<3><<<blocks, threads>>>(out, 1.0, 1e-9, 5);
+                if (m == 4) mix<4><<<blocks, threads>>>(out, 1.0, 1e-9, 5);
+                if (m == 5) mix<5><<<blocks, threads>>>(out, 1.0, 1e-9, 5);
+                if (m == 6) mix<6><<<blocks, threads>>>(out, 1.0, 1e-9, 5);
+                if (m == 7) mix<7><<<blocks, threads>>>(out, 1.0, 1e-9, 5);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                cudaEventElapsedTime(&ms, e0, e1);
+            }
+            // cycles one SMSP spends per (8 ops of each class), all its warps taken together
+            const double cyc = ms * 1e-3 * 1.965e9 / ITER / (warps / 4.0);
+            printf("mix %-14s warps/SM %2d: %.1f SMSP-cycles per 8 warp-instructions of each class\n", mn[m], warps, cyc);
         }
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
