@@ -217,6 +217,7 @@ struct cpb_batch {
     /* run state */
     DevBuf strips;
     DevBuf regions, diags, blocks, totals, lists, counts, offsets, masks, tileSums, pairCounts, partials, pairBlockOff, perPair, hmmTotal, forwardOut;
+    DevBuf ckRegions, ckDiags, ckSizes, ckpt; /* two-pass forward: plane-less first pass over the regions, block checkpoints */
     DevBuf out[3];
     int64_t outCount[3] = { 0, 0, 0 };
     std::vector<int64_t> pairOff[3]; /* n+1 */
@@ -240,7 +241,7 @@ extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *se
     {
         DevBuf *all[] = { &b->strips, &b->symX, &b->symY, &b->dAnchors, &b->regions, &b->diags, &b->blocks, &b->totals, &b->lists, &b->counts, &b->offsets,
                           &b->masks, &b->tileSums, &b->pairCounts, &b->partials, &b->pairBlockOff, &b->perPair, &b->hmmTotal, &b->forwardOut, &b->out[0],
-                          &b->out[1], &b->out[2] };
+                          &b->out[1], &b->out[2], &b->ckRegions, &b->ckDiags, &b->ckSizes, &b->ckpt };
         for (DevBuf *d : all) d->pool = &ctx->pool;
     }
     b->n = nPairs;
@@ -292,7 +293,7 @@ extern "C" void cpb_batch_destroy(cpb_batch *b) {
     cudaSetDevice(b->ctx->device);
     DevBuf *bufs[] = { &b->strips, &b->symX, &b->symY, &b->dAnchors, &b->regions, &b->diags, &b->blocks, &b->totals, &b->lists, &b->counts,
                        &b->offsets, &b->masks, &b->tileSums, &b->pairCounts, &b->partials, &b->pairBlockOff, &b->perPair, &b->hmmTotal, &b->forwardOut, &b->out[0], &b->out[1],
-                       &b->out[2] };
+                       &b->out[2], &b->ckRegions, &b->ckDiags, &b->ckSizes, &b->ckpt };
     for (DevBuf *d : bufs) d->release();
     delete b;
 }
@@ -508,7 +509,10 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         int64_t k = 0;
         for (int64_t r = 0; r < nReg; r++) {
             regionBlock0[r] = k;
-            for (int j = 0; j < regs[r].nBlocks; j++) hBlocks[k++] = slots[regs[r].blockBase + j];
+            for (int j = 0; j < regs[r].nBlocks; j++) {
+                hBlocks[k] = slots[regs[r].blockBase + j];
+                hBlocks[k++].ckBase = -1;
+            }
         }
         regionBlock0[nReg] = k;
         CUDA_TRY(cudaMemcpyAsync(b->blocks.p, hBlocks.data(), totalBlocks * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
@@ -606,26 +610,30 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
 
     /* strip engine: persistent grid of independent warps, boundary rings, work counters */
     typedef void (*StripKernel)(const DpArgs, const CpbModel, const StripArgs);
-    StripKernel kFwdStrip = nullptr, kFwdTeam = nullptr, kBwdStrip = nullptr;
+    StripKernel kFwdStrip = nullptr, kFwdTeam = nullptr, kFwdBlocks = nullptr, kBwdStrip = nullptr;
+    StripKernel kCkStrip = k_forward_strip<S, 0, kStripWPC, FWD_REGIONS>, kCkTeam = k_forward_strip<S, 0, kStripWPC, FWD_TEAMS>; /* first pass of two */
     switch (mode) {
     case CPB_MODE_FORWARD:
-        kFwdStrip = k_forward_strip<S, 0, kStripWPC, false>;
-        kFwdTeam = k_forward_strip<S, 0, kStripWPC, true>;
+        kFwdStrip = k_forward_strip<S, 0, kStripWPC, FWD_REGIONS>;
+        kFwdTeam = k_forward_strip<S, 0, kStripWPC, FWD_TEAMS>;
         kBwdStrip = k_backward_strip<S, 0, true, kStripWPC>;
         break;
     case CPB_MODE_ALIGNED_PAIRS:
-        kFwdStrip = k_forward_strip<S, 1, kStripWPC, false>;
-        kFwdTeam = k_forward_strip<S, 1, kStripWPC, true>;
+        kFwdStrip = k_forward_strip<S, 1, kStripWPC, FWD_REGIONS>;
+        kFwdTeam = k_forward_strip<S, 1, kStripWPC, FWD_TEAMS>;
+        kFwdBlocks = k_forward_strip<S, 1, kStripWPC, FWD_BLOCKS>;
         kBwdStrip = k_backward_strip<S, 1, true, kStripWPC>;
         break;
     case CPB_MODE_ALIGNED_PAIRS_INDELS:
-        kFwdStrip = k_forward_strip<S, 3, kStripWPC, false>;
-        kFwdTeam = k_forward_strip<S, 3, kStripWPC, true>;
+        kFwdStrip = k_forward_strip<S, 3, kStripWPC, FWD_REGIONS>;
+        kFwdTeam = k_forward_strip<S, 3, kStripWPC, FWD_TEAMS>;
+        kFwdBlocks = k_forward_strip<S, 3, kStripWPC, FWD_BLOCKS>;
         kBwdStrip = k_backward_strip<S, 3, true, kStripWPC>;
         break;
     default:
-        kFwdStrip = k_forward_strip<S, S, kStripWPC, false>;
-        kFwdTeam = k_forward_strip<S, S, kStripWPC, true>;
+        kFwdStrip = k_forward_strip<S, S, kStripWPC, FWD_REGIONS>;
+        kFwdTeam = k_forward_strip<S, S, kStripWPC, FWD_TEAMS>;
+        kFwdBlocks = k_forward_strip<S, S, kStripWPC, FWD_BLOCKS>;
         kBwdStrip = k_backward_strip<S, S, false, kStripWPC>;
         break;
     }
@@ -653,6 +661,108 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         sargs.boundary = ctx->boundary.as<double>();
         sargs.negRecord = ctx->negRecord.as<double>();
         sargs.ringSize = ring;
+    }
+
+    /* How many warps of a team share one region when `cnt` regions of `cells` cells in all are launched together: the largest
+     * power of two that still keeps every warp slot busy, at most 16 (a strip lags its predecessor by ~64 diagonals); 1 for short
+     * regions, where a hand-over between warps costs more than a strip. */
+    auto team_size = [&](int64_t cnt, int64_t cells) {
+        int team = 1;
+        if (cnt > 0 && cells / cnt >= (int64_t) 1 << 20) {
+            while (team < 16 && cnt * team * 2 <= (int64_t) teamGrid * kStripWPC) team *= 2;
+        }
+        if (getenv("CPB_TEAM") != nullptr) team = std::max(1, atoi(getenv("CPB_TEAM")));
+        return team;
+    };
+    auto launch_forward_regions = [&](StripKernel plain, StripKernel teamed, const DpArgs &a, int64_t cnt, int64_t cells) {
+        const int team = team_size(cnt, cells);
+        if (team > 1 || getenv("CPB_TEAM_KERNEL") != nullptr) {
+            const int grid = (int) std::min<int64_t>(teamGrid, (cnt * team + kStripWPC - 1) / kStripWPC);
+            sargs.teamSize = team;
+            cudaMemsetAsync(ctx->progress.p, 0, (size_t) grid * kStripWPC * sizeof(unsigned long long), st);
+            teamed<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
+        } else {
+            const int grid = (int) std::min<int64_t>(stripGrid, (cnt + kStripWPC - 1) / kStripWPC);
+            sargs.teamSize = 1;
+            plain<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
+        }
+        stx.kernelLaunches++;
+        return team;
+    };
+
+    /*
+     * Two-pass forward.  A chunk of few, long regions (one whose forward sweep would need teams) leaves most of the machine idle: a
+     * region is one sequential sweep and a team only gets as many warps going as the band is wide.  Such runs instead make one
+     * plane-less sweep over ALL regions of the batch at once (no HBM planes, so no chunking: every region is in flight), keeping
+     * the full cells of the two diagonals in front of every traceback block; then, chunk by chunk, every block recomputes its own
+     * forward cells from its checkpoint -- as many work items as blocks.  Same arithmetic in the same order: bit-identical planes.
+     */
+    bool twoPass = false;
+    if (mode != CPB_MODE_FORWARD && totalBlocks > nReg) {
+        /* it pays when chunking is what starves the machine: the first pass then has several chunks' worth of regions in flight */
+        for (auto &c : chunks) {
+            int64_t cells = 0;
+            for (int64_t r = c.region0; r < c.region1; r++) cells += regs[r].cells;
+            if (chunks.size() > 1 && team_size(c.region1 - c.region0, cells) > 1) twoPass = true;
+        }
+        if (getenv("CPB_TWO_PASS") != nullptr) twoPass = atoi(getenv("CPB_TWO_PASS")) != 0;
+        for (int64_t k = 0; k < totalBlocks && twoPass; k++) {
+            /* diagonal 0 is not stored through the aux path, and the checkpoint diagonals of two blocks must not coincide
+             * (library defaults put block starts >= 960 diagonals apart) */
+            if (hBlocks[k].T == 1) twoPass = false;
+            if (k > 0 && hBlocks[k].region == hBlocks[k - 1].region && hBlocks[k].T - hBlocks[k - 1].T < 2) twoPass = false;
+        }
+    }
+    if (twoPass) {
+        std::vector<int32_t> sizes(totalBlocks);
+        if ((rc = b->ckSizes.reserve(totalBlocks * sizeof(int32_t))) != CPB_OK) return rc;
+        k_ckpt_sizes<<<(unsigned) ((totalBlocks + 255) / 256), 256, 0, st>>>(b->blocks.as<BlockRec>(), b->regions.as<RegionDev>(), b->diags.as<DiagRec>(),
+                                                                         (int) totalBlocks, S, b->ckSizes.as<int32_t>());
+        CUDA_TRY(cudaMemcpyAsync(sizes.data(), b->ckSizes.p, totalBlocks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        int64_t total = 0;
+        for (int64_t k = 0; k < totalBlocks; k++) {
+            hBlocks[k].ckBase = total;
+            total += sizes[k];
+        }
+        if (total >= ((int64_t) 1 << 32)) {
+            twoPass = false; /* aux offsets are 32-bit */
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(b->blocks.p, hBlocks.data(), totalBlocks * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
+            if ((rc = b->ckpt.reserve(std::max<int64_t>(total, 1) * sizeof(double))) != CPB_OK) return rc;
+            if ((rc = b->ckDiags.reserve(nDiagRecs * sizeof(DiagRec))) != CPB_OK) return rc;
+            if ((rc = b->ckRegions.reserve(nReg * sizeof(RegionDev))) != CPB_OK) return rc;
+            std::vector<RegionDev> ckRegs(regs);
+            for (auto &r : ckRegs) r.auxBase = 0; /* checkpoint offsets are absolute */
+            CUDA_TRY(cudaMemcpyAsync(b->ckRegions.p, ckRegs.data(), nReg * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
+            k_ckpt_diags<<<(unsigned) ((nDiagRecs + 255) / 256), 256, 0, st>>>(b->diags.as<DiagRec>(), b->ckDiags.as<DiagRec>(), nDiagRecs);
+            k_ckpt_mark<<<(unsigned) ((totalBlocks + 255) / 256), 256, 0, st>>>(b->blocks.as<BlockRec>(), b->regions.as<RegionDev>(), b->ckDiags.as<DiagRec>(),
+                                                                            (int) totalBlocks, S);
+            stx.kernelLaunches += 3;
+            /* all regions, most expensive first */
+            std::vector<int32_t> order(nReg);
+            for (int64_t r = 0; r < nReg; r++) order[r] = (int32_t) r;
+            std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return regs[x].cells > regs[y].cells; });
+            if ((rc = b->ckSizes.reserve(std::max<size_t>(totalBlocks * sizeof(int32_t), nReg * sizeof(int32_t)))) != CPB_OK) return rc;
+            CUDA_TRY(cudaMemcpyAsync(b->ckSizes.p, order.data(), nReg * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            DpArgs a1;
+            memset(&a1, 0, sizeof(a1));
+            a1.regions = b->ckRegions.as<RegionDev>();
+            a1.blocks = b->blocks.as<BlockRec>();
+            a1.diags = b->ckDiags.as<DiagRec>();
+            a1.symX = b->symX.as<uint8_t>() + kSymPad;
+            a1.symY = b->symY.as<uint8_t>() + kSymPad;
+            a1.aux = b->ckpt.as<double>();
+            a1.auxF = S;
+            a1.list = b->ckSizes.as<int32_t>();
+            sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunks.size();
+            sargs.nItems = (int32_t) nReg;
+            size_t ev = tic(&stx.msForward);
+            launch_forward_regions(kCkStrip, kCkTeam, a1, nReg, stx.cells);
+            CUDA_TRY(cudaGetLastError());
+            toc(ev);
+            CUDA_TRY(cudaStreamSynchronize(st)); /* `order` and `ckRegs` are read by the copies above */
+        }
     }
 
     std::vector<int64_t> hPairOff;
@@ -683,45 +793,32 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
 
         chunkIndex++;
         size_t ev = tic(&stx.msForward);
-        {
+        if (twoPass) {
+            /* every block of the chunk recomputes its forward cells from its checkpoint */
+            const int64_t nbF = c.block1 - c.block0;
+            a.ckpt = b->ckpt.as<double>();
+            a.list = dLists + c.stripBwdOff;
+            sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex;
+            sargs.nItems = (int32_t) nbF;
+            sargs.teamSize = 1;
+            const int grid = (int) std::min<int64_t>(stripGrid, (nbF + kStripWPC - 1) / kStripWPC);
+            kFwdBlocks<<<std::max(grid, 1), 32 * kStripWPC, 0, st>>>(a, *m, sargs);
+            stx.kernelLaunches++;
+        } else {
             const int64_t cnt = c.region1 - c.region0;
             a.list = dLists + c.stripFwdOff;
             sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex;
             sargs.nItems = (int32_t) cnt;
-            /* few regions for the machine: let teams of warps pipeline the strips of one region (largest power of two that still
-             * keeps every warp slot busy, at most 16: a strip lags its predecessor by ~64 diagonals) */
-            int team = 1;
             int64_t chunkCells = 0;
             for (int64_t r = c.region0; r < c.region1; r++) chunkCells += regs[r].cells;
-            if (chunkCells / cnt >= (int64_t) 1 << 20) { /* only long regions: a hand-over between warps costs more than a short strip */
-                while (team < 16 && cnt * team * 2 <= (int64_t) teamGrid * kStripWPC) team *= 2;
-            }
-            if (getenv("CPB_TEAM") != nullptr) team = std::max(1, atoi(getenv("CPB_TEAM")));
-            if (team > 1 || getenv("CPB_TEAM_KERNEL") != nullptr) {
-                const int grid = (int) std::min<int64_t>(teamGrid, (cnt * team + kStripWPC - 1) / kStripWPC);
-                sargs.teamSize = team;
-                CUDA_TRY(cudaMemsetAsync(ctx->progress.p, 0, (size_t) grid * kStripWPC * sizeof(unsigned long long), st));
-                kFwdTeam<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
-            } else {
-                const int grid = (int) std::min<int64_t>(stripGrid, (cnt + kStripWPC - 1) / kStripWPC);
-                sargs.teamSize = 1;
-                kFwdStrip<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
-            }
-            stx.kernelLaunches++;
+            const int team = launch_forward_regions(kFwdStrip, kFwdTeam, a, cnt, chunkCells);
+            (void) team;
 #ifdef CPB_TEAM_DEBUG
             if (team > 1) {
                 unsigned long long dbg[8] = { 0 }, zero[8] = { 0 };
                 cudaStreamSynchronize(st);
                 cudaMemcpyFromSymbol(dbg, g_teamDebug, sizeof(dbg));
                 cudaMemcpyToSymbol(g_teamDebug, zero, sizeof(zero));
-                if (getenv("CPB_TEAM_TRACE") != nullptr) {
-                    unsigned long long tr[64 * 4];
-                    cudaMemcpyFromSymbol(tr, g_teamTrace, sizeof(tr));
-                    unsigned long long stt[256];
-                    cudaMemcpyFromSymbol(stt, g_stepTrace, sizeof(stt));
-                    for (int q = 0; q < 256; q++) fprintf(stderr, "step strip %d +%d: %.1f\n", 1 + q / 128, q % 128, stt[q] > tr[1] ? (stt[q] - tr[1]) / 1e3 : -1.0);
-                    for (int q = 0; q < 34; q++) fprintf(stderr, "  strip %2d slot %llu start %8.1f loop %8.1f end %8.1f us\n", q, tr[4 * q], (tr[4 * q + 1] - tr[1]) / 1e3, (tr[4 * q + 2] - tr[1]) / 1e3, (tr[4 * q + 3] - tr[1]) / 1e3);
-                }
                 fprintf(stderr, "team %d: %llu wait calls, %llu spun, %llu spin iterations, %.3f ms waiting; %llu publishes, %.3f ms publishing (summed over warps)\n",
                         team, dbg[3], dbg[1], dbg[2], (double) dbg[0] / 1.965e6, dbg[5], (double) dbg[4] / 1.965e6);
             }

@@ -72,6 +72,7 @@ struct BlockRec {
     int32_t cells;   /* band cells on the diagonals (T, top] */
     int32_t atEnd;
     int64_t decadeBase; /* chunk-relative index of the block's first decade (host, after planning) */
+    int64_t ckBase;     /* two-pass forward: offset (doubles) of the block's checkpoint, the full cells of diagonals T-1 and T */
 };
 
 /* Everything the DP kernels need besides the launch list. */
@@ -89,6 +90,7 @@ struct DpArgs {
     int32_t auxF;          /* planes of full forward state kept in aux records of total diagonals (S or 0) */
     const int32_t *list;   /* region ids (forward) or block ids (others) */
     double *forwardOut;    /* per region, forward-only mode */
+    const double *ckpt;    /* two-pass forward: block checkpoints (k_forward_strip<..., FWD_BLOCKS>) */
 };
 
 /* ---------------------------------------------------------------------------------------------
@@ -223,6 +225,35 @@ template <int S> __host__ __device__ constexpr int lower_to(int k) { return S ==
 template <int S> __host__ __device__ constexpr int middle_from(int k) { return k; }
 template <int S> __host__ __device__ constexpr int upper_from(int k) { return S == 5 ? (k == 0 ? 0 : (k == 1 ? 2 : (k == 2 ? 0 : 4))) : (k == 0 ? 0 : (k == 1 ? 2 : 1)); }
 template <int S> __host__ __device__ constexpr int upper_to(int k) { return S == 5 ? (k < 2 ? 2 : 4) : 2; }
+
+/* ---------------------------------------------------------------------------------------------
+ * Two-pass forward (long regions): checkpoint bookkeeping.  A block's checkpoint is the full forward cells of its
+ * diagonals T-1 and T, [state][cell], T-1 first.  The plane-less first pass writes them through the kernel's "aux"
+ * stores: it runs on a copy of the diagonal records in which exactly the checkpoint diagonals carry an aux offset.
+ * ------------------------------------------------------------------------------------------- */
+__global__ void k_ckpt_sizes(const BlockRec *blocks, const RegionDev *regions, const DiagRec *diags, int nBlocks, int S, int32_t *sizes) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nBlocks) return;
+    const BlockRec B = blocks[k];
+    const DiagRec *dg = diags + regions[B.region].diagBase;
+    sizes[k] = B.T > 0 ? S * (dg[B.T - 1].width + dg[B.T].width) : 0;
+}
+__global__ void k_ckpt_diags(const DiagRec *diags, DiagRec *out, int64_t n) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DiagRec r = diags[i];
+    r.aoff = NO_AUX;
+    out[i] = r;
+}
+__global__ void k_ckpt_mark(const BlockRec *blocks, const RegionDev *regions, DiagRec *ckDiags, int nBlocks, int S) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nBlocks) return;
+    const BlockRec B = blocks[k];
+    if (B.T <= 0) return;
+    DiagRec *dg = ckDiags + regions[B.region].diagBase;
+    dg[B.T - 1].aoff = (uint32_t) B.ckBase;
+    dg[B.T].aoff = (uint32_t) (B.ckBase + (int64_t) S * dg[B.T - 1].width);
+}
 
 /* ---------------------------------------------------------------------------------------------
  * k_totals : one warp per block, one lane per decade (10 owned diagonals share one totalProbability,

@@ -100,6 +100,8 @@ __device__ __forceinline__ void team_wait(const unsigned long long *slotWord, un
 struct Yes { static constexpr bool value = true; };
 struct No { static constexpr bool value = false; };
 
+enum { FWD_REGIONS = 0, FWD_TEAMS = 1, FWD_BLOCKS = 2 };
+
 template <int S> struct Msg;
 template <> struct Msg<5> { static constexpr int N = 3; };
 template <> struct Msg<3> { static constexpr int N = 2; };
@@ -182,13 +184,18 @@ template <int S> __device__ __forceinline__ void lower_folds(double *g, const do
 }
 
 /* ---------------------------------------------------------------------------------------------
- * k_forward_strip<S, NP, WPC, TEAM>: NP = state planes written to HBM (0 forward-only, 1 match, 3 match+gaps, S all).
- * TEAM = false: every warp fetches whole regions from the work counter (many regions per launch).
- * TEAM = true : sa.teamSize consecutive warp slots share a region (few, long regions): strips are dealt round-robin and
- *               pipelined through the rings, regions are dealt round-robin to the teams.
+ * k_forward_strip<S, NP, WPC, MODE>: NP = state planes written to HBM (0 forward-only, 1 match, 3 match+gaps, S all).
+ * FWD_REGIONS: every warp fetches whole regions from the work counter (many regions per launch).
+ * FWD_TEAMS  : sa.teamSize consecutive warp slots share a region (few, long regions): strips are dealt round-robin and
+ *              pipelined through the rings, regions are dealt round-robin to the teams.
+ * FWD_BLOCKS : every warp fetches one traceback block and recomputes the forward cells of its diagonals (T, top] from the
+ *              checkpoint of diagonals T-1 and T that an earlier plane-less pass over the regions left in a.ckpt (that pass is
+ *              this kernel in one of the other two modes with NP = 0 and the checkpoint diagonals marked as "aux" diagonals).
+ *              Long regions then offer as many work items as they have blocks, instead of one.
  * ------------------------------------------------------------------------------------------- */
-template <int S, int NP, int WPC, bool TEAM>
+template <int S, int NP, int WPC, int MODE>
 __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_strip(const DpArgs a, const CpbModel model, const StripArgs sa) {
+    constexpr bool TEAM = MODE == FWD_TEAMS, BLOCKS = MODE == FWD_BLOCKS;
     __shared__ __align__(16) StripTables<S> tab;
     fill_strip_tables<S>(tab, model, threadIdx.x, 32 * WPC);
     __syncthreads();
@@ -223,7 +230,16 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
             if (lane < K) team_wait(sa.progress + teamBase + lane, strip_serial(iter - 1, 0xFFFFF), PROGRESS_DONE);
             __syncwarp();
         }
-        const int regionId = a.list[item];
+        int regionId = a.list[item];
+        int blockT = 0, blockTop = 0x7FFFFFFF; /* FWD_BLOCKS: the diagonals (T, top] of the block */
+        int64_t ckBase = 0;
+        if (BLOCKS) {
+            const BlockRec B = a.blocks[regionId];
+            regionId = B.region;
+            blockT = B.T;
+            blockTop = B.top;
+            ckBase = B.ckBase;
+        }
         const RegionDev R = a.regions[regionId];
         const int N = R.lX + R.lY;
         const DiagRec *dg = a.diags + R.diagBase;
@@ -232,15 +248,31 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
         double *aux = a.aux + R.auxBase;
         const StripRec *strips = sa.strips + R.stripBase;
         const int nStrips = (R.lX >> 5) + 1;
+        /* The part of a strip this work item computes.  FWD_BLOCKS: steps T+1 .. min(dLast, top); a strip that is under way on
+         * diagonal T-1 or T starts from the checkpoint (fromCk) and first writes the message its step T would have left (ring
+         * index T): diagonal T+1 of the next strip still hears from a row whose last band cell is on diagonal T-1. */
+        auto clipped = [&](StripRec q, bool &fromCk) {
+            fromCk = false;
+            if (BLOCKS) {
+                q.dLast = min(q.dLast, blockTop);
+                if (blockT > 0 && q.dFirst <= blockT) {
+                    fromCk = q.dLast >= blockT - 1;
+                    q.dFirst = blockT + 1;
+                    q.dLast = fromCk ? max(q.dLast, blockT) : blockT; /* not fromCk: over before the block starts, empty */
+                }
+            }
+            return q;
+        };
 
         for (int s = member; s < nStrips; s += K) {
-            const StripRec sr = strips[s];
+            bool fromCk, prevFromCk;
+            const StripRec sr = clipped(strips[s], fromCk);
             /* ring indices the previous strip writes: its diagonals and one flush record */
             int prevFirst = 1, prevLast = 0;
             if (s > 0) {
-                const StripRec sp = strips[s - 1];
-                if (sp.dLast >= sp.dFirst) {
-                    prevFirst = sp.dFirst;
+                const StripRec sp = clipped(strips[s - 1], prevFromCk);
+                if (sp.dLast >= sp.dFirst || prevFromCk) {
+                    prevFirst = prevFromCk ? blockT : sp.dFirst;
                     prevLast = sp.dLast + 1;
                 }
             }
@@ -251,7 +283,7 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
             const unsigned long long mySerial = strip_serial(iter, s), prodSerial = strip_serial(iter, s - 1);
             unsigned long long *myWord = sa.progress + slot;
             const unsigned long long *prodWord = sa.progress + producer;
-            if (sr.dLast < sr.dFirst) {
+            if (sr.dLast < sr.dFirst && !fromCk) {
                 if (TEAM && lane == 31) team_publish(myWord, mySerial, PROGRESS_DONE);
                 continue;
             }
@@ -298,13 +330,35 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
                 send[0] = CPB_NEG_INF;
                 if (lane == 31) store_record<NSH>(bOut, send);
                 d0 = 1;
-            } else if (lane == 0) {
-                /* message for diagonal d0 from row x-1 (the previous strip's last lane) */
-                const int t = d0 - 1;
-                const DiagRec r0 = dg[d0 <= N ? d0 : N];
-                const bool ok = t >= prevFirst && t <= prevLast && (unsigned) (x - ((d0 + r0.xmyL) >> 1)) < (unsigned) r0.width;
-                if (ok) await(t);
-                load_record<NSH>(bNext, ok ? bIn + (size_t) (t & rm) * BND_REC : sa.negRecord);
+            } else {
+                if (BLOCKS && fromCk) {
+                    /* the state step T would have left: own = cell (x, T-x), send = {middle fold of cell (x, T-1-x), lower folds of own} */
+                    const DiagRec rB = dg[blockT], rA = dg[blockT - 1];
+                    const double *ckA = a.ckpt + ckBase, *ckB = ckA + (size_t) S * rA.width; /* [state][cell] of diagonals T-1 and T */
+                    const int iA = x - ((blockT - 1 + rA.xmyL) >> 1), iB = x - ((blockT + rB.xmyL) >> 1);
+                    const bool inA = (unsigned) iA < (unsigned) rA.width, inB = (unsigned) iB < (unsigned) rB.width;
+                    double before[S], tmD[NM];
+#pragma unroll
+                    for (int k = 0; k < S; k++) {
+                        before[k] = inA ? ckA[(size_t) k * rA.width + iA] : CPB_NEG_INF;
+                        own[k] = inB ? ckB[(size_t) k * rB.width + iB] : CPB_NEG_INF;
+                    }
+                    const double eM = tab.eM[cXn6 + ptrY[blockT - 1]][l16]; /* column T - x, the column of step T */
+#pragma unroll
+                    for (int k = 0; k < NM; k++) tmD[k] = eM + model.tMiddle[k];
+                    send[0] = middle_fold<S>(before, tmD, la);
+                    lower_folds<S>(send + 1, own, tlD, la);
+                    if (lane == 31) store_record<NSH>(bOut + (size_t) (blockT & rm) * BND_REC, send);
+                    d0 = blockT + 1;
+                }
+                if (lane == 0) {
+                    /* message for diagonal d0 from row x-1 (the previous strip's last lane) */
+                    const int t = d0 - 1;
+                    const DiagRec r0 = dg[d0 <= N ? d0 : N];
+                    const bool ok = t >= prevFirst && t <= prevLast && (unsigned) (x - ((d0 + r0.xmyL) >> 1)) < (unsigned) r0.width;
+                    if (ok) await(t);
+                    load_record<NSH>(bNext, ok ? bIn + (size_t) (t & rm) * BND_REC : sa.negRecord);
+                }
             }
             /* diagonal records and column symbols are fetched two steps ahead (records N+1, N+2 are sentinels) */
             DiagRec cur = dg[d0 <= N ? d0 : N], nxt = dg[d0 <= N ? d0 + 1 : N + 1];

@@ -16,6 +16,18 @@ pytestmark = pytest.mark.gpu
 EXPECT_RTOL = 1e-9
 
 
+@pytest.fixture(autouse=True, params=["auto", "two_pass"])
+def forward_schedule(request, monkeypatch):
+    """Every test of this module runs twice: with the engine's own choice between the one-sweep forward and the checkpointed
+    two-pass forward (engine.cu; it picks two-pass only for chunked runs of long regions), and with two-pass forced, which puts
+    its block restarts through every edge case here (blocks a few diagonals long, ragged ends, splits, empty problems)."""
+    if request.param == "two_pass":
+        monkeypatch.setenv("CPB_TWO_PASS", "1")
+    else:
+        monkeypatch.delenv("CPB_TWO_PASS", raising=False)
+    return request.param
+
+
 def compare_triples(got, want, what=""):
     g = helpers.sort_triples(got)
     w = helpers.sort_triples(want)
@@ -377,3 +389,36 @@ def test_all_pairs_of_10kb_sequences(ctx, oracle):
             cases.append((members[i][0], members[j][0], a, False, False))
     n = check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.fiveState), p, cases, "all pairs 10kb")
     assert n > 6 * 8000
+
+
+def test_two_pass_forward_is_bit_identical(ctx, oracle, monkeypatch):
+    """Long regions: one plane-less sweep leaves a checkpoint in front of every traceback block, then every block recomputes
+    its own forward cells (engine.cu, FWD_BLOCKS).  Same arithmetic in the same order, so every result is identical to the
+    one-pass run bit for bit -- and the one-pass run is what the other tests pin to the oracle."""
+    rng = np.random.default_rng(808)
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    p.minDiagsBetweenTraceBack = 150  # many blocks per pair
+    cases = []
+    for length in (3000, 4500, 700, 0, 37, 2500):
+        sX = synth.random_sequence(rng, length, acgt_only=True)
+        sY, pos = synth.evolve_with_alignment(rng, sX, sub_rate=0.08, indel_rate=0.02)
+        a = synth.anchors_between((sX, np.arange(len(sX))), (sY, pos), trim=int(p.constraintDiagonalTrim), expansion=int(p.diagonalExpansion))
+        cases.append((sX, sY, a, bool(length % 2), bool(length % 3)))
+    for type_ in (cp.fiveState, cp.threeState):
+        spec = helpers.ModelSpec(type_)
+        for mode in (cp.MODE_ALIGNED_PAIRS, cp.MODE_ALIGNED_PAIRS_INDELS, cp.MODE_EXPECTATIONS):
+            res = []
+            for flag in ("0", "1"):
+                monkeypatch.setenv("CPB_TWO_PASS", flag)
+                b = run_batch(ctx, spec, p, cases, mode)
+                if mode == cp.MODE_EXPECTATIONS:
+                    res.append([b.fetch_expectations()[0]])
+                else:
+                    res.append([np.concatenate([b.fetch_pairs(k)[0], b.fetch_pairs(k)[1].ravel()]) for k in range(1 if mode == cp.MODE_ALIGNED_PAIRS else 3)])
+                assert int(b.stats().nBlocks) > 60
+                b.close()
+            for x, y in zip(*res):
+                assert np.array_equal(x, y), "two-pass forward differs (type %d mode %d)" % (type_, mode)
+    # and against the oracle directly
+    monkeypatch.setenv("CPB_TWO_PASS", "1")
+    check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.fiveState), p, cases[:3], "two-pass")
