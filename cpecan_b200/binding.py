@@ -74,7 +74,8 @@ class CpbRunStats(C.Structure):
         ("msTotals", C.c_double),
         ("msPosterior", C.c_double),
         ("maxWidth", C.c_int32),
-        ("pad_", C.c_int32),
+        ("twoPass", C.c_int32),
+        ("msCheckpoint", C.c_double),
     ]
 
 

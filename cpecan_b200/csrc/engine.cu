@@ -687,6 +687,16 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             plain<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
         }
         stx.kernelLaunches++;
+#ifdef CPB_TEAM_DEBUG
+        if (team > 1) {
+            unsigned long long dbg[8] = { 0 }, zero[8] = { 0 };
+            cudaStreamSynchronize(st);
+            cudaMemcpyFromSymbol(dbg, g_teamDebug, sizeof(dbg));
+            cudaMemcpyToSymbol(g_teamDebug, zero, sizeof(zero));
+            fprintf(stderr, "team %d, %lld regions: %llu wait calls, %llu spun, %llu spin iterations, %.3f ms waiting; %llu publishes, %.3f ms publishing (summed over warps)\n",
+                    team, (long long) cnt, dbg[3], dbg[1], dbg[2], (double) dbg[0] / 1.965e6, dbg[5], (double) dbg[4] / 1.965e6);
+        }
+#endif
         return team;
     };
 
@@ -757,10 +767,11 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             a1.list = b->ckSizes.as<int32_t>();
             sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunks.size();
             sargs.nItems = (int32_t) nReg;
-            size_t ev = tic(&stx.msForward);
+            size_t ev = tic(&stx.msCheckpoint);
             launch_forward_regions(kCkStrip, kCkTeam, a1, nReg, stx.cells);
             CUDA_TRY(cudaGetLastError());
             toc(ev);
+            stx.twoPass = 1;
             CUDA_TRY(cudaStreamSynchronize(st)); /* `order` and `ckRegs` are read by the copies above */
         }
     }
@@ -813,16 +824,6 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             for (int64_t r = c.region0; r < c.region1; r++) chunkCells += regs[r].cells;
             const int team = launch_forward_regions(kFwdStrip, kFwdTeam, a, cnt, chunkCells);
             (void) team;
-#ifdef CPB_TEAM_DEBUG
-            if (team > 1) {
-                unsigned long long dbg[8] = { 0 }, zero[8] = { 0 };
-                cudaStreamSynchronize(st);
-                cudaMemcpyFromSymbol(dbg, g_teamDebug, sizeof(dbg));
-                cudaMemcpyToSymbol(g_teamDebug, zero, sizeof(zero));
-                fprintf(stderr, "team %d: %llu wait calls, %llu spun, %llu spin iterations, %.3f ms waiting; %llu publishes, %.3f ms publishing (summed over warps)\n",
-                        team, dbg[3], dbg[1], dbg[2], (double) dbg[0] / 1.965e6, dbg[5], (double) dbg[4] / 1.965e6);
-            }
-#endif
         }
         toc(ev);
         if (mode == CPB_MODE_FORWARD) continue;
@@ -945,6 +946,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     }
 #endif
     finish_events();
+    stx.msForward += stx.msCheckpoint; /* the forward phase is both passes */
     for (int l = 0; l < nLists; l++) {
         b->outCount[l] = running[l];
         stx.outputTriples += running[l];

@@ -57,12 +57,34 @@ struct RegionDev {
     int32_t maxStripRange; /* out: longest diagonal range of a 32-row strip */
     int32_t err;           /* out: 0 ok, 1 invalid diagonal, 2 block table overflow */
     uint8_t raggedL, raggedR;
-    uint8_t pad_[6];
+    uint8_t stripsSorted;  /* out: dFirst and dLast are non-decreasing along the strips (always, for a monotone band): block kernels
+                            * then find their strips by bisection instead of scanning all of them */
+    uint8_t pad_[5];
 };
 
 struct StripRec {
     int32_t dFirst, dLast; /* diagonals on which any row of the 32-row strip is inside the band (dLast < dFirst: never) */
 };
+
+/* bisection over the strips of a region with sorted strip records */
+__device__ __forceinline__ int first_strip_with_last_at_least(const StripRec *strips, int n, int d) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (strips[mid].dLast >= d) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo; /* n if none */
+}
+__device__ __forceinline__ int last_strip_with_first_at_most(const StripRec *strips, int n, int d) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (strips[mid].dFirst <= d) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo - 1; /* -1 if none */
+}
 
 struct BlockRec {
     int32_t region;
@@ -845,7 +867,11 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) k_band(const BandArgs b) {
     __syncwarp();
     for (int k = lane; k < nStrips; k += 32) msr = max(msr, st[k].dLast - st[k].dFirst + 1);
     msr = __reduce_max_sync(FULL, msr);
+    int sorted = 1;
+    for (int k = 1 + lane; k < nStrips; k += 32) sorted &= st[k].dFirst >= st[k - 1].dFirst && st[k].dLast >= st[k - 1].dLast && st[k].dLast >= st[k].dFirst;
+    sorted = __all_sync(FULL, sorted) && st[0].dLast >= st[0].dFirst;
     if (lane == 0) {
+        R.stripsSorted = (uint8_t) sorted;
         R.cells = cellsBefore;
         R.auxDoubles = auxD;
         R.nBlocks = nBlocks;

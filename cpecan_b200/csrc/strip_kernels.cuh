@@ -264,7 +264,13 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
             return q;
         };
 
-        for (int s = member; s < nStrips; s += K) {
+        /* FWD_BLOCKS: only the strips that reach diagonal T-1 and have started by `top` take part */
+        int sBegin = member, sEnd = nStrips;
+        if (BLOCKS && R.stripsSorted) {
+            sBegin = blockT > 0 ? first_strip_with_last_at_least(strips, nStrips, blockT - 1) : 0;
+            sEnd = last_strip_with_first_at_most(strips, nStrips, blockTop) + 1;
+        }
+        for (int s = sBegin; s < sEnd; s += K) {
             bool fromCk, prevFromCk;
             const StripRec sr = clipped(strips[s], fromCk);
             /* ring indices the previous strip writes: its diagonals and one flush record */
@@ -556,7 +562,12 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_backward_str
         const double *endVec = (K.atEnd && R.raggedR) ? tab.rendv : tab.endv;
         int prevHi = 0, prevLo = 1; /* ring indices the previously processed (higher) strip wrote */
 
-        for (int s = nStrips - 1; s >= 0; s--) {
+        int sHigh = nStrips - 1, sLow = 0;
+        if (R.stripsSorted) { /* strips that have started by `top` and reach diagonal T+1 */
+            sHigh = last_strip_with_first_at_most(strips, nStrips, top);
+            sLow = first_strip_with_last_at_least(strips, nStrips, T + 1);
+        }
+        for (int s = sHigh; s >= sLow; s--) {
             const StripRec sr = strips[s];
             const int dHi = min(sr.dLast, top), dLo = max(sr.dFirst, T + 1);
             if (dHi < dLo) { /* no row of this strip is inside the band on the block's diagonals */

@@ -136,7 +136,8 @@ typedef struct {
     int64_t kernelLaunches;
     double msBand, msForward, msBackward, msTotals, msPosterior; /* CUDA-event times of the last run, summed over chunks */
     int32_t maxWidth;
-    int32_t pad_;
+    int32_t twoPass;       /* 1 if the forward sweep ran as checkpoint pass + per-block recomputation (chunked runs of long regions) */
+    double msCheckpoint;   /* part of msForward spent in the plane-less checkpoint pass (0 unless twoPass) */
 } CpbRunStats;
 void cpb_batch_stats(const cpb_batch *b, CpbRunStats *out);
 

@@ -34,7 +34,7 @@ def timed(batch, model, p, mode, steps=2):
 def line(name, n, st, dt, extra=None):
     out = {"config": name, "pairs": n, "cells": int(st.cells), "regions": int(st.nRegions), "blocks": int(st.nBlocks),
            "max_band_width": int(st.maxWidth), "ms_per_pass": 1e3 * dt, "gcups": st.cells / dt / 1e9, "pairs_per_s": n / dt,
-           "phase_ms": {"band": st.msBand, "forward": st.msForward, "backward": st.msBackward, "totals": st.msTotals, "posterior": st.msPosterior}}
+           "phase_ms": {"band": st.msBand, "forward": st.msForward, "forward_checkpoint_pass": st.msCheckpoint, "backward": st.msBackward, "totals": st.msTotals, "posterior": st.msPosterior}}
     if extra:
         out.update(extra)
     print(json.dumps(out), flush=True)
