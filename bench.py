@@ -160,7 +160,7 @@ def main():
         # the reference's CPU path on all host cores; rank 0 only
         if rank != 0:
             return
-        n_sample = max(2 * threads, 64)
+        n_sample = max(32 * threads, 256)  # enough pairs per thread for an even load
         packed = make_inputs(n_sample, 0, params)
         ident, dt_probe, _ = cpu_arm(packed, min(8, n_sample), 1)
         per_pair = dt_probe / min(8, n_sample)

@@ -277,6 +277,49 @@ void getExpectationsUsingAnchorsBatch(StateMachine *sM, Hmm *hmmExpectations, in
     packed_free(&k);
 }
 
+/* ---- resident batches: the inputs go to the device once, every EM iteration is one more pass with a new model ---- */
+
+struct _cpecanResidentBatch {
+    cpb_batch *b;
+    int64_t n;
+};
+
+CpecanResidentBatch *cpecanResidentBatch_construct(int64_t n, const char *const *sX, const char *const *sY, stList *const *anchorPairs,
+                                                   PairwiseAlignmentParameters *p, const bool *raggedLeft, const bool *raggedRight) {
+    Packed k;
+    pack(&k, n, sX, sY, anchorPairs, raggedLeft, raggedRight, p->diagonalExpansion);
+    CpecanResidentBatch *r = cpecan_malloc(sizeof(*r));
+    r->n = n;
+    r->b = NULL;
+    if (cpb_batch_create(context(), k.n, k.seqX, k.xOff, k.seqY, k.yOff, k.anchors, k.aOff, k.rl, k.rr, &r->b) != CPB_OK)
+        st_errAbort("cpecan: %s", cpb_last_error());
+    packed_free(&k);
+    return r;
+}
+
+void cpecanResidentBatch_destruct(CpecanResidentBatch *r) {
+    if (r == NULL) return;
+    cpb_batch_destroy(r->b);
+    free(r);
+}
+
+void cpecanResidentBatch_getExpectations(CpecanResidentBatch *r, StateMachine *sM, Hmm *hmmExpectations, PairwiseAlignmentParameters *p) {
+    if (hmmExpectations->stateNumber != sM->stateNumber)
+        st_errAbort("getExpectations: the Hmm has %lld states, the state machine %lld", (long long) hmmExpectations->stateNumber,
+                    (long long) sM->stateNumber);
+    CpbParams q;
+    to_engine_params(p, &q);
+    const int rc = cpb_batch_run(r->b, cpecan_model_of(sM), &q, CPB_MODE_EXPECTATIONS);
+    if (rc == CPB_ERR_BAND) st_errAbort("%s: %s", PAIRWISE_ALIGNMENT_EXCEPTION_ID, cpb_last_error());
+    if (rc != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
+    const int64_t S = sM->stateNumber;
+    double total[CPB_HMM_LEN(5)];
+    if (cpb_batch_fetch_expectations(r->b, NULL, total) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
+    for (int64_t i = 0; i < S * S; i++) hmmExpectations->transitions[i] += total[i];
+    for (int64_t i = 0; i < S * 16; i++) hmmExpectations->emissions[i] += total[S * S + i];
+    hmmExpectations->likelihood += total[S * S + S * 16];
+}
+
 void computeForwardProbabilityBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY, stList *const *anchorPairs,
                                     PairwiseAlignmentParameters *p, const bool *raggedLeft, const bool *raggedRight, double *logProbs) {
     Packed k;

@@ -164,6 +164,15 @@ void getExpectationsUsingAnchorsBatch(StateMachine *sM, Hmm *hmmExpectations, in
 void computeForwardProbabilityBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY, stList *const *anchorPairs,
                                     PairwiseAlignmentParameters *p, const bool *raggedLeft, const bool *raggedRight, double *logProbs);
 
+/* A batch whose sequences and anchors stay on the device: EM runs the expectation pass over the same alignments once per iteration
+ * with a new model (cPecanEm.py:176-215 re-reads everything through a cPecanRealign subprocess per iteration and alignment file). */
+typedef struct _cpecanResidentBatch CpecanResidentBatch;
+CpecanResidentBatch *cpecanResidentBatch_construct(int64_t n, const char *const *sX, const char *const *sY, stList *const *anchorPairs,
+                                                   PairwiseAlignmentParameters *p, const bool *raggedLeft, const bool *raggedRight);
+void cpecanResidentBatch_destruct(CpecanResidentBatch *batch);
+/* += into hmmExpectations, as getExpectationsUsingAnchorsBatch */
+void cpecanResidentBatch_getExpectations(CpecanResidentBatch *batch, StateMachine *sM, Hmm *hmmExpectations, PairwiseAlignmentParameters *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,3 +194,77 @@ def test_missing_sequence_is_an_error(tmp_path):
     fa.write_text(">a\nACGT\n")
     out = subprocess.run([EXE, str(fa)], input="cigar: b 0 4 + a 0 4 + 0 M 4\n", capture_output=True, text=True)
     assert out.returncode != 0 and "no sequence named b" in out.stderr
+
+
+# ---- cPecanEm: the EM trainer over the same inputs ----
+EM_EXE = os.path.join(ROOT, "cpecan_b200", "lib", "cPecanEm")
+
+
+def read_model(path):
+    lines = open(path).read().splitlines()
+    head = lines[0].split()
+    S = 5 if int(head[0]) < 2 else 3
+    return dict(type=int(head[0]), transitions=np.array([float(v) for v in head[1:1 + S * S]]), likelihood=float(head[1 + S * S]),
+                emissions=np.array([float(v) for v in lines[1].split()]), running=[float(v) for v in lines[2].split()] if len(lines) > 2 else [])
+
+
+def em_params():
+    p = cp.pairwiseAlignmentBandingParameters_construct()  # cPecanRealign's defaults, then cPecanEm.py:371
+    p.constraintDiagonalTrim, p.diagonalExpansion, p.splitMatrixBiggerThanThis = 0, 10, 3000 * 3000
+    return p
+
+
+def run_em(tmp_path, fasta, jobs, args):
+    fa = tmp_path / "seqs.fa"
+    fa.write_text("".join("%s\n%s\n" % (h, s) for h, s in fasta))
+    cig = "".join(cigar_line(j["name1"], j["s1"], j["e1"], 1, j["name2"], j["s2"], j["e2"], j["strand2"], 1.0, j["ops"]) + "\n" for j in jobs)
+    out = subprocess.run([EM_EXE] + args + [str(fa)], input=cig, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return out
+
+
+@pytest.mark.parametrize("type_,name", [(cp.fiveState, "fiveState"), (cp.threeState, "threeState")])
+def test_em_iterations_match_the_oracle(tmp_path, type_, name):
+    """three iterations from the all-equal model, emissions trained: expectation pass (oracle: the reference's
+    getExpectationsUsingAnchors) + normalise, as cPecanEm.py:176-209 does through expectation files"""
+    from cpecan_b200 import sharding
+
+    oracle = helpers.best_oracle()
+    rng = np.random.default_rng(46)
+    fasta, jobs = make_inputs(rng, 10, 250)
+    model = tmp_path / "out.hmm"
+    run_em(tmp_path, fasta, jobs, ["--iterations", "3", "--trainEmissions", "--modelType", name, "--outputModel", str(model)])
+    got = read_model(model)
+    S = 5 if type_ == cp.fiveState else 3
+    p = em_params()
+    trans, emis, running = np.full(S * S, 1.0 / S), np.full(S * 16, 1.0 / 16), []
+    for _ in range(3):
+        spec = helpers.ModelSpec(type_, trans.reshape(S, S), emis.reshape(S, 16))
+        total = np.zeros(cp.hmm_len(S))
+        for j in jobs:
+            sX, sY = j["subX"], j["subY"]
+            anchors = np.array([(x, y, 10) for x, y in j["cols"] if sX[x] == sY[y]], dtype=np.int64).reshape(-1, 3)
+            total += oracle.expectations(spec.orc(), helpers.orc_params_from(p), sX, sY, anchors, True, True)
+        total[:-1] += 1e-12
+        running.append(total[-1])
+        hmm = sharding.normalise_hmm(total, S)
+        trans, emis = hmm[:S * S], hmm[S * S:S * S + 16 * S]
+    assert got["type"] == type_
+    np.testing.assert_allclose(got["transitions"], trans, rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(got["emissions"], emis, rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(got["running"], running, rtol=1e-9)
+    assert running[2] > running[1] > running[0]  # EM increases the likelihood (tests/pairwiseAlignerTest.c:1091-1155)
+
+
+def test_em_random_trials_keep_the_best(tmp_path):
+    rng = np.random.default_rng(47)
+    fasta, jobs = make_inputs(rng, 6, 200)
+    model = tmp_path / "best.hmm"
+    run_em(tmp_path, fasta, jobs, ["--iterations", "2", "--randomStart", "--trials", "3", "--seed", "7", "--outputTrialHmms", "--outputModel", str(model)])
+    trials = [read_model(str(model) + "_%d" % i) for i in range(3)]
+    best = max(trials, key=lambda m: m["likelihood"])
+    got = read_model(model)
+    assert got["likelihood"] == best["likelihood"] and np.array_equal(got["transitions"], best["transitions"])
+    assert len({m["likelihood"] for m in trials}) == 3  # different random starts
+    # emissions are not trained by default: they stay the random start's (cPecanEm.py:200-202)
+    assert all(len(m["running"]) == 2 for m in trials)

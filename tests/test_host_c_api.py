@@ -57,6 +57,10 @@ def test_host_library_has_no_dp_of_its_own():
     for fn in os.listdir(host_dir):
         text = open(os.path.join(host_dir, fn)).read()
         assert "oracle" not in text.lower().replace("oracle/", "") or fn.endswith(".md")
+        if fn == "cPecanEm.c":
+            # the EM trainer's Jukes-Cantor starting emissions (cPecanEm.py:87-93) are the one exponential on the host side
+            assert len(re.findall(r"\bexp\s*\(", text)) == 1 and "jukes_cantor_emissions" in text
+            text = re.sub(r"\bexp\s*\(-4\.0 \* divergence / 3\.0\)", "", text)
         assert not re.search(r"\blogAdd\s*\(|\bexp\s*\(|\blog\s*\(", text), fn
 
 
