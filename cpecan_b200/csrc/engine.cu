@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 #include "cpecan_b200.h"
@@ -302,59 +304,79 @@ extern "C" void cpb_batch_destroy(cpb_batch *b) {
  * region construction on the host
  * ---------------------------------------------------------------------------------------------- */
 static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
-    b->hRegions.clear();
-    std::vector<int64_t> split;
-    int64_t diagBase = 0, blockBase = 0, stripBase = 0;
-    for (int64_t i = 0; i < b->n; i++) {
-        const int64_t lX = b->xOff[i + 1] - b->xOff[i], lY = b->yOff[i + 1] - b->yOff[i];
-        const int64_t a0 = b->aOff[i], nA = b->aOff[i + 1] - a0;
-        const int64_t *an = b->anchors.data() + 3 * a0;
-        int64_t nReg = 1;
-        if (mode == CPB_MODE_FORWARD) {
-            split.assign({ 0, 0, lX, lY });
-        } else {
-            split.resize(4 * 4);
-            nReg = cpb_split_points(an, nA, lX, lY, p->splitMatrixBiggerThanThis, b->rl[i], b->rr[i], split.data(), 4);
-            if (nReg > 4) {
-                split.resize(4 * nReg);
-                nReg = cpb_split_points(an, nA, lX, lY, p->splitMatrixBiggerThanThis, b->rl[i], b->rr[i], split.data(), nReg);
+    /* Pairs are independent: the split points and region records of every pair are made by a pool of host threads (this is a scan over
+     * all anchors, ~1 ms per 300 k anchors per thread), then one serial pass assigns the offsets into the device arrays. */
+    const int64_t n = b->n;
+    std::vector<std::vector<RegionDev>> perPair((size_t) n);
+    auto work = [&](int64_t i0, int64_t i1) {
+        std::vector<int64_t> split;
+        for (int64_t i = i0; i < i1; i++) {
+            const int64_t lX = b->xOff[i + 1] - b->xOff[i], lY = b->yOff[i + 1] - b->yOff[i];
+            const int64_t a0 = b->aOff[i], nA = b->aOff[i + 1] - a0;
+            const int64_t *an = b->anchors.data() + 3 * a0;
+            int64_t nReg = 1;
+            if (mode == CPB_MODE_FORWARD) {
+                split.assign({ 0, 0, lX, lY });
+            } else {
+                split.resize(4 * 4);
+                nReg = cpb_split_points(an, nA, lX, lY, p->splitMatrixBiggerThanThis, b->rl[i], b->rr[i], split.data(), 4);
+                if (nReg > 4) {
+                    split.resize(4 * nReg);
+                    nReg = cpb_split_points(an, nA, lX, lY, p->splitMatrixBiggerThanThis, b->rl[i], b->rr[i], split.data(), nReg);
+                }
+            }
+            std::vector<RegionDev> &out = perPair[(size_t) i];
+            out.reserve((size_t) nReg);
+            int64_t j = 0;
+            for (int64_t r = 0; r < nReg; r++) {
+                const int64_t x1 = split[4 * r], y1 = split[4 * r + 1], x2 = split[4 * r + 2], y2 = split[4 * r + 3];
+                RegionDev R;
+                memset(&R, 0, sizeof(R));
+                R.xBase = b->xOff[i] + x1;
+                R.yBase = b->yOff[i] + y1;
+                R.anchorBase = a0 + j;
+                int64_t cnt = 0;
+                /* anchors of this region: up to the first one on or past the region's last diagonal (impl/pairwiseAligner.c:1296-1308) */
+                while (j < nA && an[3 * j] + an[3 * j + 1] < x2 + y2) {
+                    j++;
+                    cnt++;
+                }
+                R.nAnchors = (int32_t) cnt;
+                R.lX = (int32_t) (x2 - x1);
+                R.lY = (int32_t) (y2 - y1);
+                R.pair = (int32_t) i;
+                R.ox = (int32_t) x1;
+                R.oy = (int32_t) y1;
+                if (mode == CPB_MODE_FORWARD) {
+                    R.raggedL = b->rl[i];
+                    R.raggedR = b->rr[i];
+                } else {
+                    R.raggedL = b->rl[i] || r > 0;
+                    R.raggedR = b->rr[i] || r < nReg - 1;
+                }
+                /* consecutive traceback points are at least minDiags - (traceBack+1) diagonals apart (T moves to d - traceBack - 1) */
+                R.blockCap = (int32_t) (((int64_t) R.lX + R.lY) / (p->minDiagsBetweenTraceBack - p->traceBackDiagonals - 1) + 2);
+                out.push_back(R);
             }
         }
-        int64_t j = 0;
-        for (int64_t r = 0; r < nReg; r++) {
-            const int64_t x1 = split[4 * r], y1 = split[4 * r + 1], x2 = split[4 * r + 2], y2 = split[4 * r + 3];
-            RegionDev R;
-            memset(&R, 0, sizeof(R));
-            R.xBase = b->xOff[i] + x1;
-            R.yBase = b->yOff[i] + y1;
-            R.anchorBase = a0 + j;
-            int64_t cnt = 0;
-            /* anchors of this region: up to the first one on or past the region's last diagonal (impl/pairwiseAligner.c:1296-1308) */
-            while (j < nA && an[3 * j] + an[3 * j + 1] < x2 + y2) {
-                j++;
-                cnt++;
-            }
-            R.nAnchors = (int32_t) cnt;
-            R.lX = (int32_t) (x2 - x1);
-            R.lY = (int32_t) (y2 - y1);
-            R.pair = (int32_t) i;
-            R.ox = (int32_t) x1;
-            R.oy = (int32_t) y1;
-            if (mode == CPB_MODE_FORWARD) {
-                R.raggedL = b->rl[i];
-                R.raggedR = b->rr[i];
-            } else {
-                R.raggedL = b->rl[i] || r > 0;
-                R.raggedR = b->rr[i] || r < nReg - 1;
-            }
-            const int64_t N = (int64_t) R.lX + R.lY;
+    };
+    const int64_t nThreads = std::max<int64_t>(1, std::min<int64_t>({ (int64_t) std::thread::hardware_concurrency(), (int64_t) 16, n / 256 }));
+    if (nThreads <= 1) {
+        work(0, n);
+    } else {
+        std::vector<std::thread> pool;
+        for (int64_t t = 0; t < nThreads; t++) pool.emplace_back(work, n * t / nThreads, n * (t + 1) / nThreads);
+        for (auto &t : pool) t.join();
+    }
+    b->hRegions.clear();
+    int64_t diagBase = 0, blockBase = 0, stripBase = 0;
+    for (int64_t i = 0; i < n; i++) {
+        for (RegionDev &R : perPair[(size_t) i]) {
             R.diagBase = diagBase;
             R.blockBase = blockBase;
             R.stripBase = stripBase;
             stripBase += (R.lX >> 5) + 1;
-            /* consecutive traceback points are at least minDiags - (traceBack+1) diagonals apart (T moves to d - traceBack - 1) */
-            R.blockCap = (int32_t) (N / (p->minDiagsBetweenTraceBack - p->traceBackDiagonals - 1) + 2);
-            diagBase += N + 3; /* lX+lY+1 diagonals and two sentinels */
+            diagBase += (int64_t) R.lX + R.lY + 3; /* lX+lY+1 diagonals and two sentinels */
             blockBase += R.blockCap;
             b->hRegions.push_back(R);
         }
@@ -411,6 +433,18 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         events.clear();
     };
 
+    /* CPB_HOST_TIMING=1: wall-clock stamps (with a stream synchronisation each) at the stages of a run, on stderr */
+    const bool hostTiming = getenv("CPB_HOST_TIMING") != nullptr;
+    auto wall = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tStamp = wall();
+    auto stamp = [&](const char *what) {
+        if (!hostTiming) return;
+        cudaStreamSynchronize(st);
+        const double now = wall();
+        fprintf(stderr, "  [run] %-28s %9.3f ms\n", what, now - tStamp);
+        tStamp = now;
+    };
+
     const int nPlanes = mode == CPB_MODE_FORWARD ? 0 : (mode == CPB_MODE_ALIGNED_PAIRS ? 1 : (mode == CPB_MODE_ALIGNED_PAIRS_INDELS ? 3 : S));
     const int auxF = (mode == CPB_MODE_ALIGNED_PAIRS || mode == CPB_MODE_ALIGNED_PAIRS_INDELS) ? S : 0;
     const int nLists = mode == CPB_MODE_ALIGNED_PAIRS ? 1 : (mode == CPB_MODE_ALIGNED_PAIRS_INDELS ? 3 : 0);
@@ -418,6 +452,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
 
     int rc = build_regions(b, p, mode);
     if (rc != CPB_OK) return rc;
+    stamp("build_regions");
     std::vector<RegionDev> &regs = b->hRegions;
     const int64_t nReg = (int64_t) regs.size();
     stx.nRegions = nReg;
@@ -477,6 +512,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
 
+    stamp("k_band + region sizes");
     /* validate, gather the block table in compact region order */
     int64_t totalBlocks = 0;
     for (int64_t r = 0; r < nReg; r++) {
@@ -518,6 +554,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         CUDA_TRY(cudaMemcpyAsync(b->blocks.p, hBlocks.data(), totalBlocks * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
     }
 
+    stamp("block table");
     /* chunk planning */
     size_t freeB = 0, totalB = 0;
     CUDA_TRY(cudaMemGetInfo(&freeB, &totalB));
@@ -563,11 +600,13 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         }
     }
     stx.nChunks = (int64_t) chunks.size();
+    stamp("chunk planning");
     if (totalBlocks > 0) CUDA_TRY(cudaMemcpyAsync(b->blocks.p, hBlocks.data(), totalBlocks * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
     size_t scratchNeed = 0;
     for (auto &c : chunks) scratchNeed = std::max(scratchNeed, (size_t) (c.stride * bytesPerCell + c.aux * 8 + 256));
     if ((rc = ctx->scratch.reserve(std::max<size_t>(scratchNeed, 256))) != CPB_OK) return rc;
 
+    stamp("scratch");
     /* launch lists: forward regions per class, backward blocks per class, all blocks in order */
     std::vector<int32_t> lists;
     for (auto &c : chunks) {
@@ -586,6 +625,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     CUDA_TRY(cudaMemcpyAsync(b->lists.p, lists.data(), lists.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->regions.p, regs.data(), nReg * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
 
+    stamp("lists");
     int64_t maxChunkBlocks = 1, maxDecades = 1, maxMaskWords = 1, maxChunkPairs = 1;
     for (auto &c : chunks) {
         maxChunkBlocks = std::max(maxChunkBlocks, c.block1 - c.block0);
@@ -608,6 +648,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         if ((rc = b->pairBlockOff.reserve((size_t) (maxChunkPairs + 2) * sizeof(int64_t))) != CPB_OK) return rc;
     }
 
+    stamp("planning + lists");
     /* strip engine: persistent grid of independent warps, boundary rings, work counters */
     typedef void (*StripKernel)(const DpArgs, const CpbModel, const StripArgs);
     StripKernel kFwdStrip = nullptr, kFwdTeam = nullptr, kFwdBlocks = nullptr, kBwdStrip = nullptr;
@@ -776,6 +817,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         }
     }
 
+    stamp("strip setup (+ checkpoint pass)");
     std::vector<int64_t> hPairOff;
     int64_t running[3] = { 0, 0, 0 };
     int64_t chunkIndex = -1;
@@ -945,6 +987,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
                 100.0 * ls[1] / (ls[0] ? ls[0] : 1), ls[2], 100.0 * ls[3] / (ls[2] ? ls[2] : 1));
     }
 #endif
+    stamp("chunks");
     finish_events();
     stx.msForward += stx.msCheckpoint; /* the forward phase is both passes */
     for (int l = 0; l < nLists; l++) {
