@@ -545,20 +545,43 @@ __global__ void __launch_bounds__(32) k_expect(const DpArgs a, const CpbModel mo
     for (int k = 0; k < NL + NM + NU; k++) accT[k] = 0.0;
     double likelihood = 0.0;
 
-    for (int d = K.from; d > K.T; d--) {
-        const int dt = K.from - 10 * ((K.from - d) / 10);
+    /* The owned cells of a decade (10 diagonals sharing one totalProbability) are one contiguous range of the cell enumeration:
+     * lanes sweep it flat, 32 cells at a time whatever the band width, and find their diagonal among the decade's records, which
+     * lanes 0..nd+1 hold (two more below the decade for the lower / upper and middle neighbours). */
+    const int nDecades = (K.from - K.T + 9) / 10;
+    for (int j = 0; j < nDecades; j++) {
+        const int dt = K.from - 10 * j, dLow = max(dt - 9, K.T + 1), nd = dt - dLow + 1;
         const double total = tot[dt];
-        likelihood += total; /* once per diagonal (impl/pairwiseAligner.c:743) */
-        const DiagRec rec = dg[d];
-        const DiagRec rec1 = dg[d - 1];
-        const bool haveM = d >= 2 && !(K.T > 0 && d == K.T + 1); /* F[d-2] was freed at the block boundary (:855) */
-        DiagRec rec2 = rec1;
-        if (d >= 2) rec2 = dg[d - 2];
-        for (int i = lane; i < rec.width; i += 32) {
+        for (int q = 0; q < nd; q++) likelihood += total; /* once per diagonal (impl/pairwiseAligner.c:743), highest first */
+        DiagRec mine = dg[max(dLow - 2 + min(lane, nd + 1), 0)]; /* lane r: diagonal dLow - 2 + r */
+        const int c0 = (int) __shfl_sync(0xFFFFFFFFu, mine.coff, 2);
+        const int c1 = (int) (__shfl_sync(0xFFFFFFFFu, mine.coff, nd + 1) + __shfl_sync(0xFFFFFFFFu, (uint32_t) mine.width, nd + 1));
+        for (int base = c0; base < c1; base += 32) {
+            const int c = base + lane;
+            const bool valid = c < c1;
+            int q = 0;
+            for (int t = 1; t < nd; t++) {
+                const int ct = (int) __shfl_sync(0xFFFFFFFFu, mine.coff, t + 2);
+                if (c >= ct) q = t;
+            }
+            DiagRec rec, rec1, rec2;
+            rec.xmyL = __shfl_sync(0xFFFFFFFFu, mine.xmyL, q + 2);
+            rec.width = __shfl_sync(0xFFFFFFFFu, mine.width, q + 2);
+            rec.coff = __shfl_sync(0xFFFFFFFFu, mine.coff, q + 2);
+            rec1.xmyL = __shfl_sync(0xFFFFFFFFu, mine.xmyL, q + 1);
+            rec1.width = __shfl_sync(0xFFFFFFFFu, mine.width, q + 1);
+            rec1.coff = __shfl_sync(0xFFFFFFFFu, mine.coff, q + 1);
+            rec2.xmyL = __shfl_sync(0xFFFFFFFFu, mine.xmyL, q);
+            rec2.width = __shfl_sync(0xFFFFFFFFu, mine.width, q);
+            rec2.coff = __shfl_sync(0xFFFFFFFFu, mine.coff, q);
+            if (!valid) continue;
+            const int d = dLow + q;
+            const int i = c - (int) rec.coff;
+            const bool haveM = d >= 2 && !(K.T > 0 && d == K.T + 1); /* F[d-2] was freed at the block boundary (:855) */
             const int xmy = rec.xmyL + 2 * i;
             const int x = (d + xmy) >> 1, y = (d - xmy) >> 1;
             const int cX = x > 0 ? sx[x - 1] : 4, cY = y > 0 ? sy[y - 1] : 4;
-            const int64_t cell = (int64_t) rec.coff + i;
+            const int64_t cell = c;
             double b[S];
 #pragma unroll
             for (int s = 0; s < S; s++) b[s] = pb[(int64_t) s * a.planeStride + cell];
@@ -567,9 +590,9 @@ __global__ void __launch_bounds__(32) k_expect(const DpArgs a, const CpbModel mo
             const bool inU = xmy + 1 >= rec1.xmyL && iU < rec1.width;
             const int iM = (xmy - rec2.xmyL) >> 1;
             const bool inM = haveM && xmy >= rec2.xmyL && iM < rec2.width;
-            double q[S]; /* per to-state sum for the emission expectation */
+            double q2[S]; /* per to-state sum for the emission expectation */
 #pragma unroll
-            for (int s = 0; s < S; s++) q[s] = 0.0;
+            for (int s = 0; s < S; s++) q2[s] = 0.0;
             const bool emit = cX < 4 && cY < 4;
             if (inL) {
 #pragma unroll
@@ -577,7 +600,7 @@ __global__ void __launch_bounds__(32) k_expect(const DpArgs a, const CpbModel mo
                     const int f = lower_from<S>(k), t = lower_to<S>(k);
                     const double pr = exp(pf[(int64_t) f * a.planeStride + rec1.coff + iL] + b[t] + tab.tl[cX][k] - total);
                     accT[k] += pr;
-                    q[t] += pr;
+                    q2[t] += pr;
                 }
             }
             if (inM) {
@@ -586,7 +609,7 @@ __global__ void __launch_bounds__(32) k_expect(const DpArgs a, const CpbModel mo
                     const int f = middle_from<S>(k);
                     const double pr = exp(pf[(int64_t) f * a.planeStride + rec2.coff + iM] + b[0] + tab.tm[cX * 5 + cY][k] - total);
                     accT[NL + k] += pr;
-                    q[0] += pr;
+                    q2[0] += pr;
                 }
             }
             if (inU) {
@@ -595,12 +618,12 @@ __global__ void __launch_bounds__(32) k_expect(const DpArgs a, const CpbModel mo
                     const int f = upper_from<S>(k), t = upper_to<S>(k);
                     const double pr = exp(pf[(int64_t) f * a.planeStride + rec1.coff + iU] + b[t] + tab.tu[cY][k] - total);
                     accT[NL + NM + k] += pr;
-                    q[t] += pr;
+                    q2[t] += pr;
                 }
             }
             if (emit) {
 #pragma unroll
-                for (int s = 0; s < S; s++) ePriv[((s * 16) + cX * 4 + cY) * 32 + lane] += q[s];
+                for (int s = 0; s < S; s++) ePriv[((s * 16) + cX * 4 + cY) * 32 + lane] += q2[s];
             }
         }
     }
