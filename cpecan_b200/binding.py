@@ -111,6 +111,8 @@ def _load():
     L.cpb_batch_result_count.argtypes = [C.c_void_p, C.c_int]
     L.cpb_batch_fetch_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.cpb_batch_fetch_pairs_reference_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.cpb_batch_reweight_pairs.argtypes = [C.c_void_p, C.c_double]
+    L.cpb_batch_alignment_scores.argtypes = [C.c_void_p, C.c_void_p]
     L.cpb_batch_device_triples.restype = C.c_void_p
     L.cpb_batch_device_triples.argtypes = [C.c_void_p, C.c_int]
     L.cpb_batch_fetch_expectations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -282,6 +284,16 @@ class Batch:
         fetch = lib.cpb_batch_fetch_pairs_reference_order if reference_order else lib.cpb_batch_fetch_pairs
         _check(fetch(self.h, which, C.c_void_p(off.ctypes.data), C.c_void_p(tri.ctypes.data)))
         return off, tri[:cnt]
+
+    def reweight_pairs(self, gap_gamma):
+        """reweightAlignedPairs2 (impl/pairwiseAligner.c:1519-1560) on the device, in place on list 0"""
+        _check(lib.cpb_batch_reweight_pairs(self.h, float(gap_gamma)))
+
+    def alignment_scores(self):
+        """getAlignmentScore (impl/multipleAligner.c:604-619) per pair -> int64[n]"""
+        out = np.zeros(self.n, dtype=np.int64)
+        _check(lib.cpb_batch_alignment_scores(self.h, C.c_void_p(out.ctypes.data)))
+        return out
 
     def fetch_expectations(self, per_pair=True):
         L = hmm_len(self.S)

@@ -1090,6 +1090,80 @@ extern "C" int cpb_batch_fetch_pairs_reference_order(cpb_batch *b, int list, int
     return CPB_OK;
 }
 
+/* device copies of the per-pair offsets the post-posterior kernels need */
+static int upload_pair_tables(cpb_batch *b, int list, DevBuf &dOff, DevBuf &dX, DevBuf &dY) {
+    int rc;
+    const size_t bytes = (size_t) (b->n + 1) * sizeof(int64_t);
+    if ((rc = dOff.reserve(bytes)) != CPB_OK || (rc = dX.reserve(bytes)) != CPB_OK || (rc = dY.reserve(bytes)) != CPB_OK) return rc;
+    cudaStream_t st = b->ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(dOff.p, b->pairOff[list].data(), bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dX.p, b->xOff.data(), bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dY.p, b->yOff.data(), bytes, cudaMemcpyHostToDevice, st));
+    return CPB_OK;
+}
+
+extern "C" int cpb_batch_reweight_pairs(cpb_batch *b, double gapGamma) {
+    if (b == nullptr || (b->lastMode != CPB_MODE_ALIGNED_PAIRS && b->lastMode != CPB_MODE_ALIGNED_PAIRS_INDELS)) {
+        cpb_set_error("cpb_batch_reweight_pairs: no aligned-pair results in this batch");
+        return CPB_ERR_ARGUMENT;
+    }
+    if (!(gapGamma > 0.0) || b->outCount[0] == 0) return CPB_OK; /* reweightAlignedPairs2 returns its input for gapGamma <= 0 */
+    CUDA_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    DevBuf dOff, dX, dY, gX, gY;
+    for (DevBuf *d : { &dOff, &dX, &dY, &gX, &gY }) d->pool = &b->ctx->pool;
+    int rc = upload_pair_tables(b, 0, dOff, dX, dY);
+    const int64_t lenX = b->xOff[b->n], lenY = b->yOff[b->n];
+    if (rc == CPB_OK) rc = gX.reserve(std::max<int64_t>(lenX, 1) * sizeof(long long));
+    if (rc == CPB_OK) rc = gY.reserve(std::max<int64_t>(lenY, 1) * sizeof(long long));
+    if (rc == CPB_OK) {
+        k_fill_i64<<<1184, 256, 0, st>>>(gX.as<long long>(), lenX, (long long) CPB_PAIR_ALIGNMENT_PROB_1);
+        k_fill_i64<<<1184, 256, 0, st>>>(gY.as<long long>(), lenY, (long long) CPB_PAIR_ALIGNMENT_PROB_1);
+        const int64_t nT = b->outCount[0];
+        const unsigned grid = (unsigned) ((nT + 255) / 256);
+        k_gap_weights<<<grid, 256, 0, st>>>(b->out[0].as<int32_t>(), nT, dOff.as<int64_t>(), (int) b->n, dX.as<int64_t>(), dY.as<int64_t>(),
+                                            gX.as<long long>(), gY.as<long long>());
+        k_reweight<<<grid, 256, 0, st>>>(b->out[0].as<int32_t>(), nT, dOff.as<int64_t>(), (int) b->n, dX.as<int64_t>(), dY.as<int64_t>(),
+                                         gX.as<long long>(), gY.as<long long>(), gapGamma);
+        b->stats.kernelLaunches += 4;
+        cudaError_t e = cudaStreamSynchronize(st); /* the temporaries go back to the pool */
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            cpb_set_error("cpb_batch_reweight_pairs: %s", cudaGetErrorString(e));
+            rc = CPB_ERR_CUDA;
+        }
+    }
+    for (DevBuf *d : { &dOff, &dX, &dY, &gX, &gY }) d->release();
+    return rc;
+}
+
+extern "C" int cpb_batch_alignment_scores(cpb_batch *b, int64_t *scores) {
+    if (b == nullptr || scores == nullptr || (b->lastMode != CPB_MODE_ALIGNED_PAIRS && b->lastMode != CPB_MODE_ALIGNED_PAIRS_INDELS)) {
+        cpb_set_error("cpb_batch_alignment_scores: no aligned-pair results in this batch");
+        return CPB_ERR_ARGUMENT;
+    }
+    if (b->n == 0) return CPB_OK;
+    CUDA_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    DevBuf dOff, dX, dY, dS;
+    for (DevBuf *d : { &dOff, &dX, &dY, &dS }) d->pool = &b->ctx->pool;
+    int rc = upload_pair_tables(b, 0, dOff, dX, dY);
+    if (rc == CPB_OK) rc = dS.reserve((size_t) b->n * sizeof(int64_t));
+    if (rc == CPB_OK) {
+        k_alignment_scores<<<(unsigned) ((b->n * 32 + 255) / 256), 256, 0, st>>>(b->out[0].as<int32_t>(), dOff.as<int64_t>(), (int) b->n, dX.as<int64_t>(),
+                                                                              dY.as<int64_t>(), dS.as<int64_t>());
+        b->stats.kernelLaunches++;
+        cudaError_t e = cudaMemcpyAsync(scores, dS.p, (size_t) b->n * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            cpb_set_error("cpb_batch_alignment_scores: %s", cudaGetErrorString(e));
+            rc = CPB_ERR_CUDA;
+        }
+    }
+    for (DevBuf *d : { &dOff, &dX, &dY, &dS }) d->release();
+    return rc;
+}
+
 extern "C" int cpb_batch_fetch_expectations(cpb_batch *b, double *perPair, double *total) {
     if (b == nullptr || b->lastMode != CPB_MODE_EXPECTATIONS) {
         cpb_set_error("cpb_batch_fetch_expectations: last run was not in expectation mode");

@@ -177,6 +177,7 @@ typedef struct {
         rescoreByPosteriorProbabilityIgnoringGaps;
     int64_t splitIndelsLongerThanThis; /* -1 = never */
     const char *posteriorProbsFile, *allPosteriorProbsFile;
+    bool reweightedOnDevice; /* the pairs arrive already reweighted by gapGamma (nobody asked for the raw posteriors) */
 } Options;
 
 /* everything after the device pass for one alignment (cPecanRealign.c:540-599); consumes alignedPairs */
@@ -191,7 +192,7 @@ static void job_finish(Job *j, stList *alignedPairs, const Options *o, const Pai
         stList_destruct(alignedPairs);
         alignedPairs = rescored;
     } else {
-        alignedPairs = reweightAlignedPairs2(alignedPairs, lX, lY, p->gapGamma);
+        if (!o->reweightedOnDevice) alignedPairs = reweightAlignedPairs2(alignedPairs, lX, lY, p->gapGamma);
         alignedPairs = filterPairwiseAlignmentToMakePairsOrdered(alignedPairs, j->subX, j->subY, o->matchGamma);
     }
     if (o->rescoreByPosteriorProbability) pA->score = scoreByPosteriorProbability(lX, lY, alignedPairs);
@@ -347,7 +348,10 @@ int main(int argc, char *argv[]) {
         if (hmmExpectations != NULL) {
             getExpectationsUsingAnchorsBatch(sM, hmmExpectations, n, sX, sY, anchors, p, ragged, ragged);
         } else {
-            stList **pairs = getAlignedPairsUsingAnchorsBatch(sM, n, sX, sY, anchors, p, ragged, ragged);
+            /* the gap reweighting (cPecanRealign.c:560) runs on the device unless the raw posteriors are wanted as well */
+            o.reweightedOnDevice = !o.rescoreOriginalAlignment && o.allPosteriorProbsFile == NULL;
+            stList **pairs = o.reweightedOnDevice ? getReweightedAlignedPairsUsingAnchorsBatch(sM, n, sX, sY, anchors, p, ragged, ragged, p->gapGamma)
+                                                  : getAlignedPairsUsingAnchorsBatch(sM, n, sX, sY, anchors, p, ragged, ragged);
             for (int64_t i = 0; i < n; i++) job_finish(&jobs[i], pairs[i], &o, p, stdout);
             free(pairs);
         }

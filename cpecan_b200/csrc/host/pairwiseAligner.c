@@ -245,6 +245,19 @@ stList **getAlignedPairsUsingAnchorsBatch(StateMachine *sM, int64_t n, const cha
     return lists;
 }
 
+stList **getReweightedAlignedPairsUsingAnchorsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY,
+                                                    stList *const *anchorPairs, PairwiseAlignmentParameters *p, const bool *raggedLeft,
+                                                    const bool *raggedRight, double gapGamma) {
+    Packed k;
+    pack(&k, n, sX, sY, anchorPairs, raggedLeft, raggedRight, p->diagonalExpansion);
+    cpb_batch *b = run(&k, sM, p, CPB_MODE_ALIGNED_PAIRS);
+    if (cpb_batch_reweight_pairs(b, gapGamma) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
+    stList **lists = fetch_lists(b, n, 0);
+    cpb_batch_destroy(b);
+    packed_free(&k);
+    return lists;
+}
+
 void getAlignedPairsWithIndelsUsingAnchorsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY,
                                                 stList *const *anchorPairs, PairwiseAlignmentParameters *p, stList ***alignedPairs,
                                                 stList ***gapXPairs, stList ***gapYPairs, const bool *raggedLeft, const bool *raggedRight) {

@@ -520,6 +520,61 @@ __global__ void k_pair_counts(const int32_t *counts, int64_t nDecades, int nList
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * Post-posterior filters on the compacted output: the AMAP-style gap reweighting
+ * (getIndelProbabilities / reweightAlignedPairs, impl/pairwiseAligner.c:1519-1560) and the per-pair alignment score
+ * (getAlignmentScore, impl/multipleAligner.c:604-619).  Integer sums, so atomics give the reference's result whatever the order.
+ * ------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ int pair_of_triple(const int64_t *pairOff, int nPairs, int64_t t) {
+    int lo = 0, hi = nPairs; /* last pair with pairOff[pair] <= t */
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pairOff[mid] <= t) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+__global__ void k_fill_i64(long long *p, int64_t n, long long v) {
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) p[i] = v;
+}
+/* gapX[xOff[pair] + x] and gapY[yOff[pair] + y] start at PAIR_ALIGNMENT_PROB_1; every aligned pair takes its weight off both */
+__global__ void k_gap_weights(const int32_t *triples, int64_t nTriples, const int64_t *pairOff, int nPairs, const int64_t *xOff, const int64_t *yOff,
+                              long long *gapX, long long *gapY) {
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTriples) return;
+    const int pair = pair_of_triple(pairOff, nPairs, t);
+    const long long w = triples[3 * t];
+    atomicAdd(reinterpret_cast<unsigned long long *>(gapX + xOff[pair] + triples[3 * t + 1]), (unsigned long long) (-w));
+    atomicAdd(reinterpret_cast<unsigned long long *>(gapY + yOff[pair] + triples[3 * t + 2]), (unsigned long long) (-w));
+}
+/* weight - gapGamma * (gap weight of x + gap weight of y), gap weights floored at 0, the result truncated towards zero (:1536-1547) */
+__global__ void k_reweight(int32_t *triples, int64_t nTriples, const int64_t *pairOff, int nPairs, const int64_t *xOff, const int64_t *yOff,
+                           const long long *gapX, const long long *gapY, double gapGamma) {
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTriples) return;
+    const int pair = pair_of_triple(pairOff, nPairs, t);
+    const long long gx = max(gapX[xOff[pair] + triples[3 * t + 1]], 0ll), gy = max(gapY[yOff[pair] + triples[3 * t + 2]], 0ll);
+    triples[3 * t] = (int32_t) (long long) ((double) triples[3 * t] - gapGamma * (double) (gx + gy));
+}
+/* one warp per pair: the sum of its weights, normalised by the shorter sequence, clamped to [0, 1], in units of 1e-7 */
+__global__ void k_alignment_scores(const int32_t *triples, const int64_t *pairOff, int nPairs, const int64_t *xOff, const int64_t *yOff, int64_t *scores) {
+    const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (pair >= nPairs) return;
+    long long sum = 0;
+    for (int64_t t = pairOff[pair] + lane; t < pairOff[pair + 1]; t += 32) sum += triples[3 * t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if (lane == 0) {
+        const int64_t l1 = xOff[pair + 1] - xOff[pair], l2 = yOff[pair + 1] - yOff[pair];
+        int64_t j = l1 < l2 ? l1 : l2;
+        j = j == 0 ? 1 : j;
+        double d = (double) sum / (double) (j * (int64_t) CPB_PAIR_ALIGNMENT_PROB_1);
+        d = d > 1.0 ? 1.0 : d;
+        d = d < 0.0 ? 0.0 : d;
+        scores[pair] = (int64_t) (d * CPB_PAIR_ALIGNMENT_PROB_1);
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
  * k_expect : one warp per block; expected transition and emission counts
  * (diagonalCalculationExpectations / updateExpectations, impl/pairwiseAligner.c:418-438, :735-746)
  * partial[block][CPB_HMM_LEN(S)]

@@ -154,6 +154,11 @@ void cpecan_shutdown(void);
 stList **getAlignedPairsUsingAnchorsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY,
                                           stList *const *anchorPairs, PairwiseAlignmentParameters *p, const bool *raggedLeft,
                                           const bool *raggedRight);
+/* the same followed by reweightAlignedPairs2(pairs, lX, lY, gapGamma) (:278) for every problem, done on the device before the
+ * pairs come back */
+stList **getReweightedAlignedPairsUsingAnchorsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY,
+                                                    stList *const *anchorPairs, PairwiseAlignmentParameters *p, const bool *raggedLeft,
+                                                    const bool *raggedRight, double gapGamma);
 void getAlignedPairsWithIndelsUsingAnchorsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY,
                                                 stList *const *anchorPairs, PairwiseAlignmentParameters *p, stList ***alignedPairs,
                                                 stList ***gapXPairs, stList ***gapYPairs, const bool *raggedLeft, const bool *raggedRight);

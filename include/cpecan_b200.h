@@ -150,6 +150,13 @@ int cpb_batch_fetch_pairs(cpb_batch *b, int list, int64_t *offsets, int32_t *tri
  * the traceback blocks last to first; inside a block x+y ascending and x descending): what libcpecan.so returns, so that callers whose
  * result depends on list order (impl/pairwiseAligner.c:1603-1724) behave as with the reference. */
 int cpb_batch_fetch_pairs_reference_order(cpb_batch *b, int list, int64_t *offsets, int32_t *triples);
+/* Post-posterior filters on the device (list 0 of the last ALIGNED_PAIRS / ALIGNED_PAIRS_INDELS run).
+ * cpb_batch_reweight_pairs: every weight becomes weight - gapGamma * (gap weight of its x + gap weight of its y), where the gap
+ * weight of a position is PAIR_ALIGNMENT_PROB_1 minus the weights aligned to it, floored at 0 -- reweightAlignedPairs2 of
+ * impl/pairwiseAligner.c:1519-1560, in place, before the pairs are fetched; gapGamma <= 0 leaves them alone, as there.
+ * cpb_batch_alignment_scores: per pair, getAlignmentScore of impl/multipleAligner.c:604-619 (n int64 values to the host). */
+int cpb_batch_reweight_pairs(cpb_batch *b, double gapGamma);
+int cpb_batch_alignment_scores(cpb_batch *b, int64_t *scores);
 /* device pointers of the same (valid until the next run / destroy) */
 const int32_t *cpb_batch_device_triples(const cpb_batch *b, int list);
 /* EXPECTATIONS mode: perPair (may be NULL) receives n * CPB_HMM_LEN(S) doubles, total receives CPB_HMM_LEN(S) doubles

@@ -422,3 +422,34 @@ def test_two_pass_forward_is_bit_identical(ctx, oracle, monkeypatch):
     # and against the oracle directly
     monkeypatch.setenv("CPB_TWO_PASS", "1")
     check_aligned_pairs(ctx, oracle, helpers.ModelSpec(cp.fiveState), p, cases[:3], "two-pass")
+
+
+def test_device_reweighting_and_alignment_scores(ctx):
+    """reweightAlignedPairs2 (impl/pairwiseAligner.c:1519-1560) and getAlignmentScore
+    (impl/multipleAligner.c:604-619) on the compacted device output, against the host list functions that
+    tests/test_realign_host.py pins to the reference build.  Integer arithmetic: exact."""
+    from test_realign_host import Host
+
+    host = Host()
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    packed = synth.evolved_pairs(40, 300, seed=91, trim=int(p.constraintDiagonalTrim), expansion=int(p.diagonalExpansion))
+    b = cp.Batch(ctx, None, None, packed=packed)
+    b.run(cp.stateMachine5_construct(), p, cp.MODE_ALIGNED_PAIRS)
+    off, before = b.fetch_pairs(0)
+    before = before.copy()
+    scores = b.alignment_scores()
+    for gamma in (0.0, 0.5, 0.9):
+        b.run(cp.stateMachine5_construct(), p, cp.MODE_ALIGNED_PAIRS)
+        b.reweight_pairs(gamma)
+        off2, after = b.fetch_pairs(0)
+        assert np.array_equal(off, off2) and np.array_equal(before[:, 1:], after[:, 1:])
+        for i in range(40):
+            sx, sy, _ = synth.unpack(packed, i)
+            mine = before[off[i]:off[i + 1]]
+            want = host.reweight(mine, len(sx), len(sy), gamma)
+            assert np.array_equal(after[off[i]:off[i + 1], 0], want[:, 0]), "pair %d gamma %g" % (i, gamma)
+    for i in range(40):
+        sx, sy, _ = synth.unpack(packed, i)
+        d = float(before[off[i]:off[i + 1], 0].astype(np.int64).sum()) / (max(1, min(len(sx), len(sy))) * 1e7)
+        assert scores[i] == int(min(max(d, 0.0), 1.0) * 1e7)
+    b.close()
