@@ -24,6 +24,7 @@
 #include "internal.h"
 #include "kernels.cuh"
 #include "strip_kernels.cuh"
+#include "narrow_kernels.cuh"
 
 using namespace cpb;
 
@@ -399,6 +400,22 @@ static int check_params(const CpbParams *p) {
     return CPB_OK;
 }
 
+/* Orders idx[0..n) by cost, most expensive first, to within 1/1024 of the largest cost: a counting sort on the leading bits.  The
+ * work-fetch order only needs the big items early; an exact std::sort of a few hundred thousand items was the largest host stage. */
+template <class Cost> static void order_by_cost_descending(int32_t *idx, int64_t n, Cost cost) {
+    if (n < 2) return;
+    int64_t largest = 1;
+    for (int64_t i = 0; i < n; i++) largest = std::max<int64_t>(largest, cost(idx[i]));
+    int shift = 0;
+    while ((largest >> shift) >= 2048) shift++;
+    std::vector<int64_t> start(2049, 0);
+    for (int64_t i = 0; i < n; i++) start[2047 - (cost(idx[i]) >> shift) + 1]++;
+    for (int k = 0; k < 2048; k++) start[k + 1] += start[k];
+    std::vector<int32_t> out((size_t) n);
+    for (int64_t i = 0; i < n; i++) out[(size_t) start[2047 - (cost(idx[i]) >> shift)]++] = idx[i];
+    memcpy(idx, out.data(), (size_t) n * sizeof(int32_t));
+}
+
 struct EventPair {
     cudaEvent_t a, b;
     double *sink;
@@ -556,10 +573,21 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
 
     stamp("block table");
     /* chunk planning */
-    size_t freeB = 0, totalB = 0;
-    CUDA_TRY(cudaMemGetInfo(&freeB, &totalB));
-    size_t budget = ctx->scratchBudget ? ctx->scratchBudget : (size_t) ((double) (freeB + ctx->scratch.cap) * 0.70);
     const int64_t bytesPerCell = (int64_t) sizeof(double) * 2 * nPlanes;
+    size_t budget = ctx->scratchBudget;
+    if (budget == 0) {
+        /* 70 % of what is free; a run that fits the scratch buffer already there does not need to ask the driver (cudaMemGetInfo
+         * costs tens of milliseconds once a few hundred buffers are live) */
+        size_t wholeRun = 0;
+        for (int64_t r = 0; r < nReg; r++) wholeRun += (size_t) ((regs[r].cells + 36) * bytesPerCell + (regs[r].auxDoubles + 6) * 8);
+        if (wholeRun + 256 <= ctx->scratch.cap) {
+            budget = ctx->scratch.cap;
+        } else {
+            size_t freeB = 0, totalB = 0;
+            CUDA_TRY(cudaMemGetInfo(&freeB, &totalB));
+            budget = (size_t) ((double) (freeB + ctx->scratch.cap) * 0.70);
+        }
+    }
     std::vector<Chunk> chunks;
     {
         int64_t r = 0;
@@ -615,11 +643,10 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         /* strip engine: one list of regions and one of blocks, most expensive first (work is fetched dynamically) */
         c.stripFwdOff = (int64_t) lists.size();
         for (int64_t r = c.region0; r < c.region1; r++) lists.push_back((int32_t) r);
-        std::sort(lists.begin() + c.stripFwdOff, lists.end(), [&](int32_t x, int32_t y) { return regs[x].cells > regs[y].cells; });
+        order_by_cost_descending(lists.data() + c.stripFwdOff, c.region1 - c.region0, [&](int32_t x) { return (int64_t) regs[x].cells; });
         c.stripBwdOff = (int64_t) lists.size();
         for (int64_t k = c.block0; k < c.block1; k++) lists.push_back((int32_t) k);
-        auto blockCost = [&](int32_t k) { return (int64_t) hBlocks[k].cells; };
-        std::sort(lists.begin() + c.stripBwdOff, lists.end(), [&](int32_t x, int32_t y) { return blockCost(x) > blockCost(y); });
+        order_by_cost_descending(lists.data() + c.stripBwdOff, c.block1 - c.block0, [&](int32_t k) { return (int64_t) hBlocks[k].cells; });
     }
     if ((rc = b->lists.reserve(std::max<size_t>(lists.size(), 1) * sizeof(int32_t))) != CPB_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(b->lists.p, lists.data(), lists.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -678,6 +705,31 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         kBwdStrip = k_backward_strip<S, S, false, kStripWPC>;
         break;
     }
+    /* narrow bands: groups of 8 or 16 lanes per region / block (narrow_kernels.cuh) */
+    typedef void (*NarrowKernel)(const DpArgs, const CpbModel, const NarrowArgs);
+    auto narrow_forward = [&](int G) -> NarrowKernel {
+        switch (mode) {
+        case CPB_MODE_ALIGNED_PAIRS:
+            return G == 8 ? k_forward_narrow<S, 1, 8, kStripWPC> : (G == 16 ? k_forward_narrow<S, 1, 16, kStripWPC> : k_forward_narrow<S, 1, 32, kStripWPC>);
+        case CPB_MODE_ALIGNED_PAIRS_INDELS:
+            return G == 8 ? k_forward_narrow<S, 3, 8, kStripWPC> : (G == 16 ? k_forward_narrow<S, 3, 16, kStripWPC> : k_forward_narrow<S, 3, 32, kStripWPC>);
+        default:
+            return G == 8 ? k_forward_narrow<S, S, 8, kStripWPC> : (G == 16 ? k_forward_narrow<S, S, 16, kStripWPC> : k_forward_narrow<S, S, 32, kStripWPC>);
+        }
+    };
+    auto narrow_backward = [&](int G) -> NarrowKernel {
+        switch (mode) {
+        case CPB_MODE_ALIGNED_PAIRS:
+            return G == 8 ? k_backward_narrow<S, 1, true, 8, kStripWPC>
+                          : (G == 16 ? k_backward_narrow<S, 1, true, 16, kStripWPC> : k_backward_narrow<S, 1, true, 32, kStripWPC>);
+        case CPB_MODE_ALIGNED_PAIRS_INDELS:
+            return G == 8 ? k_backward_narrow<S, 3, true, 8, kStripWPC>
+                          : (G == 16 ? k_backward_narrow<S, 3, true, 16, kStripWPC> : k_backward_narrow<S, 3, true, 32, kStripWPC>);
+        default:
+            return G == 8 ? k_backward_narrow<S, S, false, 8, kStripWPC>
+                          : (G == 16 ? k_backward_narrow<S, S, false, 16, kStripWPC> : k_backward_narrow<S, S, false, 32, kStripWPC>);
+        }
+    };
     StripArgs sargs;
     memset(&sargs, 0, sizeof(sargs));
     int stripGrid = 1, teamGrid = 1;
@@ -793,7 +845,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             /* all regions, most expensive first */
             std::vector<int32_t> order(nReg);
             for (int64_t r = 0; r < nReg; r++) order[r] = (int32_t) r;
-            std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return regs[x].cells > regs[y].cells; });
+            order_by_cost_descending(order.data(), nReg, [&](int32_t x) { return (int64_t) regs[x].cells; });
             if ((rc = b->ckSizes.reserve(std::max<size_t>(totalBlocks * sizeof(int32_t), nReg * sizeof(int32_t)))) != CPB_OK) return rc;
             CUDA_TRY(cudaMemcpyAsync(b->ckSizes.p, order.data(), nReg * sizeof(int32_t), cudaMemcpyHostToDevice, st));
             DpArgs a1;
@@ -846,7 +898,28 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
 
         chunkIndex++;
         size_t ev = tic(&stx.msForward);
-        if (twoPass) {
+        /* narrow chunk: no diagonal of any of its regions has more than 32 cells */
+        int narrowG = 0;
+        if (mode != CPB_MODE_FORWARD && !twoPass) {
+            int widest = 0;
+            for (int64_t r = c.region0; r < c.region1; r++) widest = std::max(widest, regs[r].maxW);
+            if (widest <= 32) narrowG = widest <= 8 ? 8 : (widest <= 16 ? 16 : 32);
+            if (getenv("CPB_NARROW") != nullptr && atoi(getenv("CPB_NARROW")) == 0) narrowG = 0;
+        }
+        NarrowArgs nargs;
+        memset(&nargs, 0, sizeof(nargs));
+        auto launch_narrow = [&](NarrowKernel k, int64_t cnt) {
+            const int64_t perCta = (int64_t) kStripWPC * (32 / narrowG);
+            const int grid = (int) std::max<int64_t>(1, std::min<int64_t>(stripGrid, (cnt + perCta - 1) / perCta));
+            nargs.nItems = (int32_t) cnt;
+            k<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, nargs);
+            stx.kernelLaunches++;
+        };
+        if (narrowG != 0) {
+            a.list = dLists + c.stripFwdOff;
+            nargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex;
+            launch_narrow(narrow_forward(narrowG), c.region1 - c.region0);
+        } else if (twoPass) {
             /* every block of the chunk recomputes its forward cells from its checkpoint */
             const int64_t nbF = c.block1 - c.block0;
             a.ckpt = b->ckpt.as<double>();
@@ -873,7 +946,11 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         const int64_t nb = c.block1 - c.block0;
         if (nb == 0) continue;
         ev = tic(&stx.msBackward);
-        {
+        if (narrowG != 0) {
+            a.list = dLists + c.stripBwdOff;
+            nargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex + 1;
+            launch_narrow(narrow_backward(narrowG), nb);
+        } else {
             a.list = dLists + c.stripBwdOff;
             sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex + 1;
             sargs.nItems = (int32_t) nb;

@@ -16,15 +16,19 @@ pytestmark = pytest.mark.gpu
 EXPECT_RTOL = 1e-9
 
 
-@pytest.fixture(autouse=True, params=["auto", "two_pass"])
+@pytest.fixture(autouse=True, params=["auto", "two_pass", "strips_only"])
 def forward_schedule(request, monkeypatch):
-    """Every test of this module runs twice: with the engine's own choice between the one-sweep forward and the checkpointed
-    two-pass forward (engine.cu; it picks two-pass only for chunked runs of long regions), and with two-pass forced, which puts
-    its block restarts through every edge case here (blocks a few diagonals long, ragged ends, splits, empty problems)."""
+    """Every test of this module runs three times: with the engine's own choices (narrow-band group kernels where every diagonal
+    has at most 16 cells, else the strip kernels; one-sweep forward unless the run is chunked and made of long regions); with the
+    checkpointed two-pass forward forced, which puts its block restarts through every edge case here (blocks a few diagonals
+    long, ragged ends, splits, empty problems); and with the narrow-band kernels switched off, so that the strip kernels also see
+    the narrow cases."""
+    monkeypatch.delenv("CPB_TWO_PASS", raising=False)
+    monkeypatch.delenv("CPB_NARROW", raising=False)
     if request.param == "two_pass":
         monkeypatch.setenv("CPB_TWO_PASS", "1")
-    else:
-        monkeypatch.delenv("CPB_TWO_PASS", raising=False)
+    if request.param == "strips_only":
+        monkeypatch.setenv("CPB_NARROW", "0")
     return request.param
 
 
