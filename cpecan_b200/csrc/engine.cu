@@ -1027,7 +1027,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             stx.kernelLaunches++;
             toc(ev);
         } else if (mode == CPB_MODE_EXPECTATIONS) {
-            const size_t smem = ((sizeof(Tables<S>) + 15) & ~size_t(15)) + (size_t) S * 16 * 32 * sizeof(double);
+            const size_t smem = ((sizeof(Tables<S>) + 15) & ~size_t(15)) + (size_t) S * 16 * EXPECT_COLS * sizeof(double);
             ev = tic(&stx.msPosterior);
             k_expect<S><<<(unsigned) nb, 32, smem, st>>>(a, *m, b->partials.as<double>());
             stx.kernelLaunches++;

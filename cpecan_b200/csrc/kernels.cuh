@@ -579,16 +579,20 @@ __global__ void k_alignment_scores(const int32_t *triples, const int64_t *pairOf
  * (diagonalCalculationExpectations / updateExpectations, impl/pairwiseAligner.c:418-438, :735-746)
  * partial[block][CPB_HMM_LEN(S)]
  * ------------------------------------------------------------------------------------------- */
+constexpr int EXPECT_SHARE = 4, EXPECT_COLS = 32 / EXPECT_SHARE;
 template <int S>
-__global__ void __launch_bounds__(32) k_expect(const DpArgs a, const CpbModel model, double *partials) {
+__global__ void __launch_bounds__(32, S == 5 ? 20 : 1) k_expect(const DpArgs a, const CpbModel model, double *partials) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     Tables<S> &tab = *reinterpret_cast<Tables<S> *>(smemRaw);
-    double *ePriv = reinterpret_cast<double *>(smemRaw + ((sizeof(Tables<S>) + 15) & ~size_t(15))); /* [S*16][32] lane-private */
+    /* emission accumulators [S*16][EXPECT_COLS]: a column is shared by EXPECT_SHARE neighbouring lanes, which add to it one after
+     * the other (fixed order, so the sums are reproducible); 5 KB instead of 20 KB per warp lets four times as many warps stay
+     * resident, and this kernel is a chain of dependent loads and exponentials that needs them */
+    double *ePriv = reinterpret_cast<double *>(smemRaw + ((sizeof(Tables<S>) + 15) & ~size_t(15)));
     const int lane = threadIdx.x;
     const BlockRec K = a.blocks[a.list[blockIdx.x]];
     const RegionDev R = a.regions[K.region];
     fill_tables<S>(tab, model, lane, 32);
-    for (int i = 0; i < S * 16; i++) ePriv[i * 32 + lane] = 0.0;
+    for (int i = lane; i < S * 16 * EXPECT_COLS; i += 32) ePriv[i] = 0.0;
     __syncwarp();
     const DiagRec *dg = a.diags + R.diagBase;
     const uint8_t *sx = a.symX + R.xBase, *sy = a.symY + R.yBase;
@@ -629,7 +633,12 @@ __global__ void __launch_bounds__(32) k_expect(const DpArgs a, const CpbModel mo
             rec2.xmyL = __shfl_sync(0xFFFFFFFFu, mine.xmyL, q);
             rec2.width = __shfl_sync(0xFFFFFFFFu, mine.width, q);
             rec2.coff = __shfl_sync(0xFFFFFFFFu, mine.coff, q);
-            if (!valid) continue;
+            double q2[S]; /* per to-state sum for the emission expectation */
+#pragma unroll
+            for (int s = 0; s < S; s++) q2[s] = 0.0;
+            bool emit = false;
+            int eIdx = 0;
+            if (valid) {
             const int d = dLow + q;
             const int i = c - (int) rec.coff;
             const bool haveM = d >= 2 && !(K.T > 0 && d == K.T + 1); /* F[d-2] was freed at the block boundary (:855) */
@@ -645,10 +654,8 @@ __global__ void __launch_bounds__(32) k_expect(const DpArgs a, const CpbModel mo
             const bool inU = xmy + 1 >= rec1.xmyL && iU < rec1.width;
             const int iM = (xmy - rec2.xmyL) >> 1;
             const bool inM = haveM && xmy >= rec2.xmyL && iM < rec2.width;
-            double q2[S]; /* per to-state sum for the emission expectation */
-#pragma unroll
-            for (int s = 0; s < S; s++) q2[s] = 0.0;
-            const bool emit = cX < 4 && cY < 4;
+            emit = cX < 4 && cY < 4;
+            eIdx = cX * 4 + cY;
             if (inL) {
 #pragma unroll
                 for (int k = 0; k < NL; k++) {
@@ -676,9 +683,13 @@ __global__ void __launch_bounds__(32) k_expect(const DpArgs a, const CpbModel mo
                     q2[t] += pr;
                 }
             }
-            if (emit) {
+            }
+            for (int ph = 0; ph < EXPECT_SHARE; ph++) {
+                if ((lane & (EXPECT_SHARE - 1)) == ph && emit) {
 #pragma unroll
-                for (int s = 0; s < S; s++) ePriv[((s * 16) + cX * 4 + cY) * 32 + lane] += q2[s];
+                    for (int s = 0; s < S; s++) ePriv[(s * 16 + eIdx) * EXPECT_COLS + lane / EXPECT_SHARE] += q2[s];
+                }
+                __syncwarp();
             }
         }
     }
@@ -703,7 +714,7 @@ __global__ void __launch_bounds__(32) k_expect(const DpArgs a, const CpbModel mo
         out[S * S + S * 16] = likelihood;
     }
     for (int i = 0; i < S * 16; i++) {
-        const double v = reduce(ePriv[i * 32 + lane]);
+        const double v = reduce(lane < EXPECT_COLS ? ePriv[i * EXPECT_COLS + lane] : 0.0);
         if (lane == 0) out[S * S + i] = v;
     }
 }
