@@ -581,7 +581,7 @@ __global__ void k_alignment_scores(const int32_t *triples, const int64_t *pairOf
  * ------------------------------------------------------------------------------------------- */
 constexpr int EXPECT_SHARE = 4, EXPECT_COLS = 32 / EXPECT_SHARE;
 template <int S>
-__global__ void __launch_bounds__(32, S == 5 ? 20 : 1) k_expect(const DpArgs a, const CpbModel model, double *partials) {
+__global__ void __launch_bounds__(32, S == 5 ? 20 : 16) k_expect(const DpArgs a, const CpbModel model, double *partials) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     Tables<S> &tab = *reinterpret_cast<Tables<S> *>(smemRaw);
     /* emission accumulators [S*16][EXPECT_COLS]: a column is shared by EXPECT_SHARE neighbouring lanes, which add to it one after
