@@ -50,7 +50,14 @@ template <> struct NarrowShape<3> {
 
 /* ---------------------------------------------------------------------------------------------
  * k_forward_narrow<S, NP, G, WPC>: one group of G lanes per region, diagonals 0 .. lX+lY.
+ * A step needs what the cells of the two previous diagonals folded for their successors; the three sets (d, d-1, d-2) and the
+ * three diagonal records in flight rotate through fixed registers, three steps per loop iteration, so nothing is copied.
  * ------------------------------------------------------------------------------------------- */
+template <int S> struct NarrowFwdSet {
+    double g[NarrowShape<S>::NG], u[NarrowShape<S>::NG], m; /* lower folds, upper folds and middle fold of this lane's cell */
+    int xmyL, w;                                            /* left edge and width of the diagonal */
+};
+
 template <int S, int NP, int G, int WPC>
 __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_narrow(const DpArgs a, const CpbModel model, const NarrowArgs na) {
     __shared__ __align__(16) StripTables<S> tab;
@@ -63,22 +70,92 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_narr
     const bool keepFull = a.auxF != 0;
 
     bool active = false, exhausted = false;
-    int d = 0, N = 0, lX = 0, lY = 0, raggedL = 0;
+    int d = 0, N = 0, lX = 0, lY = 0;
     const DiagRec *dg = nullptr;
     const uint8_t *sx = nullptr, *sy = nullptr;
     double *pf = nullptr, *aux = nullptr;
-    int xmyL1 = 0, w1 = 0, xmyL2 = 0, w2 = 0; /* left edge and width of diagonals d-1 and d-2 */
-    /* diagonal records are fetched two steps ahead and the symbols of a diagonal's cells one step ahead (records N+1, N+2 are
+    /* diagonal records are fetched three steps ahead and the symbols of a diagonal's cells one step ahead (records N+1, N+2 are
      * sentinels): nothing a step needs is a load issued in that step */
-    DiagRec cur, nx1, nx2;
-    cur.xmyL = nx1.xmyL = nx2.xmyL = 0;
-    cur.width = nx1.width = nx2.width = 0;
-    cur.coff = nx1.coff = nx2.coff = 0;
-    cur.aoff = nx1.aoff = nx2.aoff = NO_AUX;
+    DiagRec R0, R1, R2;
+    R0.xmyL = R1.xmyL = R2.xmyL = 0;
+    R0.width = R1.width = R2.width = 0;
+    R0.coff = R1.coff = R2.coff = 0;
+    R0.aoff = R1.aoff = R2.aoff = NO_AUX;
     int cXn = 4, cYn = 4; /* symbols of row x+1 and column y+1 of this lane's cell on the current diagonal */
-    double gS[NG], uS[NG], mS1 = CPB_NEG_INF, mS2 = CPB_NEG_INF; /* what this lane's cells on d-1 (gS, uS, mS1) and d-2 (mS2) folded for their successors */
+    NarrowFwdSet<S> M0, M1, M2;
+    auto clear = [&](NarrowFwdSet<S> &q) {
 #pragma unroll
-    for (int k = 0; k < NG; k++) gS[k] = uS[k] = CPB_NEG_INF;
+        for (int k = 0; k < NG; k++) q.g[k] = q.u[k] = CPB_NEG_INF;
+        q.m = CPB_NEG_INF;
+        q.xmyL = 0;
+        q.w = 0;
+    };
+    clear(M0);
+    clear(M1);
+    clear(M2);
+
+    /* one diagonal: `rec` is its record (replaced by the one three diagonals on), `recNext` the next diagonal's */
+    auto step = [&](DiagRec &rec, const DiagRec &recNext, const NarrowFwdSet<S> &in1, const NarrowFwdSet<S> &in2, NarrowFwdSet<S> &out) {
+        const int width = active ? rec.width : 0;
+        const bool valid = gl < width;
+        const int xmy = rec.xmyL + 2 * gl;
+        /* the cell: finished sums from the lower (x-1, y) and upper (x, y-1) neighbours on d-1 and the middle one (x-1, y-1) on d-2 */
+        const int iL = (xmy - 1 - in1.xmyL) >> 1, iU = iL + 1, iM = (xmy - in2.xmyL) >> 1;
+        double cell[S];
+        {
+            double g[NG], u[NG];
+#pragma unroll
+            for (int k = 0; k < NG; k++) {
+                g[k] = __shfl_sync(0xFFFFFFFFu, in1.g[k], gbase + (iL & (G - 1)));
+                u[k] = __shfl_sync(0xFFFFFFFFu, in1.u[k], gbase + (iU & (G - 1)));
+            }
+            const double m = __shfl_sync(0xFFFFFFFFu, in2.m, gbase + (iM & (G - 1)));
+            const bool okL = valid && (unsigned) iL < (unsigned) in1.w, okU = valid && (unsigned) iU < (unsigned) in1.w;
+            const bool okM = valid && (unsigned) iM < (unsigned) in2.w;
+            cell[0] = okM ? m : CPB_NEG_INF;
+#pragma unroll
+            for (int k = 0; k < NG; k++) {
+                cell[NarrowShape<S>::gap_x(k)] = okL ? g[k] : CPB_NEG_INF;
+                cell[NarrowShape<S>::gap_y(k)] = okU ? u[k] : CPB_NEG_INF;
+            }
+        }
+        if (valid) {
+            const int c = (int) rec.coff + gl;
+#pragma unroll
+            for (int k = 0; k < NP; k++) pf[(int64_t) k * a.planeStride + c] = cell[k];
+            if (keepFull && rec.aoff != NO_AUX) {
+#pragma unroll
+                for (int k = 0; k < S; k++) aux[(size_t) rec.aoff + (size_t) k * rec.width + gl] = cell[k];
+            }
+        }
+        /* fold for the successors: (x+1, y) and (x, y+1) on d+1, (x+1, y+1) on d+2 */
+        {
+            double tlD[NL], tmD[NM], tu[NU];
+            load_row<NL>(tlD, tab.tl[cXn]);
+            const double eM = tab.eM[cXn * 6 + cYn][l16], eY = tab.eY[cYn][l16];
+#pragma unroll
+            for (int k = 0; k < NM; k++) tmD[k] = eM + model.tMiddle[k];
+#pragma unroll
+            for (int k = 0; k < NU; k++) tu[k] = eY + model.tUpper[k];
+            out.m = middle_fold<S>(cell, tmD, la);
+            lower_folds<S>(out.g, cell, tlD, la);
+            upper_folds<S>(out.u, cell, tu, la);
+        }
+        out.xmyL = rec.xmyL;
+        out.w = width;
+        if (active) {
+            if (++d > N) {
+                active = false;
+            } else {
+                /* symbols for the cells of the next diagonal, and the record three diagonals on */
+                const int xmyN = recNext.xmyL + 2 * gl, xN = (d + xmyN) >> 1, yN = (d - xmyN) >> 1;
+                const bool validN = gl < recNext.width;
+                cXn = (validN && xN < lX) ? sx[xN] : 4;
+                cYn = (validN && yN < lY) ? sy[yN] : 4;
+                rec = dg[min(d + 2, N + 2)];
+            }
+        }
+    };
 
     for (;;) {
         if (!active && !exhausted) {
@@ -92,93 +169,41 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_narr
                 lX = R.lX;
                 lY = R.lY;
                 N = R.lX + R.lY;
-                raggedL = R.raggedL;
                 dg = a.diags + R.diagBase;
                 sx = a.symX + R.xBase;
                 sy = a.symY + R.yBase;
                 pf = a.planesF + R.cellBase;
                 aux = a.aux + R.auxBase;
                 d = 0;
-                w1 = w2 = 0;
                 active = true;
-                cur = dg[0];
-                nx1 = dg[1];
-                nx2 = dg[2];
+                R0 = dg[0];
+                R1 = dg[1];
+                R2 = dg[2];
                 cXn = (gl == 0 && lX > 0) ? sx[0] : 4; /* diagonal 0 is the cell (0, 0) */
                 cYn = (gl == 0 && lY > 0) ? sy[0] : 4;
+                /* The start vector (impl/pairwiseAligner.c:776-777) enters as what two imaginary diagonals would have handed to the
+                 * cell (0,0): its gap-X states from lane 0 and gap-Y states from lane 1 of a diagonal "-1" with left edge -1, its
+                 * match state from lane 0 of a diagonal "-2".  The values pass through the shuffles untouched. */
+                const double *sv = R.raggedL ? tab.rstartv : tab.startv;
+                clear(M0);
+                clear(M1);
+                clear(M2);
+#pragma unroll
+                for (int k = 0; k < NG; k++) {
+                    M2.g[k] = gl == 0 ? sv[NarrowShape<S>::gap_x(k)] : CPB_NEG_INF;
+                    M2.u[k] = gl == 1 ? sv[NarrowShape<S>::gap_y(k)] : CPB_NEG_INF;
+                }
+                M2.xmyL = -1;
+                M2.w = 2;
+                M1.m = gl == 0 ? sv[0] : CPB_NEG_INF;
+                M1.xmyL = 0;
+                M1.w = 1;
             }
         }
         if (__all_sync(0xFFFFFFFFu, !active)) break;
-        if (!active) cur.width = 0;
-        const bool valid = active && gl < cur.width;
-        const int xmy = cur.xmyL + 2 * gl;
-        /* the cell: finished sums from the lower (x-1, y) and upper (x, y-1) neighbours on d-1 and the middle one (x-1, y-1) on d-2 */
-        const int iL = (xmy - 1 - xmyL1) >> 1, iU = iL + 1, iM = (xmy - xmyL2) >> 1;
-        double out[S];
-        {
-            double g[NG], u[NG];
-#pragma unroll
-            for (int k = 0; k < NG; k++) {
-                g[k] = __shfl_sync(0xFFFFFFFFu, gS[k], gbase + (iL & (G - 1)));
-                u[k] = __shfl_sync(0xFFFFFFFFu, uS[k], gbase + (iU & (G - 1)));
-            }
-            const double m = __shfl_sync(0xFFFFFFFFu, mS2, gbase + (iM & (G - 1)));
-            const bool okL = valid && (unsigned) iL < (unsigned) w1, okU = valid && (unsigned) iU < (unsigned) w1;
-            const bool okM = valid && (unsigned) iM < (unsigned) w2;
-            out[0] = okM ? m : CPB_NEG_INF;
-#pragma unroll
-            for (int k = 0; k < NG; k++) {
-                out[NarrowShape<S>::gap_x(k)] = okL ? g[k] : CPB_NEG_INF;
-                out[NarrowShape<S>::gap_y(k)] = okU ? u[k] : CPB_NEG_INF;
-            }
-        }
-        if (d == 0 && valid) {
-            /* diagonal 0: the single cell (0,0) holds the start vector (impl/pairwiseAligner.c:776-777) */
-            const double *sv = raggedL ? tab.rstartv : tab.startv;
-#pragma unroll
-            for (int k = 0; k < S; k++) out[k] = sv[k];
-        }
-        if (valid) {
-            const int cell = (int) cur.coff + gl;
-#pragma unroll
-            for (int k = 0; k < NP; k++) pf[(int64_t) k * a.planeStride + cell] = out[k];
-            if (keepFull && cur.aoff != NO_AUX) {
-#pragma unroll
-                for (int k = 0; k < S; k++) aux[(size_t) cur.aoff + (size_t) k * cur.width + gl] = out[k];
-            }
-        }
-        /* fold for the successors: (x+1, y) and (x, y+1) on d+1, (x+1, y+1) on d+2 */
-        {
-            double tlD[NL], tmD[NM], tu[NU];
-            load_row<NL>(tlD, tab.tl[cXn]);
-            const double eM = tab.eM[cXn * 6 + cYn][l16], eY = tab.eY[cYn][l16];
-#pragma unroll
-            for (int k = 0; k < NM; k++) tmD[k] = eM + model.tMiddle[k];
-#pragma unroll
-            for (int k = 0; k < NU; k++) tu[k] = eY + model.tUpper[k];
-            mS2 = mS1;
-            mS1 = middle_fold<S>(out, tmD, la);
-            lower_folds<S>(gS, out, tlD, la);
-            upper_folds<S>(uS, out, tu, la);
-        }
-        xmyL2 = xmyL1;
-        w2 = w1;
-        xmyL1 = cur.xmyL;
-        w1 = active ? cur.width : 0;
-        if (active) {
-            if (++d > N) {
-                active = false;
-            } else {
-                cur = nx1;
-                nx1 = nx2;
-                nx2 = dg[min(d + 2, N + 2)];
-                /* symbols for the cells of the diagonal just made current */
-                const int xmyN = cur.xmyL + 2 * gl, xN = (d + xmyN) >> 1, yN = (d - xmyN) >> 1;
-                const bool validN = gl < cur.width;
-                cXn = (validN && xN < lX) ? sx[xN] : 4;
-                cYn = (validN && yN < lY) ? sy[yN] : 4;
-            }
-        }
+        step(R0, R1, M2, M1, M0);
+        step(R1, R2, M0, M2, M1);
+        step(R2, R0, M1, M0, M2);
     }
 }
 
