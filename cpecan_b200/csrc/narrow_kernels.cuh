@@ -211,6 +211,11 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_narr
  * k_backward_narrow<S, NP, ZSUM, G, WPC>: one group of G lanes per traceback block, diagonals top .. T+1, gather form
  * (cell_backward).  ZSUM: the planes written are F + B per state; otherwise raw B (expectations).
  * ------------------------------------------------------------------------------------------- */
+template <int S> struct NarrowBwdSet {
+    double b[S];  /* backward states of this lane's cell */
+    int xmyL, w;  /* left edge and width of the diagonal */
+};
+
 template <int S, int NP, bool ZSUM, int G, int WPC>
 __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_backward_narrow(const DpArgs a, const CpbModel model, const NarrowArgs na) {
     __shared__ __align__(16) StripTables<S> tab;
@@ -230,19 +235,116 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_backward_nar
     const uint8_t *sx = nullptr, *sy = nullptr;
     const double *pf = nullptr;
     double *pb = nullptr, *aux = nullptr;
-    int xmyL1 = 0, w1 = 0, xmyL2 = 0, w2 = 0; /* diagonals d+1 and d+2 */
-    DiagRec cur, nxt, nx2; /* d, d-1, d-2: fetched ahead, like the symbols and F values of the next diagonal's cells */
-    cur.xmyL = nxt.xmyL = nx2.xmyL = 0;
-    cur.width = nxt.width = nx2.width = 0;
-    cur.coff = nxt.coff = nx2.coff = 0;
-    cur.aoff = nxt.aoff = nx2.aoff = NO_AUX;
+    /* records of d, d-1, d-2 in flight; the symbols and F values of a diagonal's cells are fetched one step ahead */
+    DiagRec R0, R1, R2;
+    R0.xmyL = R1.xmyL = R2.xmyL = 0;
+    R0.width = R1.width = R2.width = 0;
+    R0.coff = R1.coff = R2.coff = 0;
+    R0.aoff = R1.aoff = R2.aoff = NO_AUX;
     int cXn = 4, cYn = 4;
     double fNext[NFM];
 #pragma unroll
     for (int k = 0; k < NFM; k++) fNext[k] = 0.0;
-    double b1[S], m2 = CPB_NEG_INF;           /* this lane's cell on d+1, and B.M of its cell on d+2 */
+    NarrowBwdSet<S> B0, B1, B2; /* the cells of d, d+1, d+2, rotating through fixed registers (three steps per loop iteration) */
+    auto clear = [&](NarrowBwdSet<S> &q) {
 #pragma unroll
-    for (int k = 0; k < S; k++) b1[k] = CPB_NEG_INF;
+        for (int k = 0; k < S; k++) q.b[k] = CPB_NEG_INF;
+        q.xmyL = 0;
+        q.w = 0;
+    };
+    clear(B0);
+    clear(B1);
+    clear(B2);
+
+    /* one diagonal: `rec` is its record (replaced by the one three diagonals down), `recNext` the record of d-1 */
+    auto step = [&](DiagRec &rec, const DiagRec &recNext, const NarrowBwdSet<S> &in1, const NarrowBwdSet<S> &in2, NarrowBwdSet<S> &out) {
+        const int width = active ? rec.width : 0;
+        const bool valid = gl < width;
+        const int xmy = rec.xmyL + 2 * gl;
+        /* (x, y+1) and (x+1, y) on d+1, (x+1, y+1) on d+2 */
+        const int iA = (xmy - 1 - in1.xmyL) >> 1, iB = iA + 1, iM = (xmy - in2.xmyL) >> 1;
+        double cell[S];
+        {
+            double u[S], l[NG];
+#pragma unroll
+            for (int k = 0; k < S; k++) u[k] = CPB_NEG_INF;
+            const bool okA = valid && (unsigned) iA < (unsigned) in1.w, okB = valid && (unsigned) iB < (unsigned) in1.w;
+            const bool okM = valid && (unsigned) iM < (unsigned) in2.w;
+#pragma unroll
+            for (int k = 0; k < NG; k++) {
+                const double vu = __shfl_sync(0xFFFFFFFFu, in1.b[NarrowShape<S>::gap_y(k)], gbase + (iA & (G - 1)));
+                const double vl = __shfl_sync(0xFFFFFFFFu, in1.b[NarrowShape<S>::gap_x(k)], gbase + (iB & (G - 1)));
+                u[NarrowShape<S>::gap_y(k)] = okA ? vu : CPB_NEG_INF;
+                l[k] = okB ? vl : CPB_NEG_INF;
+            }
+            const double vm = __shfl_sync(0xFFFFFFFFu, in2.b[0], gbase + (iM & (G - 1)));
+            const double t2m = okM ? vm : CPB_NEG_INF;
+            double tl[NL], tm[NM], tu[NU];
+            load_row<NL>(tl, tab.tl[cXn]);
+            const double eM = tab.eM[cXn * 6 + cYn][l16], eY = tab.eY[cYn][l16];
+#pragma unroll
+            for (int k = 0; k < NM; k++) tm[k] = eM + model.tMiddle[k];
+#pragma unroll
+            for (int k = 0; k < NU; k++) tu[k] = eY + model.tUpper[k];
+            cell_backward<S>(cell, t2m, u, l, tm, tu, tl, la);
+        }
+        if (d == top) {
+            /* the block's top diagonal holds the end vector (impl/pairwiseAligner.c:798-799) */
+#pragma unroll
+            for (int k = 0; k < S; k++) cell[k] = valid ? endVec[k] : CPB_NEG_INF;
+        }
+        if (valid) {
+            const int c = (int) rec.coff + gl;
+            double fm[NFM];
+#pragma unroll
+            for (int k = 0; k < NFM; k++) fm[k] = fNext[k];
+            const bool owned = d <= from;
+            const bool feeds = d - 1 > T && d - 1 <= from && recNext.aoff != NO_AUX; /* d-1 is a total diagonal */
+            double f0 = fm[0];
+            if (!ZSUM && feeds) f0 = pf[c];
+            if (owned) {
+#pragma unroll
+                for (int k = 0; k < NP; k++) pb[(int64_t) k * a.planeStride + c] = ZSUM ? fm[k] + cell[k] : cell[k];
+                if (rec.aoff != NO_AUX) {
+                    /* cell_dotProduct(F[d], B[d]) (impl/pairwiseAligner.c:402-408); folded over the cells by k_totals */
+                    double f[S];
+                    if (nF != 0) {
+#pragma unroll
+                        for (int k = 0; k < S; k++) f[k] = aux[(size_t) rec.aoff + (size_t) k * rec.width + gl];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < S; k++) f[k] = pf[(int64_t) k * a.planeStride + c];
+                    }
+                    double t = f[0] + cell[0];
+#pragma unroll
+                    for (int k = 1; k < S; k++) t = log_add(t, f[k] + cell[k], la);
+                    aux[(size_t) rec.aoff + (size_t) nF * rec.width + gl] = t;
+                }
+            }
+            /* diagonal d-1 is a total diagonal: its second term is the fold of F[d].M + B[d].M (:643-651) */
+            if (feeds) aux[(size_t) recNext.aoff + (size_t) (nF + 1) * recNext.width + gl] = f0 + cell[0];
+        }
+#pragma unroll
+        for (int k = 0; k < S; k++) out.b[k] = cell[k];
+        out.xmyL = rec.xmyL;
+        out.w = width;
+        if (active) {
+            if (--d <= T) {
+                active = false;
+            } else {
+                /* symbols and F values for the cells of the next diagonal, and the record three diagonals down */
+                const int xmyN = recNext.xmyL + 2 * gl, xN = (d + xmyN) >> 1, yN = (d - xmyN) >> 1;
+                const bool validN = gl < recNext.width;
+                cXn = (validN && xN < lX) ? sx[xN] : 4;
+                cYn = (validN && yN < lY) ? sy[yN] : 4;
+                if (ZSUM && NP > 0 && validN) {
+#pragma unroll
+                    for (int k = 0; k < NFM; k++) fNext[k] = pf[(int64_t) k * a.planeStride + (int) recNext.coff + gl];
+                }
+                rec = dg[d >= 2 ? d - 2 : 0];
+            }
+        }
+    };
 
     for (;;) {
         if (!active && !exhausted) {
@@ -267,112 +369,27 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_backward_nar
                 pb = a.planesB + R.cellBase;
                 aux = a.aux + R.auxBase;
                 d = top;
-                w1 = w2 = 0;
                 active = d > T;
-                cur = dg[d];
-                nxt = dg[d - 1]; /* d - 1 >= T >= 0 */
-                nx2 = dg[d >= 2 ? d - 2 : 0];
-                const int xmy0 = cur.xmyL + 2 * gl, x0 = (d + xmy0) >> 1, y0 = (d - xmy0) >> 1;
-                const bool valid0 = gl < cur.width;
+                R0 = dg[d];
+                R1 = dg[d - 1]; /* d - 1 >= T >= 0 */
+                R2 = dg[d >= 2 ? d - 2 : 0];
+                clear(B0);
+                clear(B1);
+                clear(B2);
+                const int xmy0 = R0.xmyL + 2 * gl, x0 = (d + xmy0) >> 1, y0 = (d - xmy0) >> 1;
+                const bool valid0 = gl < R0.width;
                 cXn = (valid0 && x0 < lX) ? sx[x0] : 4;
                 cYn = (valid0 && y0 < lY) ? sy[y0] : 4;
                 if (ZSUM && NP > 0 && valid0) {
 #pragma unroll
-                    for (int k = 0; k < NFM; k++) fNext[k] = pf[(int64_t) k * a.planeStride + (int) cur.coff + gl];
+                    for (int k = 0; k < NFM; k++) fNext[k] = pf[(int64_t) k * a.planeStride + (int) R0.coff + gl];
                 }
             }
         }
         if (__all_sync(0xFFFFFFFFu, !active)) break;
-        if (!active) cur.width = 0;
-        const bool valid = active && gl < cur.width;
-        const int xmy = cur.xmyL + 2 * gl;
-        /* (x, y+1) and (x+1, y) on d+1, (x+1, y+1) on d+2 */
-        const int iA = (xmy - 1 - xmyL1) >> 1, iB = iA + 1, iM = (xmy - xmyL2) >> 1;
-        double out[S];
-        {
-            double u[S], l[NG];
-#pragma unroll
-            for (int k = 0; k < S; k++) u[k] = CPB_NEG_INF;
-            const bool okA = valid && (unsigned) iA < (unsigned) w1, okB = valid && (unsigned) iB < (unsigned) w1;
-            const bool okM = valid && (unsigned) iM < (unsigned) w2;
-#pragma unroll
-            for (int k = 0; k < NG; k++) {
-                const double vu = __shfl_sync(0xFFFFFFFFu, b1[NarrowShape<S>::gap_y(k)], gbase + (iA & (G - 1)));
-                const double vl = __shfl_sync(0xFFFFFFFFu, b1[NarrowShape<S>::gap_x(k)], gbase + (iB & (G - 1)));
-                u[NarrowShape<S>::gap_y(k)] = okA ? vu : CPB_NEG_INF;
-                l[k] = okB ? vl : CPB_NEG_INF;
-            }
-            const double vm = __shfl_sync(0xFFFFFFFFu, m2, gbase + (iM & (G - 1)));
-            const double t2m = okM ? vm : CPB_NEG_INF;
-            double tl[NL], tm[NM], tu[NU];
-            load_row<NL>(tl, tab.tl[cXn]);
-            const double eM = tab.eM[cXn * 6 + cYn][l16], eY = tab.eY[cYn][l16];
-#pragma unroll
-            for (int k = 0; k < NM; k++) tm[k] = eM + model.tMiddle[k];
-#pragma unroll
-            for (int k = 0; k < NU; k++) tu[k] = eY + model.tUpper[k];
-            cell_backward<S>(out, t2m, u, l, tm, tu, tl, la);
-        }
-        if (d == top) {
-            /* the block's top diagonal holds the end vector (impl/pairwiseAligner.c:798-799) */
-#pragma unroll
-            for (int k = 0; k < S; k++) out[k] = valid ? endVec[k] : CPB_NEG_INF;
-        }
-        if (valid) {
-            const int cell = (int) cur.coff + gl;
-            double fm[NFM];
-#pragma unroll
-            for (int k = 0; k < NFM; k++) fm[k] = fNext[k];
-            const bool owned = d <= from;
-            const bool feeds = d - 1 > T && d - 1 <= from && nxt.aoff != NO_AUX; /* d-1 is a total diagonal */
-            double f0 = fm[0];
-            if (!ZSUM && feeds) f0 = pf[cell];
-            if (owned) {
-#pragma unroll
-                for (int k = 0; k < NP; k++) pb[(int64_t) k * a.planeStride + cell] = ZSUM ? fm[k] + out[k] : out[k];
-                if (cur.aoff != NO_AUX) {
-                    /* cell_dotProduct(F[d], B[d]) (impl/pairwiseAligner.c:402-408); folded over the cells by k_totals */
-                    double f[S];
-                    if (nF != 0) {
-#pragma unroll
-                        for (int k = 0; k < S; k++) f[k] = aux[(size_t) cur.aoff + (size_t) k * cur.width + gl];
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < S; k++) f[k] = pf[(int64_t) k * a.planeStride + cell];
-                    }
-                    double t = f[0] + out[0];
-#pragma unroll
-                    for (int k = 1; k < S; k++) t = log_add(t, f[k] + out[k], la);
-                    aux[(size_t) cur.aoff + (size_t) nF * cur.width + gl] = t;
-                }
-            }
-            /* diagonal d-1 is a total diagonal: its second term is the fold of F[d].M + B[d].M (:643-651) */
-            if (feeds) aux[(size_t) nxt.aoff + (size_t) (nF + 1) * nxt.width + gl] = f0 + out[0];
-        }
-        m2 = b1[0];
-#pragma unroll
-        for (int k = 0; k < S; k++) b1[k] = out[k];
-        xmyL2 = xmyL1;
-        w2 = w1;
-        xmyL1 = cur.xmyL;
-        w1 = active ? cur.width : 0;
-        if (active) {
-            if (--d <= T) {
-                active = false;
-            } else {
-                cur = nxt;
-                nxt = nx2;
-                nx2 = dg[d >= 2 ? d - 2 : 0];
-                const int xmyN = cur.xmyL + 2 * gl, xN = (d + xmyN) >> 1, yN = (d - xmyN) >> 1;
-                const bool validN = gl < cur.width;
-                cXn = (validN && xN < lX) ? sx[xN] : 4;
-                cYn = (validN && yN < lY) ? sy[yN] : 4;
-                if (ZSUM && NP > 0 && validN) {
-#pragma unroll
-                    for (int k = 0; k < NFM; k++) fNext[k] = pf[(int64_t) k * a.planeStride + (int) cur.coff + gl];
-                }
-            }
-        }
+        step(R0, R1, B2, B1, B0);
+        step(R1, R2, B0, B2, B1);
+        step(R2, R0, B1, B0, B2);
     }
 }
 
