@@ -353,6 +353,7 @@ __device__ __forceinline__ bool posterior_keep(double z, double total, const Pos
 
 template <bool WRITE>
 __global__ void __launch_bounds__(32 * POST_WARPS) k_posterior(const DpArgs a, const PostArgs p) {
+    __shared__ int sCoff[POST_WARPS][12], sXmyL[POST_WARPS][12]; /* WRITE: the current decade's diagonal records, per warp */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const BlockRec K = a.blocks[a.list[blockIdx.x]];
     const RegionDev R = a.regions[K.region];
@@ -420,29 +421,46 @@ __global__ void __launch_bounds__(32 * POST_WARPS) k_posterior(const DpArgs a, c
                 for (int o = 16; o > 0; o >>= 1) struck += __shfl_xor_sync(0xFFFFFFFFu, struck, o);
                 if (lane == 0) p.counts[(int64_t) l * p.nDecades + g] = cnt - struck;
             } else {
+                /* Kept cells are rare (about one per diagonal): every lane takes one 32-cell mask word of the decade, a warp scan gives
+                 * each word its place in the output, and the lane writes out its own word's few set bits.  The decade's records sit in
+                 * shared memory so that this per-lane loop needs no warp-wide operation. */
                 int64_t run = p.offsets[(int64_t) l * p.nDecades + g];
-                const unsigned ltMask = (1u << lane) - 1u;
-                for (int64_t C = cA; C < c1; C += 32) {
-                    const unsigned m = masks[C >> 5];
-                    if (m == 0) continue; /* warp-uniform */
-                    const int64_t cell = C + lane;
-                    /* the diagonal of the cell: the last of the decade's diagonals that starts at or before it */
-                    int k = -1;
-                    for (int q = 0; q < nd; q++) k += (cell >= R.cellBase + (int64_t) __shfl_sync(0xFFFFFFFFu, mine.coff, q)) ? 1 : 0;
-                    k = max(k, 0);
-                    const int64_t coffK = R.cellBase + (int64_t) __shfl_sync(0xFFFFFFFFu, mine.coff, k);
-                    const int xmyLK = __shfl_sync(0xFFFFFFFFu, mine.xmyL, k);
-                    if ((m >> lane) & 1u) {
+                __syncwarp();
+                if (lane < nd) {
+                    sCoff[warp][lane] = (int) mine.coff;
+                    sXmyL[warp][lane] = mine.xmyL;
+                }
+                __syncwarp();
+                const int64_t nWords = (c1 - cA + 31) >> 5;
+                for (int64_t wb = 0; wb < nWords; wb += 32) {
+                    const int64_t wi = wb + lane;
+                    unsigned m = wi < nWords ? masks[(cA >> 5) + wi] : 0u;
+                    const int cnt = __popc(m);
+                    int incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    int64_t pos = run + incl - cnt;
+                    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    while (m != 0) {
+                        const int bit = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int64_t cell = cA + (wi << 5) + bit;
+                        /* the diagonal of the cell: the last of the decade's diagonals that starts at or before it */
+                        int k = 0;
+                        for (int q = 1; q < nd; q++) k = cell >= R.cellBase + sCoff[warp][q] ? q : k;
                         const int d = dLow + k;
-                        const int x = ((d + xmyLK) >> 1) + (int) (cell - coffK), y = d - x;
+                        const int x = ((d + sXmyL[warp][k]) >> 1) + (int) (cell - R.cellBase - sCoff[warp][k]), y = d - x;
                         int pInt = 0;
                         posterior_keep(plane[cell], total, p, pInt);
-                        int32_t *o = p.out[l] + 3 * (run + __popc(m & ltMask));
+                        int32_t *o = p.out[l] + 3 * pos;
                         o[0] = pInt;
                         o[1] = x - 1 + R.ox;
                         o[2] = y - 1 + R.oy;
+                        pos++;
                     }
-                    run += __popc(m);
                 }
             }
         }
