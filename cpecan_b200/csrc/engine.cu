@@ -112,6 +112,58 @@ struct DevBuf {
 };
 
 /* ------------------------------------------------------------------------------------------------ */
+/* page-locked host buffers handed out to batches (anchor staging) and taken back when the batch goes: pinning costs milliseconds per
+ * 100 MB, so the buffers are kept */
+struct PinnedPool {
+    struct Item {
+        void *p;
+        size_t cap;
+        bool inUse;
+    };
+    std::vector<Item> items;
+    void *take(size_t bytes) {
+        for (auto &it : items) {
+            if (!it.inUse && it.cap >= bytes) {
+                it.inUse = true;
+                return it.p;
+            }
+        }
+        for (auto &it : items) { /* grow an idle one rather than keep both */
+            if (!it.inUse) {
+                cudaFreeHost(it.p);
+                it.p = nullptr;
+                if (cudaHostAlloc(&it.p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+                    (void) cudaGetLastError();
+                    it.p = nullptr;
+                    it.cap = 0;
+                    return nullptr;
+                }
+                it.cap = bytes;
+                it.inUse = true;
+                return it.p;
+            }
+        }
+        Item it = { nullptr, bytes, true };
+        if (cudaHostAlloc(&it.p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+            (void) cudaGetLastError();
+            return nullptr;
+        }
+        items.push_back(it);
+        return it.p;
+    }
+    void give(void *p) {
+        for (auto &it : items) {
+            if (it.p == p) it.inUse = false;
+        }
+    }
+    void drain() {
+        for (auto &it : items) {
+            if (it.p) cudaFreeHost(it.p);
+        }
+        items.clear();
+    }
+};
+
 struct cpb_context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -121,6 +173,7 @@ struct cpb_context {
     DevBuf boundary, counters, negRecord, progress; /* strip engine: per-warp-slot boundary rings, work-fetch counters, one LOG_ZERO ring record */
     int smCount = 148;
     DevPool pool;              /* buffers handed back by destroyed batches */
+    PinnedPool pinned;         /* page-locked host staging, same idea */
 };
 
 static const int kStripWPC = 4; /* warps per CTA of the strip kernels */
@@ -191,6 +244,7 @@ extern "C" void cpb_context_destroy(cpb_context *ctx) {
     ctx->negRecord.release();
     ctx->progress.release();
     ctx->pool.drain();
+    ctx->pinned.drain();
     ctx->counters.release();
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -214,7 +268,9 @@ struct Chunk {
 struct cpb_batch {
     cpb_context *ctx = nullptr;
     int64_t n = 0;
-    std::vector<int64_t> xOff, yOff, aOff, anchors;
+    std::vector<int64_t> xOff, yOff, aOff;
+    int32_t *anchors = nullptr;      /* host copy of the anchor triples as the device has them (page-locked, from ctx->pinned) */
+    std::vector<int32_t> anchorsOwn; /* fallback if page-locked memory cannot be had */
     std::vector<uint8_t> rl, rr;
     DevBuf symX, symY, dAnchors;
     /* run state */
@@ -253,7 +309,6 @@ extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *se
     if (anchorOff != nullptr) b->aOff.assign(anchorOff, anchorOff + nPairs + 1);
     else b->aOff.assign(nPairs + 1, 0);
     const int64_t nA = b->aOff[nPairs];
-    if (nA > 0) b->anchors.assign(anchors, anchors + 3 * nA);
     b->rl.assign(nPairs, 0);
     b->rr.assign(nPairs, 0);
     if (raggedLeft) b->rl.assign(raggedLeft, raggedLeft + nPairs);
@@ -280,10 +335,27 @@ extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *se
         k_encode<<<(unsigned) ((ny + 255) / 256), 256, 0, st>>>(b->symY.as<uint8_t>() + kSymPad, ny);
     }
     if (nA > 0) {
-        std::vector<int32_t> a32(3 * nA);
-        for (int64_t i = 0; i < 3 * nA; i++) a32[i] = (int32_t) anchors[i];
-        CUDA_TRY(cudaMemcpyAsync(b->dAnchors.p, a32.data(), a32.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaStreamSynchronize(st)); /* a32 is a temporary */
+        /* int64 triples of the caller -> int32 triples, straight into a page-locked buffer that serves both the copy to the device
+         * and the host-side region construction of every run; a few host threads share the conversion */
+        const size_t bytes = (size_t) (3 * nA) * sizeof(int32_t);
+        b->anchors = static_cast<int32_t *>(ctx->pinned.take(bytes));
+        if (b->anchors == nullptr) {
+            b->anchorsOwn.resize((size_t) (3 * nA));
+            b->anchors = b->anchorsOwn.data();
+        }
+        int32_t *dst = b->anchors;
+        auto convert = [&](int64_t i0, int64_t i1) {
+            for (int64_t i = i0; i < i1; i++) dst[i] = (int32_t) anchors[i];
+        };
+        const int64_t total = 3 * nA, nThreads = std::max<int64_t>(1, std::min<int64_t>({ (int64_t) std::thread::hardware_concurrency(), (int64_t) 8, total >> 20 }));
+        if (nThreads <= 1) {
+            convert(0, total);
+        } else {
+            std::vector<std::thread> pool;
+            for (int64_t t = 0; t < nThreads; t++) pool.emplace_back(convert, total * t / nThreads, total * (t + 1) / nThreads);
+            for (auto &t : pool) t.join();
+        }
+        CUDA_TRY(cudaMemcpyAsync(b->dAnchors.p, b->anchors, bytes, cudaMemcpyHostToDevice, st));
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
@@ -298,12 +370,47 @@ extern "C" void cpb_batch_destroy(cpb_batch *b) {
                        &b->offsets, &b->masks, &b->tileSums, &b->pairCounts, &b->partials, &b->pairBlockOff, &b->perPair, &b->hmmTotal, &b->forwardOut, &b->out[0], &b->out[1],
                        &b->out[2], &b->ckRegions, &b->ckDiags, &b->ckSizes, &b->ckpt };
     for (DevBuf *d : bufs) d->release();
+    if (b->anchors != nullptr && b->anchorsOwn.empty()) b->ctx->pinned.give(b->anchors);
     delete b;
 }
 
 /* ------------------------------------------------------------------------------------------------
  * region construction on the host
  * ---------------------------------------------------------------------------------------------- */
+/* cpb_split_points (model.c; getSplitPoints, impl/pairwiseAligner.c:1230-1257) over the int32 triples the batch keeps */
+static int64_t split_points32(const int32_t *anchors, int64_t nAnchors, int64_t lX, int64_t lY, int64_t splitBiggerThan, int raggedLeft,
+                              int raggedRight, int64_t *out4, int64_t cap) {
+    int64_t n = 0;
+    auto sink = [&](int64_t x1, int64_t y1, int64_t x2, int64_t y2) {
+        if (n < cap) {
+            out4[4 * n] = x1;
+            out4[4 * n + 1] = y1;
+            out4[4 * n + 2] = x2;
+            out4[4 * n + 3] = y2;
+        }
+        n++;
+    };
+    const int64_t half = (int64_t) sqrt((double) splitBiggerThan);
+    int64_t openX = 0, openY = 0, prevX = 0, prevY = 0; /* start of the region being grown; one past the previous anchor */
+    int lastGapSplit = 0;
+    for (int64_t i = 0; i <= nAnchors; i++) {
+        const int64_t nextX = i < nAnchors ? anchors[3 * i] : lX, nextY = i < nAnchors ? anchors[3 * i + 1] : lY;
+        const int64_t gapX = nextX - prevX, gapY = nextY - prevY;
+        lastGapSplit = 0;
+        if (gapX * gapY > splitBiggerThan) {
+            const int64_t hX = gapX / 2 > half ? half : gapX / 2, hY = gapY / 2 > half ? half : gapY / 2;
+            if (!(raggedLeft && i == 0)) sink(openX, openY, prevX + hX, prevY + hY); /* a ragged left end drops the region before the first anchor */
+            openX = nextX - hX;
+            openY = nextY - hY;
+            lastGapSplit = 1;
+        }
+        prevX = nextX + 1;
+        prevY = nextY + 1;
+    }
+    if (!lastGapSplit || !raggedRight) sink(openX, openY, lX, lY); /* a ragged right end drops the region after a trailing split */
+    return n;
+}
+
 static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
     /* Pairs are independent: the split points and region records of every pair are made by a pool of host threads (this is a scan over
      * all anchors, ~1 ms per 300 k anchors per thread), then one serial pass assigns the offsets into the device arrays. */
@@ -314,16 +421,16 @@ static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
         for (int64_t i = i0; i < i1; i++) {
             const int64_t lX = b->xOff[i + 1] - b->xOff[i], lY = b->yOff[i + 1] - b->yOff[i];
             const int64_t a0 = b->aOff[i], nA = b->aOff[i + 1] - a0;
-            const int64_t *an = b->anchors.data() + 3 * a0;
+            const int32_t *an = b->anchors + 3 * a0;
             int64_t nReg = 1;
             if (mode == CPB_MODE_FORWARD) {
                 split.assign({ 0, 0, lX, lY });
             } else {
                 split.resize(4 * 4);
-                nReg = cpb_split_points(an, nA, lX, lY, p->splitMatrixBiggerThanThis, b->rl[i], b->rr[i], split.data(), 4);
+                nReg = split_points32(an, nA, lX, lY, p->splitMatrixBiggerThanThis, b->rl[i], b->rr[i], split.data(), 4);
                 if (nReg > 4) {
                     split.resize(4 * nReg);
-                    nReg = cpb_split_points(an, nA, lX, lY, p->splitMatrixBiggerThanThis, b->rl[i], b->rr[i], split.data(), nReg);
+                    nReg = split_points32(an, nA, lX, lY, p->splitMatrixBiggerThanThis, b->rl[i], b->rr[i], split.data(), nReg);
                 }
             }
             std::vector<RegionDev> &out = perPair[(size_t) i];
