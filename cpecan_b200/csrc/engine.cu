@@ -221,7 +221,11 @@ extern "C" int cpb_context_create(int device, void *stream, cpb_context **out) {
     int rc = configure_kernels();
     if (rc == CPB_OK && (rc = ctx->negRecord.reserve(BND_REC * sizeof(double))) == CPB_OK) {
         double neg[BND_REC];
+#ifdef CPB_FINITE_LOG_ZERO
+        for (int i = 0; i < BND_REC; i++) neg[i] = -1e290; /* the kernels' LOG_ZERO stand-in (kernels.cuh) */
+#else
         for (int i = 0; i < BND_REC; i++) neg[i] = -INFINITY;
+#endif
         if (cudaMemcpy(ctx->negRecord.p, neg, sizeof(neg), cudaMemcpyHostToDevice) != cudaSuccess) {
             cpb_set_error("cudaMemcpy failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = CPB_ERR_CUDA;
@@ -535,6 +539,21 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     cudaStream_t st = ctx->stream;
     CpbRunStats &stx = b->stats;
     memset(&stx, 0, sizeof(stx));
+#ifdef CPB_FINITE_LOG_ZERO
+    /* log(0) entries of the model (start / end vectors, impossible transitions of a loaded Hmm) become the kernels' finite stand-in */
+    CpbModel finiteModel = *m;
+    {
+        double *groups[] = { finiteModel.start, finiteModel.raggedStart, finiteModel.end, finiteModel.raggedEnd, finiteModel.tLower, finiteModel.tMiddle,
+                             finiteModel.tUpper, finiteModel.eMatch, finiteModel.eGapX, finiteModel.eGapY };
+        const int sizes[] = { 5, 5, 5, 5, 4, 5, 4, 25, 5, 5 };
+        for (int g = 0; g < 10; g++) {
+            for (int i = 0; i < sizes[g]; i++) {
+                if (!(groups[g][i] > -1e290)) groups[g][i] = -1e290;
+            }
+        }
+    }
+    m = &finiteModel;
+#endif
     stx.nPairs = b->n;
     std::vector<EventPair> events;
     auto tic = [&](double *sink) {

@@ -118,6 +118,9 @@ struct DpArgs {
 /* ---------------------------------------------------------------------------------------------
  * logAdd, bit-compatible with impl/pairwiseAligner.c:290-307
  * ------------------------------------------------------------------------------------------- */
+#ifndef CPB_TRUE_LOG_ZERO
+#define CPB_FINITE_LOG_ZERO 1 /* default; -DCPB_TRUE_LOG_ZERO builds the kernels with -infinity as LOG_ZERO and the three-select logAdd */
+#endif
 /* the reference's 4-segment cubic, [segment][a,b,c,k]; the literals are floats promoted to double exactly as in C */
 __constant__ double c_coefficients[16] = {
     (double) -0.009350833524763f, (double) 0.130659527668286f, (double) 0.498799810682272f, (double) 0.693203116424741f,
@@ -132,7 +135,11 @@ __constant__ double c_coefficients[16] = {
  * maps the clamped bucket to its coefficients: rows 0-9: (1, 2.5]; rows 10-16: (2.5, 4.5]; rows 17-23: above 4.5 (the
  * polynomial is discarded from 7.5 on); row 24: d <= 1 (and, harmlessly, everything at or beyond the cut-off).
  */
+#ifdef CPB_FINITE_LOG_ZERO
+constexpr int LA_ROWS = 26; /* one more row of zeros: the "polynomial" at and beyond the cut-off */
+#else
 constexpr int LA_ROWS = 25;
+#endif
 /* Shared-memory layout of the table: two planes ({a,b} and {c,k}) of LA_ROWS rows; every row is replicated for the
  * 8 lanes of a quarter warp (8 x 16 bytes = all 32 banks), so a 128-bit fetch never has a bank conflict whatever
  * rows the lanes pick. */
@@ -143,8 +150,13 @@ constexpr int LA_TABLE_DOUBLES = 2 * LA_PLANE_DOUBLES;    /* 6400 bytes */
 __device__ __forceinline__ void fill_logadd_rows(double *la, int tid, int nthreads) {
     for (int i = tid; i < LA_TABLE_DOUBLES; i += nthreads) {
         const int plane = i / LA_PLANE_DOUBLES, r = (i % LA_PLANE_DOUBLES) / LA_ROW_DOUBLES, e = i & 1;
+#ifdef CPB_FINITE_LOG_ZERO
+        const int seg = r == 24 ? 0 : (r <= 9 ? 1 : (r <= 16 ? 2 : 3));
+        la[i] = r == 25 ? 0.0 : c_coefficients[4 * seg + 2 * plane + e];
+#else
         const int seg = r == LA_ROWS - 1 ? 0 : (r <= 9 ? 1 : (r <= 16 ? 2 : 3));
         la[i] = c_coefficients[4 * seg + 2 * plane + e];
+#endif
     }
 }
 /* the calling lane's view of the table: the shared-memory byte address of its own 16-byte column */
@@ -156,6 +168,32 @@ __device__ __forceinline__ LaTable logadd_lane_table(const double *la) {
 #ifdef CPB_LA_STATS
 __device__ unsigned long long g_laStats[4]; /* warp-level calls, calls where every active lane is at or beyond the cut-off, lane calls, lane cut-offs */
 #endif
+#ifdef CPB_FINITE_LOG_ZERO
+/*
+ * Inside the kernels LOG_ZERO is the finite stand-in CPB_NEG_INF = -1e290 (see below): under this logAdd it behaves exactly as
+ * -infinity does under the reference's (a term that far below the other operand is dropped, two of them give one of them back, sums
+ * with finite terms stay "that far below"), and no infinity or NaN can reach the arithmetic.  That buys a cheaper operand selection:
+ * beyond the cut-off the coefficient row is all zeros, so the polynomial is exactly 0 and the result is p + t with
+ * t = the smaller operand (near) or the larger one (far) -- one 64-bit select instead of three.
+ */
+__device__ __forceinline__ double log_add(double x, double y, const LaTable la) {
+    const double diff = __dsub_rn(x, y);
+    const double d = fabs(diff);
+    const bool far = !(d < 7.5);
+    const bool pickX = (__double2hiint(diff) < 0) != far; /* near: x if it is the smaller; far: x if it is the larger */
+    const int hi3 = __double2hiint(__dadd_rd(d, -4.9406564584124654e-324)); /* predecessor of d, see above */
+    unsigned r = min((unsigned) ((hi3 >> 17) - 0x1FF8), 24u);
+    r = far ? 25u : r;
+    double a, b, c, k;
+    asm("ld.shared.v2.f64 {%0, %1}, [%4];\n\tld.shared.v2.f64 {%2, %3}, [%4+%5];"
+        : "=d"(a), "=d"(b), "=d"(c), "=d"(k)
+        : "r"(la + (unsigned) (LA_ROW_DOUBLES * 8) * r), "n"(LA_PLANE_DOUBLES * 8));
+    double p = __dadd_rn(__dmul_rn(a, d), b);
+    p = __dadd_rn(__dmul_rn(p, d), c);
+    p = __dadd_rn(__dmul_rn(p, d), k);
+    return __dadd_rn(p, pickX ? x : y);
+}
+#else
 __device__ __forceinline__ double log_add(double x, double y, const LaTable la) {
     const double diff = __dsub_rn(x, y);
 #ifdef CPB_LA_STATS
@@ -191,8 +229,16 @@ __device__ __forceinline__ double log_add(double x, double y, const LaTable la) 
     /* d >= 7.5, d = +inf (one side is LOG_ZERO) and d = NaN (both are) all return the larger operand */
     return d < 7.5 ? p : big;
 }
+#endif
 
-#define CPB_NEG_INF (__longlong_as_double(0xFFF0000000000000LL))
+#define CPB_TRUE_NEG_INF (__longlong_as_double(0xFFF0000000000000LL))
+#ifdef CPB_FINITE_LOG_ZERO
+#define CPB_NEG_INF (-1e290)            /* LOG_ZERO inside the kernels: tables, initial states, band masks, planes */
+#define CPB_IS_LOG_ZERO(v) (!((v) > -1e280)) /* anything that low is "log of zero" (sums of stand-ins included) */
+#else
+#define CPB_NEG_INF CPB_TRUE_NEG_INF
+#define CPB_IS_LOG_ZERO(v) (false)
+#endif
 
 #ifndef CPB_STRIP_MIN_BLOCKS
 #define CPB_STRIP_MIN_BLOCKS 4 /* resident CTAs per SM the strip kernels are compiled for (register budget) */
@@ -364,6 +410,7 @@ __global__ void __launch_bounds__(32 * POST_WARPS) k_posterior(const DpArgs a, c
         const int dt = K.from - 10 * j;                       /* the decade's total diagonal (its highest) */
         const int64_t g = K.decadeBase + (nDecades - 1 - j);  /* ascending-diagonal numbering */
         const double total = tot[dt];
+        const bool alive = !CPB_IS_LOG_ZERO(total); /* no path through the decade: the reference's p is NaN there and nothing is kept */
         const int dLow = max(dt - 9, K.T + 1), nd = dt - dLow + 1;
         /* lane k < nd holds diagonal dLow + k */
         DiagRec mine;
@@ -392,7 +439,7 @@ __global__ void __launch_bounds__(32 * POST_WARPS) k_posterior(const DpArgs a, c
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         int pInt;
-                        const unsigned m = __ballot_sync(0xFFFFFFFFu, valid[u] && posterior_keep(z[u], total, p, pInt));
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, valid[u] && alive && posterior_keep(z[u], total, p, pInt));
                         if (C + 32 * u < c1) {
                             if (lane == 0) masks[(C >> 5) + u] = m;
                             cnt += __popc(m);
@@ -629,7 +676,10 @@ __global__ void __launch_bounds__(32, S == 5 ? 20 : 16) k_expect(const DpArgs a,
     for (int j = 0; j < nDecades; j++) {
         const int dt = K.from - 10 * j, dLow = max(dt - 9, K.T + 1), nd = dt - dLow + 1;
         const double total = tot[dt];
-        for (int q = 0; q < nd; q++) likelihood += total; /* once per diagonal (impl/pairwiseAligner.c:743), highest first */
+        for (int q = 0; q < nd; q++) likelihood += CPB_IS_LOG_ZERO(total) ? CPB_TRUE_NEG_INF : total; /* once per diagonal (impl/pairwiseAligner.c:743), highest first */
+        /* No path through the decade (the band forces a transition the model forbids): the reference computes exp(-inf - -inf) = NaN for
+         * every term it adds there, and so do we */
+        const double minusTotal = CPB_IS_LOG_ZERO(total) ? __longlong_as_double(0x7FF8000000000000LL) : -total;
         DiagRec mine = dg[max(dLow - 2 + min(lane, nd + 1), 0)]; /* lane r: diagonal dLow - 2 + r */
         const int c0 = (int) __shfl_sync(0xFFFFFFFFu, mine.coff, 2);
         const int c1 = (int) (__shfl_sync(0xFFFFFFFFu, mine.coff, nd + 1) + __shfl_sync(0xFFFFFFFFu, (uint32_t) mine.width, nd + 1));
@@ -678,7 +728,7 @@ __global__ void __launch_bounds__(32, S == 5 ? 20 : 16) k_expect(const DpArgs a,
 #pragma unroll
                 for (int k = 0; k < NL; k++) {
                     const int f = lower_from<S>(k), t = lower_to<S>(k);
-                    const double pr = exp(pf[(int64_t) f * a.planeStride + rec1.coff + iL] + b[t] + tab.tl[cX][k] - total);
+                    const double pr = exp(pf[(int64_t) f * a.planeStride + rec1.coff + iL] + b[t] + tab.tl[cX][k] + minusTotal);
                     accT[k] += pr;
                     q2[t] += pr;
                 }
@@ -687,7 +737,7 @@ __global__ void __launch_bounds__(32, S == 5 ? 20 : 16) k_expect(const DpArgs a,
 #pragma unroll
                 for (int k = 0; k < NM; k++) {
                     const int f = middle_from<S>(k);
-                    const double pr = exp(pf[(int64_t) f * a.planeStride + rec2.coff + iM] + b[0] + tab.tm[cX * 5 + cY][k] - total);
+                    const double pr = exp(pf[(int64_t) f * a.planeStride + rec2.coff + iM] + b[0] + tab.tm[cX * 5 + cY][k] + minusTotal);
                     accT[NL + k] += pr;
                     q2[0] += pr;
                 }
@@ -696,7 +746,7 @@ __global__ void __launch_bounds__(32, S == 5 ? 20 : 16) k_expect(const DpArgs a,
 #pragma unroll
                 for (int k = 0; k < NU; k++) {
                     const int f = upper_from<S>(k), t = upper_to<S>(k);
-                    const double pr = exp(pf[(int64_t) f * a.planeStride + rec1.coff + iU] + b[t] + tab.tu[cY][k] - total);
+                    const double pr = exp(pf[(int64_t) f * a.planeStride + rec1.coff + iU] + b[t] + tab.tu[cY][k] + minusTotal);
                     accT[NL + NM + k] += pr;
                     q2[t] += pr;
                 }

@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_stri
                 double v = own[0] + ev[0];
 #pragma unroll
                 for (int k = 1; k < S; k++) v = log_add(v, own[k] + ev[k], la);
-                a.forwardOut[regionId] = v;
+                a.forwardOut[regionId] = CPB_IS_LOG_ZERO(v) ? CPB_TRUE_NEG_INF : v;
             }
             __syncwarp();
         }

@@ -457,3 +457,43 @@ def test_device_reweighting_and_alignment_scores(ctx):
         d = float(before[off[i]:off[i + 1], 0].astype(np.int64).sum()) / (max(1, min(len(sx), len(sy))) * 1e7)
         assert scores[i] == int(min(max(d, 0.0), 1.0) * 1e7)
     b.close()
+
+
+@pytest.mark.parametrize("type_", [cp.fiveState, cp.fiveStateAsymmetric, cp.threeState, cp.threeStateAsymmetric])
+def test_models_with_impossible_transitions_and_emissions(ctx, oracle, type_):
+    """An Hmm with zero probabilities has log(0) = LOG_ZERO in its state machine (impl/stateMachine.c:529-620).  Inside the kernels
+    LOG_ZERO is a finite stand-in (kernels.cuh, CPB_FINITE_LOG_ZERO); it has to behave exactly as the reference's -infinity:
+    same pair sets, forward log-probabilities bit for bit, expectations."""
+    rng = np.random.default_rng(900 + type_)
+    S = 5 if type_ < 2 else 3
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    p.minDiagsBetweenTraceBack = 80
+    for rep in range(3):
+        t = rng.random((S, S)) + 0.01
+        e = rng.random((S, 16)) + 0.01
+        if S == 5:
+            t[0, 3] = t[0, 4] = 0.0          # the long-gap states cannot be entered from match ...
+            if rep > 0:
+                t[3, 3] = t[4, 4] = 0.0      # ... nor extended
+        else:
+            t[1, 2] = t[2, 1] = 0.0          # no gap switches
+        if rep == 2:
+            e[0, 5] = e[0, 10] = 0.0         # c/c and g/g never emitted by the match state
+        t /= t.sum(1, keepdims=True)
+        e /= e.sum(1, keepdims=True)
+        spec = helpers.ModelSpec(type_, t, e)
+        cases = small_cases(rng, 12, 140, ragged=rep == 1)
+        check_aligned_pairs(ctx, oracle, spec, p, cases, "zero-probability model type %d rep %d" % (type_, rep))
+        b = run_batch(ctx, spec, p, cases, cp.MODE_EXPECTATIONS)
+        pp, _ = b.fetch_expectations()
+        b.close()
+        unanchored = [(c[0], c[1], np.zeros((0, 3), dtype=np.int64), c[3], c[4]) for c in cases]
+        b = run_batch(ctx, spec, p, unanchored, cp.MODE_FORWARD)
+        fw = b.fetch_forward()
+        b.close()
+        for i, c in enumerate(cases):
+            want = oracle.expectations(spec.orc(), helpers.orc_params_from(p), c[0], c[1], c[2], c[3], c[4])
+            np.testing.assert_allclose(pp[i], want, rtol=EXPECT_RTOL, atol=1e-12, err_msg="case %d" % i)
+            u = unanchored[i]
+            wf = oracle.forward_prob(spec.orc(), helpers.orc_params_from(p), u[0], u[1], u[2], u[3], u[4])
+            assert float(fw[i]).hex() == float(wf).hex(), "forward log-probability case %d: %r vs %r" % (i, fw[i], wf)
