@@ -338,3 +338,40 @@ int main(int argc, char **argv) {
     assert out[3] == "cigar: seq2 30 10 - seq1 100 125 + 0.000000 M 10 I 5 M 5 D 10"
     assert out[4:7] == ["seq [one first record] 8 ACGTACGT", "seq [two] 0 ", "seq [three\tx] 8 NNNNacgt"]
     assert out[7] == "rc YacgtNACGT"
+
+
+LIB_DIR = os.path.dirname(HOST_SO)
+
+
+def test_programs_print_their_options_without_a_gpu():
+    for exe, needle in (("cPecanRealign", "--outputExpectations"), ("cPecanEm", "--trainEmissions")):
+        out = subprocess.run([os.path.join(LIB_DIR, exe), "--help"], capture_output=True, text=True)
+        assert out.returncode == 0 and needle in out.stderr, exe
+
+
+def test_programs_fail_loudly_without_a_gpu(tmp_path):
+    """no CPU implementation of the DP behind the command line either: without a CUDA device the programs abort with the engine's message"""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    fa = tmp_path / "s.fa"
+    fa.write_text(">a\nACGTACGTAC\n>b\nACGTTCGTAC\n")
+    cig = "cigar: b 0 10 + a 0 10 + 0 M 10\n"
+    for exe, args in (("cPecanRealign", []), ("cPecanEm", ["--iterations", "1", "--outputModel", str(tmp_path / "m.hmm")])):
+        out = subprocess.run([os.path.join(LIB_DIR, exe)] + args + [str(fa)], input=cig, capture_output=True, text=True)
+        assert out.returncode != 0, exe
+        assert "CUDA" in out.stderr or "no CPU implementation" in out.stderr, out.stderr
+
+
+def test_malformed_input_is_an_error(tmp_path):
+    """sonLib's convention: print a message and exit (st_errAbort), never a silent partial result"""
+    fa = tmp_path / "s.fa"
+    fa.write_text(">a\nACGTACGTAC\n>b\nACGTTCGTAC\n")
+    exe = os.path.join(LIB_DIR, "cPecanRealign")
+    for cig, needle in (("cigar: b 0 10 + a 0 10 + 0 M 9\n", "operations cover"),      # lengths do not add up
+                        ("cigar: b 0 10 + a 0 10 + 0 Q 10\n", "operation 'Q'"),        # unknown operation
+                        ("cigar: b 0 10 + a 0 10\n", "leading fields"),                # truncated line
+                        ("cigar: b 0 10 + a 0 40 + 0 M 10 D 30\n", "beyond the end")): # past the end of the sequence
+        out = subprocess.run([exe, str(fa)], input=cig, capture_output=True, text=True)
+        assert out.returncode != 0 and needle in out.stderr, (cig, out.stderr)
