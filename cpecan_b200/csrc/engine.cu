@@ -17,6 +17,7 @@
 #include <cstring>
 #include <string>
 #include <chrono>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -109,6 +110,17 @@ struct DevBuf {
         cap = 0;
     }
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+    void adopt(DevBuf &other) { /* takes over other's allocation; this buffer must be empty */
+        p = other.p;
+        cap = other.cap;
+        pool = other.pool;
+        other.p = nullptr;
+        other.cap = 0;
+    }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); } /* local buffers on error paths; owners that release explicitly leave nothing to do here */
 };
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -276,6 +288,7 @@ struct cpb_batch {
     int32_t *anchors = nullptr;      /* host copy of the anchor triples as the device has them (page-locked, from ctx->pinned) */
     std::vector<int32_t> anchorsOwn; /* fallback if page-locked memory cannot be had */
     std::vector<uint8_t> rl, rr;
+    int64_t oddExpansionPair = -1;   /* first pair with an odd anchor expansion: only an error for runs with dynamicAnchorExpansion (:166) */
     DevBuf symX, symY, dAnchors;
     /* run state */
     DevBuf strips;
@@ -297,10 +310,35 @@ extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *se
         cpb_set_error("cpb_batch_create: bad argument");
         return CPB_ERR_ARGUMENT;
     }
+    /* The kernels trust these arrays (region lengths and anchor coordinates are int32 on the device, the band builder's bisection
+     * relies on x + y growing by at least 2 per anchor): everything the reference states as asserts (impl/pairwiseAligner.c:214-219)
+     * is checked here, once, and reported with the index of the offending pair. */
+    if (xOff[0] != 0 || yOff[0] != 0 || (anchorOff != nullptr && anchorOff[0] != 0)) {
+        cpb_set_error("cpb_batch_create: offset arrays must start at 0");
+        return CPB_ERR_ARGUMENT;
+    }
+    for (int64_t i = 0; i < nPairs; i++) {
+        const int64_t lX = xOff[i + 1] - xOff[i], lY = yOff[i + 1] - yOff[i], nAi = anchorOff != nullptr ? anchorOff[i + 1] - anchorOff[i] : 0;
+        if (lX < 0 || lY < 0 || nAi < 0 || lX + lY > (int64_t) 0x7FFFFF00) {
+            cpb_set_error("cpb_batch_create: pair %lld: offsets are not non-decreasing, or the sequences are too long (lengths %lld, %lld, %lld anchors)",
+                          (long long) i, (long long) lX, (long long) lY, (long long) nAi);
+            return CPB_ERR_ARGUMENT;
+        }
+    }
+    if ((xOff[nPairs] > 0 && seqX == nullptr) || (yOff[nPairs] > 0 && seqY == nullptr) || (anchorOff != nullptr && anchorOff[nPairs] > 0 && anchors == nullptr)) {
+        cpb_set_error("cpb_batch_create: a sequence or anchor array is NULL although its offsets say it is not empty");
+        return CPB_ERR_ARGUMENT;
+    }
     *out = nullptr;
     CUDA_TRY(cudaSetDevice(ctx->device));
     cpb_batch *b = new cpb_batch();
     b->ctx = ctx;
+    struct Guard { /* every early return below frees the batch, its device buffers and its page-locked anchor buffer */
+        cpb_batch *b;
+        ~Guard() {
+            if (b != nullptr) cpb_batch_destroy(b);
+        }
+    } guard{ b };
     {
         DevBuf *all[] = { &b->strips, &b->symX, &b->symY, &b->dAnchors, &b->regions, &b->diags, &b->blocks, &b->totals, &b->lists, &b->counts, &b->offsets,
                           &b->masks, &b->tileSums, &b->pairCounts, &b->partials, &b->pairBlockOff, &b->perPair, &b->hmmTotal, &b->forwardOut, &b->out[0],
@@ -323,10 +361,8 @@ extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *se
     int rc = CPB_OK;
     /* the strip kernels index symbols up to 32 positions outside a region without bounds tests: pad both ends with 'n' */
     if ((rc = b->symX.reserve(nx + 2 * kSymPad)) != CPB_OK || (rc = b->symY.reserve(ny + 2 * kSymPad)) != CPB_OK ||
-        (rc = b->dAnchors.reserve(std::max<int64_t>(nA, 1) * 3 * sizeof(int32_t))) != CPB_OK) {
-        cpb_batch_destroy(b);
+        (rc = b->dAnchors.reserve(std::max<int64_t>(nA, 1) * 3 * sizeof(int32_t))) != CPB_OK)
         return rc;
-    }
     cudaStream_t st = ctx->stream;
     CUDA_TRY(cudaMemsetAsync(b->symX.p, 4, nx + 2 * kSymPad, st));
     CUDA_TRY(cudaMemsetAsync(b->symY.p, 4, ny + 2 * kSymPad, st));
@@ -348,21 +384,57 @@ extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *se
             b->anchors = b->anchorsOwn.data();
         }
         int32_t *dst = b->anchors;
-        auto convert = [&](int64_t i0, int64_t i1) {
-            for (int64_t i = i0; i < i1; i++) dst[i] = (int32_t) anchors[i];
+        /* conversion and validation in one pass over the triples, pairs dealt to a few host threads in contiguous ranges */
+        std::atomic<int64_t> badPair{ -1 }, oddPair{ -1 };
+        auto convert = [&](int64_t p0, int64_t p1) {
+            for (int64_t i = p0; i < p1; i++) {
+                const int64_t lX = b->xOff[i + 1] - b->xOff[i], lY = b->yOff[i + 1] - b->yOff[i];
+                int64_t px = -1, py = -1;
+                bool ok = true, even = true;
+                for (int64_t k = b->aOff[i]; k < b->aOff[i + 1]; k++) {
+                    const int64_t x = anchors[3 * k], y = anchors[3 * k + 1], e = anchors[3 * k + 2];
+                    ok &= x > px && y > py && x < lX && y < lY && e >= 0 && e <= 0x7FFFFFFF;
+                    even &= (e & 1) == 0;
+                    px = x;
+                    py = y;
+                    dst[3 * k] = (int32_t) x;
+                    dst[3 * k + 1] = (int32_t) y;
+                    dst[3 * k + 2] = (int32_t) e;
+                }
+                int64_t expect = -1;
+                if (!ok) badPair.compare_exchange_strong(expect, i);
+                expect = -1;
+                if (!even) oddPair.compare_exchange_strong(expect, i);
+            }
         };
-        const int64_t total = 3 * nA, nThreads = std::max<int64_t>(1, std::min<int64_t>({ (int64_t) std::thread::hardware_concurrency(), (int64_t) 8, total >> 20 }));
+        const int64_t nThreads = std::max<int64_t>(1, std::min<int64_t>({ (int64_t) std::thread::hardware_concurrency(), (int64_t) 8, (3 * nA) >> 20, nPairs }));
         if (nThreads <= 1) {
-            convert(0, total);
+            convert(0, nPairs);
         } else {
+            /* ranges of pairs holding about the same number of anchors */
             std::vector<std::thread> pool;
-            for (int64_t t = 0; t < nThreads; t++) pool.emplace_back(convert, total * t / nThreads, total * (t + 1) / nThreads);
+            int64_t p0 = 0;
+            for (int64_t t = 0; t < nThreads; t++) {
+                const int64_t want = nA * (t + 1) / nThreads;
+                int64_t p1 = t + 1 == nThreads ? nPairs : (int64_t) (std::upper_bound(b->aOff.begin(), b->aOff.end(), want) - b->aOff.begin()) - 1;
+                p1 = std::max(p0, std::min(p1, nPairs));
+                pool.emplace_back(convert, p0, p1);
+                p0 = p1;
+            }
             for (auto &t : pool) t.join();
+        }
+        b->oddExpansionPair = oddPair.load();
+        if (badPair.load() >= 0) {
+            cpb_set_error("cpb_batch_create: pair %lld: anchors must be (x, y, expansion) with 0 <= x < lX, 0 <= y < lY, x and y strictly increasing and "
+                          "expansion >= 0 (impl/pairwiseAligner.c:214-219)",
+                          (long long) badPair.load());
+            return CPB_ERR_ARGUMENT;
         }
         CUDA_TRY(cudaMemcpyAsync(b->dAnchors.p, b->anchors, bytes, cudaMemcpyHostToDevice, st));
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
+    guard.b = nullptr;
     *out = b;
     return CPB_OK;
 }
@@ -555,7 +627,16 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     m = &finiteModel;
 #endif
     stx.nPairs = b->n;
-    std::vector<EventPair> events;
+    struct EventList { /* an early error return destroys the events that finish_events() has not collected */
+        std::vector<EventPair> v;
+        ~EventList() {
+            for (auto &e : v) {
+                cudaEventDestroy(e.a);
+                cudaEventDestroy(e.b);
+            }
+        }
+    } eventList;
+    std::vector<EventPair> &events = eventList.v;
     auto tic = [&](double *sink) {
         EventPair e;
         cudaEventCreate(&e.a);
@@ -858,7 +939,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     };
     StripArgs sargs;
     memset(&sargs, 0, sizeof(sargs));
-    int stripGrid = 1, teamGrid = 1;
+    int stripGrid = 1, teamGrid = 1, fwdGrid = 1, bwdGrid = 1; /* stripGrid = the larger of the two: sizes the rings */
     {
         int maxRange = 1;
         for (int64_t r = 0; r < nReg; r++) maxRange = std::max(maxRange, regs[r].maxStripRange);
@@ -868,8 +949,10 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occF, kFwdStrip, 32 * kStripWPC, 0));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, kBwdStrip, 32 * kStripWPC, 0));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, kFwdTeam, 32 * kStripWPC, 0));
-        stripGrid = ctx->smCount * std::max(1, std::max(occF, occB));
-        teamGrid = ctx->smCount * std::max(1, std::min(occT, std::max(occF, occB))); /* every team CTA must be resident: teams spin on each other */
+        fwdGrid = ctx->smCount * std::max(1, occF);
+        bwdGrid = ctx->smCount * std::max(1, occB);
+        stripGrid = std::max(fwdGrid, bwdGrid);
+        teamGrid = ctx->smCount * std::max(1, std::min(occT, occF)); /* every team CTA must be resident: teams spin on each other */
         if ((rc = ctx->progress.reserve((size_t) stripGrid * kStripWPC * sizeof(unsigned long long))) != CPB_OK) return rc;
         sargs.progress = ctx->progress.as<unsigned long long>();
         const size_t need = (size_t) stripGrid * kStripWPC * 2 * ring * BND_REC * sizeof(double);
@@ -901,7 +984,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             cudaMemsetAsync(ctx->progress.p, 0, (size_t) grid * kStripWPC * sizeof(unsigned long long), st);
             teamed<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
         } else {
-            const int grid = (int) std::min<int64_t>(stripGrid, (cnt + kStripWPC - 1) / kStripWPC);
+            const int grid = (int) std::min<int64_t>(fwdGrid, (cnt + kStripWPC - 1) / kStripWPC);
             sargs.teamSize = 1;
             plain<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
         }
@@ -1053,7 +1136,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex;
             sargs.nItems = (int32_t) nbF;
             sargs.teamSize = 1;
-            const int grid = (int) std::min<int64_t>(stripGrid, (nbF + kStripWPC - 1) / kStripWPC);
+            const int grid = (int) std::min<int64_t>(fwdGrid, (nbF + kStripWPC - 1) / kStripWPC);
             kFwdBlocks<<<std::max(grid, 1), 32 * kStripWPC, 0, st>>>(a, *m, sargs);
             stx.kernelLaunches++;
         } else {
@@ -1080,7 +1163,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             a.list = dLists + c.stripBwdOff;
             sargs.counter = ctx->counters.as<unsigned int>() + 2 * chunkIndex + 1;
             sargs.nItems = (int32_t) nb;
-            const int grid = (int) std::min<int64_t>(stripGrid, (nb + kStripWPC - 1) / kStripWPC);
+            const int grid = (int) std::min<int64_t>(bwdGrid, (nb + kStripWPC - 1) / kStripWPC);
             kBwdStrip<<<grid, 32 * kStripWPC, 0, st>>>(a, *m, sargs);
             stx.kernelLaunches++;
         }
@@ -1143,7 +1226,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
                         CUDA_TRY(cudaMemcpyAsync(bigger.p, b->out[l].p, (size_t) running[l] * 3 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
                     CUDA_TRY(cudaStreamSynchronize(st));
                     b->out[l].release();
-                    b->out[l] = bigger;
+                    b->out[l].adopt(bigger);
                 }
                 pa.out[l] = b->out[l].as<int32_t>();
                 running[l] = newTotals[l];
@@ -1208,6 +1291,11 @@ extern "C" int cpb_batch_run(cpb_batch *b, const CpbModel *m, const CpbParams *p
     }
     int rc = check_params(p);
     if (rc != CPB_OK) return rc;
+    if (p->dynamicAnchorExpansion && mode != CPB_MODE_FORWARD && b->oddExpansionPair >= 0) {
+        cpb_set_error("pair %lld: with dynamicAnchorExpansion every anchor's expansion must be even (impl/pairwiseAligner.c:166)",
+                      (long long) b->oddExpansionPair);
+        return CPB_ERR_ARGUMENT;
+    }
     CUDA_TRY(cudaSetDevice(b->ctx->device));
     if (m->stateNumber == 5) return run_impl<5>(b, m, p, mode);
     if (m->stateNumber == 3) return run_impl<3>(b, m, p, mode);

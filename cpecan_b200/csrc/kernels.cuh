@@ -135,6 +135,34 @@ __constant__ double c_coefficients[16] = {
  * maps the clamped bucket to its coefficients: rows 0-9: (1, 2.5]; rows 10-16: (2.5, 4.5]; rows 17-23: above 4.5 (the
  * polynomial is discarded from 7.5 on); row 24: d <= 1 (and, harmlessly, everything at or beyond the cut-off).
  */
+#if defined(CPB_FINITE_LOG_ZERO) && !defined(CPB_LA_REPLICATED)
+#define CPB_LA_COMPACT 1 /* default: the five-row table below; -DCPB_LA_REPLICATED builds the per-bucket, lane-replicated table */
+#endif
+#ifdef CPB_LA_COMPACT
+/*
+ * Compact table: five rows only -- the four segments and a row of zeros (the "polynomial" at and beyond the cut-off) -- in two
+ * planes ({a,b} and {c,k}) of 128 bytes.  The rows of a plane lie in five different groups of four banks, so whatever rows the 32
+ * lanes pick, a 128-bit fetch touches every bank with at most one address: one shared-memory wavefront per fetch (lanes that pick
+ * the same row are served by broadcast), against four for a table with a row per lane.  The bucket -> row map is a 64-bit constant
+ * of 2-bit fields, pre-shifted so that (MAP >> 2*bucket) & 0x30 is the row's byte offset.
+ */
+constexpr int LA_PLANE_DOUBLES = 16;                      /* 128 bytes: rows at 0, 16, 32, 48 (segments) and 64 (zeros) */
+constexpr int LA_TABLE_DOUBLES = 2 * LA_PLANE_DOUBLES;
+constexpr unsigned LA_ZERO_ROW = 64;
+__host__ __device__ constexpr unsigned long long la_bucket_map() {
+    unsigned long long m = 0;
+    for (int r = 0; r < 24; r++) m |= (unsigned long long) (r <= 9 ? 1 : (r <= 16 ? 2 : 3)) << (2 * r + 4);
+    return m;
+}
+__device__ __forceinline__ void fill_logadd_rows(double *la, int tid, int nthreads) {
+    for (int i = tid; i < LA_TABLE_DOUBLES; i += nthreads) {
+        const int plane = i / LA_PLANE_DOUBLES, row = (i % LA_PLANE_DOUBLES) / 2, e = i & 1;
+        la[i] = row < 4 ? c_coefficients[4 * row + 2 * plane + e] : 0.0;
+    }
+}
+typedef unsigned LaTable;
+__device__ __forceinline__ LaTable logadd_lane_table(const double *la) { return (unsigned) __cvta_generic_to_shared(la); /* 128-byte aligned */ }
+#else
 #ifdef CPB_FINITE_LOG_ZERO
 constexpr int LA_ROWS = 26; /* one more row of zeros: the "polynomial" at and beyond the cut-off */
 #else
@@ -164,6 +192,7 @@ typedef unsigned LaTable;
 __device__ __forceinline__ LaTable logadd_lane_table(const double *la) {
     return (unsigned) __cvta_generic_to_shared(la) + 16u * (threadIdx.x & 7);
 }
+#endif
 
 #ifdef CPB_LA_STATS
 __device__ unsigned long long g_laStats[4]; /* warp-level calls, calls where every active lane is at or beyond the cut-off, lane calls, lane cut-offs */
@@ -176,6 +205,30 @@ __device__ unsigned long long g_laStats[4]; /* warp-level calls, calls where eve
  * beyond the cut-off the coefficient row is all zeros, so the polynomial is exactly 0 and the result is p + t with
  * t = the smaller operand (near) or the larger one (far) -- one 64-bit select instead of three.
  */
+#ifdef CPB_LA_COMPACT
+__device__ __forceinline__ double log_add(double x, double y, const LaTable la) {
+    const double diff = __dsub_rn(x, y);
+    const double d = fabs(diff);
+    const bool far = !(d < 7.5);
+    const bool pickX = (__double2hiint(diff) < 0) != far; /* near: x if it is the smaller; far: x if it is the larger */
+    const int hi3 = __double2hiint(__dadd_rd(d, -4.9406564584124654e-324)); /* predecessor of d, see above */
+    /* bucket = (hi3 >> 17) - 0x1FF8; below 0 (d <= 1) and from 24 on (beyond the cut-off anyway) the shift leaves no field: row 0 */
+    int bucket; /* kept opaque so that the doubling below stays one multiply-add (FMA pipe) instead of a shift, a mask and an add (ALU pipe) */
+    asm("shr.s32 %0, %1, 17;" : "=r"(bucket) : "r"(hi3));
+    const unsigned sh = (unsigned) (bucket * 2 - 2 * 0x1FF8);
+    unsigned long long f;
+    asm("shr.u64 %0, %1, %2;" : "=l"(f) : "l"(la_bucket_map()), "r"(sh)); /* PTX clamps the shift amount at 64 */
+    const unsigned row = far ? la + LA_ZERO_ROW : (((unsigned) f & 0x30u) | la);
+    double a, b, c, k;
+    asm("ld.shared.v2.f64 {%0, %1}, [%4];\n\tld.shared.v2.f64 {%2, %3}, [%4+%5];"
+        : "=d"(a), "=d"(b), "=d"(c), "=d"(k)
+        : "r"(row), "n"(LA_PLANE_DOUBLES * 8));
+    double p = __dadd_rn(__dmul_rn(a, d), b);
+    p = __dadd_rn(__dmul_rn(p, d), c);
+    p = __dadd_rn(__dmul_rn(p, d), k);
+    return __dadd_rn(p, pickX ? x : y);
+}
+#else
 __device__ __forceinline__ double log_add(double x, double y, const LaTable la) {
     const double diff = __dsub_rn(x, y);
     const double d = fabs(diff);
@@ -193,6 +246,7 @@ __device__ __forceinline__ double log_add(double x, double y, const LaTable la) 
     p = __dadd_rn(__dmul_rn(p, d), k);
     return __dadd_rn(p, pickX ? x : y);
 }
+#endif
 #else
 __device__ __forceinline__ double log_add(double x, double y, const LaTable la) {
     const double diff = __dsub_rn(x, y);
@@ -241,7 +295,13 @@ __device__ __forceinline__ double log_add(double x, double y, const LaTable la) 
 #endif
 
 #ifndef CPB_STRIP_MIN_BLOCKS
-#define CPB_STRIP_MIN_BLOCKS 4 /* resident CTAs per SM the strip kernels are compiled for (register budget) */
+#define CPB_STRIP_MIN_BLOCKS 4 /* resident CTAs per SM the wavefront kernels are compiled for (register budget) */
+#endif
+#ifndef CPB_FWD_MIN_BLOCKS
+#define CPB_FWD_MIN_BLOCKS CPB_STRIP_MIN_BLOCKS
+#endif
+#ifndef CPB_BWD_MIN_BLOCKS
+#define CPB_BWD_MIN_BLOCKS CPB_STRIP_MIN_BLOCKS
 #endif
 
 /* ---------------------------------------------------------------------------------------------
@@ -329,7 +389,7 @@ __global__ void k_ckpt_mark(const BlockRec *blocks, const RegionDev *regions, Di
  * cells of the diagonal (dpDiagonal_dotProduct, :513-523), so lanes run independent folds in parallel.
  * ------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(128) k_totals(const DpArgs a, int nBlocks) {
-    __shared__ __align__(16) double laTable[LA_TABLE_DOUBLES];
+    __shared__ __align__(128) double laTable[LA_TABLE_DOUBLES];
     fill_logadd_rows(laTable, threadIdx.x, blockDim.x);
     __syncthreads();
     const LaTable ctab = logadd_lane_table(laTable);

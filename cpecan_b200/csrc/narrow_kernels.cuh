@@ -60,7 +60,7 @@ template <int S> struct NarrowFwdSet {
 
 template <int S, int NP, int G, int WPC>
 __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_narrow(const DpArgs a, const CpbModel model, const NarrowArgs na) {
-    __shared__ __align__(16) StripTables<S> tab;
+    __shared__ __align__(128) StripTables<S> tab;
     fill_strip_tables<S>(tab, model, threadIdx.x, 32 * WPC);
     __syncthreads();
     constexpr int NG = NarrowShape<S>::NG, NL = Shape<S>::NL, NM = Shape<S>::NM, NU = Shape<S>::NU;
@@ -218,7 +218,7 @@ template <int S> struct NarrowBwdSet {
 
 template <int S, int NP, bool ZSUM, int G, int WPC>
 __global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_backward_narrow(const DpArgs a, const CpbModel model, const NarrowArgs na) {
-    __shared__ __align__(16) StripTables<S> tab;
+    __shared__ __align__(128) StripTables<S> tab;
     fill_strip_tables<S>(tab, model, threadIdx.x, 32 * WPC);
     __syncthreads();
     constexpr int NG = NarrowShape<S>::NG, NL = Shape<S>::NL, NM = Shape<S>::NM, NU = Shape<S>::NU;

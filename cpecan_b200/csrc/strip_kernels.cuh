@@ -194,9 +194,9 @@ template <int S> __device__ __forceinline__ void lower_folds(double *g, const do
  *              Long regions then offer as many work items as they have blocks, instead of one.
  * ------------------------------------------------------------------------------------------- */
 template <int S, int NP, int WPC, int MODE>
-__global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_forward_strip(const DpArgs a, const CpbModel model, const StripArgs sa) {
+__global__ void __launch_bounds__(32 * WPC, CPB_FWD_MIN_BLOCKS) k_forward_strip(const DpArgs a, const CpbModel model, const StripArgs sa) {
     constexpr bool TEAM = MODE == FWD_TEAMS, BLOCKS = MODE == FWD_BLOCKS;
-    __shared__ __align__(16) StripTables<S> tab;
+    __shared__ __align__(128) StripTables<S> tab;
     fill_strip_tables<S>(tab, model, threadIdx.x, 32 * WPC);
     __syncthreads();
     constexpr int NSH = Msg<S>::N, NL = Shape<S>::NL, NM = Shape<S>::NM, NU = Shape<S>::NU;
@@ -530,8 +530,8 @@ __device__ __forceinline__ void cell_backward(double *out, double t2m, const dou
 }
 
 template <int S, int NP, bool ZSUM, int WPC>
-__global__ void __launch_bounds__(32 * WPC, CPB_STRIP_MIN_BLOCKS) k_backward_strip(const DpArgs a, const CpbModel model, const StripArgs sa) {
-    __shared__ __align__(16) StripTables<S> tab;
+__global__ void __launch_bounds__(32 * WPC, CPB_BWD_MIN_BLOCKS) k_backward_strip(const DpArgs a, const CpbModel model, const StripArgs sa) {
+    __shared__ __align__(128) StripTables<S> tab;
     fill_strip_tables<S>(tab, model, threadIdx.x, 32 * WPC);
     __syncthreads();
     constexpr int NSH = Msg<S>::N, NL = Shape<S>::NL, NM = Shape<S>::NM, NU = Shape<S>::NU;

@@ -110,6 +110,52 @@ Symbol symbol_convertCharToSymbol(char i);
 char symbol_convertSymbolToChar(Symbol i);
 Symbol *symbol_convertStringToSymbols(const char *s, int64_t sL);
 
+/* :167 -- the reference's log-space addition: 4-segment cubic with float-literal coefficients, cut-off at 7.5
+ * (impl/pairwiseAligner.c:287-307).  A scalar helper for callers and tests; the device kernels carry their own copy. */
+double logAdd(double x, double y);
+
+/* :177-182 */
+typedef struct _symbolString {
+    Symbol *sequence;
+    int64_t length;
+} SymbolString;
+SymbolString symbolString_construct(const char *sequence, int64_t length);
+void symbolString_destruct(SymbolString s);
+
+/*
+ * :233-247, :264 -- the banded forward-backward itself, with the per-diagonal posterior callback the reference passes in.
+ *
+ * On the device the per-diagonal work is compiled into the kernels, so a callback cannot cross: the three callbacks the
+ * reference's own wrappers use (impl/pairwiseAligner.c:1441, :1472, :1502) are exported under their names and recognised BY
+ * ADDRESS -- diagonalCalculationPosteriorMatchProbs selects the aligned-pairs mode (extraArgs[0] = list of (pInt, x, y)),
+ * diagonalCalculationPosteriorProbs the match + gap-X + gap-Y mode (extraArgs[0], [2], [4]), diagonalCalculationExpectations
+ * the expectation mode (extraArgs = Hmm *, +=).  Any other function pointer aborts with a message, and so does calling one of
+ * the three directly (DpMatrix is never materialised on the host).  Lists are filled in the reference's own emission order
+ * (traceback blocks ascending, diagonals descending, x ascending) with coordinates relative to the strings passed in.
+ */
+typedef struct _dpMatrix DpMatrix;
+typedef void (*DiagonalPosteriorProbFn)(StateMachine *, int64_t, DpMatrix *, DpMatrix *, const SymbolString, const SymbolString, double,
+                                        PairwiseAlignmentParameters *, void *);
+void diagonalCalculationPosteriorMatchProbs(StateMachine *sM, int64_t xay, DpMatrix *forwardDpMatrix, DpMatrix *backwardDpMatrix,
+                                            const SymbolString sX, const SymbolString sY, double totalProbability,
+                                            PairwiseAlignmentParameters *p, void *extraArgs); /* :233 */
+void diagonalCalculationPosteriorProbs(StateMachine *sM, int64_t xay, DpMatrix *forwardDpMatrix, DpMatrix *backwardDpMatrix,
+                                       const SymbolString sX, const SymbolString sY, double totalProbability,
+                                       PairwiseAlignmentParameters *p, void *extraArgs); /* impl/pairwiseAligner.c:691 */
+void diagonalCalculationExpectations(StateMachine *sM, int64_t xay, DpMatrix *forwardDpMatrix, DpMatrix *backwardDpMatrix,
+                                     const SymbolString sX, const SymbolString sY, double totalProbability,
+                                     PairwiseAlignmentParameters *p, void *extraArgs); /* impl/pairwiseAligner.c:735 (static there) */
+/* :245 -- one region, no splitting */
+void getPosteriorProbsWithBanding(StateMachine *sM, stList *anchorPairs, const SymbolString sX, const SymbolString sY,
+                                  PairwiseAlignmentParameters *p, bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd,
+                                  DiagonalPosteriorProbFn diagonalPosteriorProbFn, void *extraArgs);
+/* :264 -- splits at anchor gaps bigger than p->splitMatrixBiggerThanThis; after every region (all of them computed in one
+ * device pass) its results are appended and coordinateCorrectionFn(x1, y1, extraArgs) is called, if not NULL */
+void getPosteriorProbsWithBandingSplittingAlignmentsByLargeGaps(StateMachine *sM, stList *anchorPairs, const char *sX, const char *sY, int64_t lX,
+                                                                int64_t lY, PairwiseAlignmentParameters *p, bool alignmentHasRaggedLeftEnd,
+                                                                bool alignmentHasRaggedRightEnd, DiagonalPosteriorProbFn diagonalPosteriorProbFn,
+                                                                void (*coordinateCorrectionFn)(), void *extraArgs);
+
 /* :261 -- list of stIntTuple (x1, y1, x2, y2) */
 stList *getSplitPoints(stList *anchorPairs, int64_t lX, int64_t lY, int64_t maxMatrixSize, bool alignmentHasRaggedLeftEnd,
                        bool alignmentHasRaggedRightEnd);

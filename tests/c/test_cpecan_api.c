@@ -205,6 +205,29 @@ static void test_diagonal_and_symbols(void) {
     CHECK(symbol_convertSymbolToChar(g) == 'G' && symbol_convertSymbolToChar(n) == 'N');
 }
 
+/* test_logAdd, tests/pairwiseAlignerTest.c:134-144: within 1e-3 of the exact value; plus the contract's edge cases */
+static void test_log_add(void) {
+    for (int i = 0; i < 100000; i++) {
+        const double x = (double) rnd_int(-1000000, 1000000) / 10000.0, y = x + (double) rnd_int(-120000, 120000) / 10000.0;
+        const double exact = (x > y ? x : y) + log1p(exp(-fabs(x - y)));
+        CHECK(fabs(logAdd(x, y) - exact) < 0.001);
+        CHECK(logAdd(x, y) == logAdd(y, x));
+    }
+    CHECK(logAdd(LOG_ZERO, 3.0) == 3.0 && logAdd(-2.0, LOG_ZERO) == -2.0 && logAdd(LOG_ZERO, LOG_ZERO) == LOG_ZERO);
+    CHECK(logAdd(0.0, 7.5) == 7.5 && logAdd(0.0, 7.4999) > 7.4999 && logAdd(1.0, 1.0) == 1.0 + (double) 0.693203116424741f);
+}
+
+static void test_symbol_string(void) {
+    SymbolString s = symbolString_construct("AcgTnX", 6);
+    const Symbol want[6] = { a, c, g, t, n, n };
+    CHECK(s.length == 6);
+    for (int i = 0; i < 6; i++) CHECK(s.sequence[i] == want[i]);
+    symbolString_destruct(s);
+    s = symbolString_construct("", 0);
+    CHECK(s.length == 0);
+    symbolString_destruct(s);
+}
+
 /* ------------------------------------------------------------------------------------- gpu tests */
 
 static int diag_is(Diagonal d, int64_t xay, int64_t l, int64_t r) { return d.xay == xay && d.xmyL == l && d.xmyR == r; }
@@ -399,6 +422,65 @@ static void write_hmm(FILE *out, const char *tag, Hmm *hmm) {
     fprintf(out, " %a\n", hmm->likelihood);
 }
 
+/* what the reference's own wrappers pass as coordinateCorrectionFn (impl/pairwiseAligner.c:1259-1271, :1411-1429): shift the region's
+ * tuples and move them, last first, onto the result list */
+static void correct_lists(int64_t offsetX, int64_t offsetY, void *extraArgs, int nLists) {
+    for (int l = 0; l < nLists; l++) {
+        stList *sub = ((void **) extraArgs)[2 * l], *all = ((void **) extraArgs)[2 * l + 1];
+        while (stList_length(sub) > 0) {
+            stIntTuple *t = stList_pop(sub);
+            stList_append(all, stIntTuple_construct3(stIntTuple_get(t, 0), stIntTuple_get(t, 1) + offsetX, stIntTuple_get(t, 2) + offsetY));
+            stIntTuple_destruct(t);
+        }
+    }
+}
+static void correct_one(int64_t offsetX, int64_t offsetY, void *extraArgs) { correct_lists(offsetX, offsetY, extraArgs, 1); }
+static void correct_three(int64_t offsetX, int64_t offsetY, void *extraArgs) { correct_lists(offsetX, offsetY, extraArgs, 3); }
+
+/* getPosteriorProbsWithBanding / ...SplittingAlignmentsByLargeGaps with each of the three callbacks (inc/pairwiseAligner.h:245, :264) */
+static void write_callback_forms(FILE *out, StateMachine *sM, const char *sX, const char *sY, stList *anchors, PairwiseAlignmentParameters *p, bool rl,
+                                 bool rr) {
+    const int64_t lX = (int64_t) strlen(sX), lY = (int64_t) strlen(sY);
+    /* one region, no splitting, lists in the callback's own order */
+    SymbolString x = symbolString_construct(sX, lX), y = symbolString_construct(sY, lY);
+    stList *lists[6];
+    for (int i = 0; i < 6; i++) lists[i] = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    getPosteriorProbsWithBanding(sM, anchors, x, y, p, rl, rr, diagonalCalculationPosteriorMatchProbs, lists);
+    write_list(out, "banding", lists[0]);
+    stList_destruct(lists[0]);
+    lists[0] = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    getPosteriorProbsWithBanding(sM, anchors, x, y, p, rl, rr, diagonalCalculationPosteriorProbs, lists);
+    write_list(out, "bandingM", lists[0]);
+    write_list(out, "bandingX", lists[2]);
+    write_list(out, "bandingY", lists[4]);
+    Hmm *h = hmm_constructEmpty(0.0, sM->type);
+    getPosteriorProbsWithBanding(sM, anchors, x, y, p, rl, rr, diagonalCalculationExpectations, h);
+    write_hmm(out, "bandingE", h);
+    hmm_destruct(h);
+    symbolString_destruct(x);
+    symbolString_destruct(y);
+    /* split at large gaps, with the reference's correction functions */
+    for (int i = 0; i < 6; i++) {
+        stList_destruct(lists[i]);
+        lists[i] = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    }
+    getPosteriorProbsWithBandingSplittingAlignmentsByLargeGaps(sM, anchors, sX, sY, lX, lY, p, rl, rr, diagonalCalculationPosteriorMatchProbs, correct_one,
+                                                               lists);
+    write_list(out, "splitting", lists[1]);
+    stList_destruct(lists[1]);
+    lists[1] = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    getPosteriorProbsWithBandingSplittingAlignmentsByLargeGaps(sM, anchors, sX, sY, lX, lY, p, rl, rr, diagonalCalculationPosteriorProbs, correct_three,
+                                                               lists);
+    write_list(out, "splittingM", lists[1]);
+    write_list(out, "splittingX", lists[3]);
+    write_list(out, "splittingY", lists[5]);
+    h = hmm_constructEmpty(0.0, sM->type);
+    getPosteriorProbsWithBandingSplittingAlignmentsByLargeGaps(sM, anchors, sX, sY, lX, lY, p, rl, rr, diagonalCalculationExpectations, NULL, h);
+    write_hmm(out, "splittingE", h);
+    hmm_destruct(h);
+    for (int i = 0; i < 6; i++) stList_destruct(lists[i]);
+}
+
 /*
  * IN:  line 1: type hmmFile|- paramsJson...   (the rest of the line is the parameter JSON)
  *      line 2: n
@@ -480,6 +562,7 @@ static int run_file(const char *inPath, const char *outPath) {
         write_hmm(out, "expectations", h);
         hmm_destruct(h);
         fprintf(out, "forward1 %a\n", computeForwardProbability(sX[i], sY[i], anchors[i], p, sM, rl[i], rr[i]));
+        write_callback_forms(out, sM, sX[i], sY[i], anchors[i], p, rl[i], rr[i]);
         stList_destruct(m[i]);
         stList_destruct(gx[i]);
         stList_destruct(gy[i]);
@@ -504,6 +587,8 @@ int main(int argc, char **argv) {
         test_json();
         test_split_points();
         test_diagonal_and_symbols();
+        test_log_add();
+        test_symbol_string();
     } else if (argc >= 2 && strcmp(argv[1], "gpu") == 0) {
         test_bands();
         test_kat();

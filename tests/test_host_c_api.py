@@ -21,6 +21,9 @@ BUILD = os.path.join(ROOT, "tests", "c", "_build")
 EXE = os.path.join(BUILD, "test_cpecan_api")
 
 
+PINT_TOL = 1  # floor(p * 1e7): CUDA exp vs glibc exp in the last place
+
+
 def build_exe():
     src = os.path.join(ROOT, "tests", "c", "test_cpecan_api.c")
     if not os.path.exists(HOST_SO):
@@ -61,7 +64,31 @@ def test_host_library_has_no_dp_of_its_own():
             # the EM trainer's Jukes-Cantor starting emissions (cPecanEm.py:87-93) are the one exponential on the host side
             assert len(re.findall(r"\bexp\s*\(", text)) == 1 and "jukes_cantor_emissions" in text
             text = re.sub(r"\bexp\s*\(-4\.0 \* divergence / 3\.0\)", "", text)
+        if fn == "logAdd.c":
+            # the reference's header exposes logAdd (inc/pairwiseAligner.h:167); this file is that scalar and nothing else, and no
+            # other host file may call it
+            assert "cubic" in text and len(text.splitlines()) < 40
+            continue
         assert not re.search(r"\blogAdd\s*\(|\bexp\s*\(|\blog\s*\(", text), fn
+
+
+def test_host_logadd_is_bit_identical_to_the_reference(oracle):
+    """logAdd (inc/pairwiseAligner.h:167) of libcpecan.so against the reference's own, over every segment, the cut-off and LOG_ZERO"""
+    import ctypes as C
+
+    build_exe()
+    lib = C.CDLL(HOST_SO)
+    lib.logAdd.restype = C.c_double
+    lib.logAdd.argtypes = [C.c_double, C.c_double]
+    rng = np.random.default_rng(7)
+    xs = rng.uniform(-50, 5, 20000)
+    ds = np.concatenate([rng.uniform(0, 9, 19000), [0.0, 1.0, 2.5, 4.5, 7.5, np.nextafter(1.0, 2), np.nextafter(7.5, 0)], rng.uniform(0, 1e-6, 993)])
+    for x, d in zip(xs, ds):
+        for u, v in ((x, x + d), (x + d, x)):
+            assert lib.logAdd(u, v) == oracle.logadd(u, v), (u, v)
+    inf = float("inf")
+    for u, v in ((-inf, 1.5), (1.5, -inf), (-inf, -inf)):
+        assert lib.logAdd(u, v) == oracle.logadd(u, v)
 
 
 def test_host_suite_without_a_gpu():
@@ -139,10 +166,10 @@ def test_c_api_matches_the_oracle(tmp_path, oracle, type_):
     for i, (sx, sy, a, rl, rr) in enumerate(cases):
         assert lines[k] == "problem %d" % i
         got = {}
-        for j in range(1, 9):
+        for j in range(1, 19):
             f = lines[k + j].split()
             got[f[0]] = f[1:]
-        k += 9
+        k += 19
         want = oracle.aligned_pairs_with_indels(om, op, sx, sy, a, rl, rr)
         for key, w in zip(("match", "gapX", "gapY"), want):
             g, w = helpers.sort_triples(_parse_list(got[key])), helpers.sort_triples(w)
@@ -156,6 +183,22 @@ def test_c_api_matches_the_oracle(tmp_path, oracle, type_):
         e = oracle.expectations(om, op, sx, sy, a, rl, rr)
         np.testing.assert_allclose(np.array([float.fromhex(v) for v in got["expectations"]]), e, rtol=1e-9, atol=1e-12)
         total += e
+        # the callback entry points (inc/pairwiseAligner.h:245, :264) with the three built-in callbacks.  Split form + the reference's
+        # correction functions = the wrapper's list, element for element; the one-region form = the oracle without splitting, in the
+        # callback's own order (the reverse of the wrapper's)
+        for key, ref in (("splitting", "one"), ("splittingM", "match"), ("splittingX", "gapX"), ("splittingY", "gapY")):
+            assert got[key] == got[ref], (i, key)
+        np.testing.assert_allclose(np.array([float.fromhex(v) for v in got["splittingE"]]), e, rtol=1e-9, atol=1e-12)
+        nosplit = helpers.orc_params_from(p)
+        nosplit.splitMatrixBiggerThanThis = 1 << 62
+        want1 = oracle.aligned_pairs_with_indels(om, nosplit, sx, sy, a, rl, rr)
+        for key, w in zip(("bandingM", "bandingX", "bandingY"), want1):
+            g = _parse_list(got[key])
+            assert g.shape == w.shape and np.array_equal(g[:, 1:], w[::-1, 1:]), (i, key)
+            assert g.shape[0] == 0 or np.abs(g[:, 0] - w[::-1, 0]).max() <= PINT_TOL
+        assert got["banding"] == got["bandingM"]
+        np.testing.assert_allclose(np.array([float.fromhex(v) for v in got["bandingE"]]), oracle.expectations(om, nosplit, sx, sy, a, rl, rr),
+                                   rtol=1e-9, atol=1e-12)
     f = lines[k].split()
     assert f[0] == "total"
     np.testing.assert_allclose(np.array([float.fromhex(v) for v in f[1:]]), total, rtol=1e-9, atol=1e-12)

@@ -73,6 +73,32 @@ template <int MODE> __global__ void mix(double *out, double a, double b, int sel
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// LDS.128 with a per-lane row that changes every iteration (what logAdd does):
+// MODE 0: compact table, 5 rows of 16 bytes in 5 different bank groups (any mix of rows: one address per bank, broadcast);
+// MODE 1: lane-replicated rows (row * 128 + 16 * (lane & 7)): conflict-free, but every quarter warp reads its own 128 bytes.
+template <int MODE> __global__ void ldsrows(double *out, double a) {
+    __shared__ __align__(128) double tab[26 * 16];
+    for (int i = threadIdx.x; i < 26 * 16; i += blockDim.x) tab[i] = a + i * 1e-9;
+    __syncthreads();
+    unsigned base = (unsigned) __cvta_generic_to_shared(tab);
+    unsigned h = threadIdx.x * 2654435761u + blockIdx.x;
+    double x[4] = {a, a, a, a};
+#pragma unroll 4
+    for (int i = 0; i < ITER; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            h = h * 1664525u + 1013904223u;
+            const unsigned r = (h >> 24);
+            const unsigned addr = MODE == 0 ? base + 16u * (r % 5u) : base + 128u * (r % 26u) + 16u * (threadIdx.x & 7);
+            double u, v;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(u), "=d"(v) : "r"(addr));
+            x[k] = __dadd_rn(x[k], u);
+            x[k] = __dadd_rn(x[k], v);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x[0] + x[1] + x[2] + x[3];
+}
+
 int main() {
     double *out;
     long long *cyc, h[16] = {0};
@@ -136,6 +162,24 @@ int main() {
             // cycles one SMSP spends per (8 ops of each class), all its warps taken together
             const double cyc = ms * 1e-3 * 1.965e9 / ITER / (warps / 4.0);
             printf("mix %-14s warps/SM %2d: %.1f SMSP-cycles per 8 warp-instructions of each class\n", mn[m], warps, cyc);
+        }
+    }
+
+    for (int warps = 4; warps <= 16; warps *= 2) {
+        for (int m = 0; m < 2; m++) {
+            const int blocks = 148 * 4, threads = 32 * warps / 4;
+            float ms = 0;
+            for (int rep = 0; rep < 2; rep++) {
+                cudaEventRecord(e0);
+                if (m == 0) ldsrows<0><<<blocks, threads>>>(out, 1.0);
+                if (m == 1) ldsrows<1><<<blocks, threads>>>(out, 1.0);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                cudaEventElapsedTime(&ms, e0, e1);
+            }
+            const double ops = (double) blocks * threads * ITER * 4;
+            printf("LDS.128 + 2 DADD, random rows, %-16s warps/SM %2d: %.2f SM-cycles per warp-level fetch\n", m == 0 ? "compact (5 rows)" : "lane-replicated", warps,
+                   ms * 1e-3 * 1.965e9 * 148 / (ops / 32));
         }
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
