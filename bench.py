@@ -31,9 +31,16 @@ import numpy as np  # noqa: E402
 METRIC = "GCUPS (banded fwd-bwd+posterior)"
 UNIT = "GCUPS"
 WORKLOAD = "100k x 1 kb evolved pairs (randomSequences-style, ~10% divergence), StateMachine5, lib-default band (expansion 20, trim 14), threshold 0.01"
-ALG_BYTES_PER_CELL = 80.0   # 5 states x 8 B written by forward + read by backward
-OPS_PER_CELL = 170.0        # 2 sweeps x (13 adds + 8 logAdds x 8 separately rounded FP64 operations)
-DRAM_BYTES_PER_CELL = 55.4  # measured: dram__bytes_read+write of k_forward_strip + k_backward_strip, profiles/README.md
+# DESIGN.md section 5, per band cell (five states, aligned-pairs mode).  One sweep = 13 transition adds + 8 logAdds of 8 separately
+# rounded FP64 operations (1 subtract, 3 multiplies, 4 adds; contraction to FMA is not allowed) = 77; the backward sweep adds the
+# F + B sum = 78; forward + backward = 155 (SURVEY.md section 8d's 280 "FLOP" counted compares and selects, which are not FP64 work).
+OPS_FORWARD, OPS_BACKWARD = 77.0, 78.0
+# HBM: what the two sweeps have to move per cell -- forward writes F.M (8 B) + 1/10 of the full cell (4 B); backward reads F.M (8 B)
+# and 1/10 of the full cell (4 B) and writes F + B (8 B); (the posterior scan reads those 8 B again in its own kernel)
+ALG_BYTES_FORWARD, ALG_BYTES_BACKWARD = 12.0, 20.0
+# measured dram__bytes_read.sum + dram__bytes_write.sum per cell of one launch (ncu --set full, profiles/): forward, backward
+DRAM_BYTES_FORWARD, DRAM_BYTES_BACKWARD = 19.9, 35.5
+FP64_LANES_PER_SM = 64      # B200: 64 FP64 lanes per SM and clock; tools/ubench.cu measures 59.4 sustained (profiles/r1_ubench.txt)
 
 
 def read_peaks():
@@ -105,16 +112,16 @@ def make_inputs(n_pairs, rank, params):
 
 
 def cpu_arm(packed, n_sample, threads):
-    """Times the CPU implementation (reference build if present) on the first n_sample pairs of the workload."""
+    """Times the CPU implementation (reference build if present) on the first n_sample pairs of the workload.  Nothing here touches
+    the product library: parameters and model come from the oracle itself, the generator is plain numpy."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers
     from cpecan_b200 import synth
-    import cpecan_b200 as cp
 
     orc = helpers.best_oracle()
     sub = synth.subset(packed, range(n_sample))
-    p = helpers.orc_params_from(cp.pairwiseAlignmentBandingParameters_construct())
-    m = helpers.ModelSpec(cp.fiveState).orc()
+    p = orc.default_params()
+    m = helpers.ModelSpec(0).orc()  # fiveState, the reference's default model
     t0 = time.perf_counter()
     counts, _, _ = orc.batch(m, p, sub, mode=0, threads=threads)
     dt = time.perf_counter() - t0
@@ -122,7 +129,7 @@ def cpu_arm(packed, n_sample, threads):
 
 
 def count_cells(packed, n_sample):
-    """band cells of the first n_sample pairs, from the product's own band builder statistics"""
+    """band cells of the first n_sample pairs, from the product's own band builder statistics (b200 arm only)"""
     import cpecan_b200 as cp
     from cpecan_b200 import synth
 
@@ -135,6 +142,51 @@ def count_cells(packed, n_sample):
     return int(cells)
 
 
+def capi_arm(cp, ctx, model, params, packed, n, barrier):
+    """The same pass through the reference-named batch call of libcpecan.so (tools/bench_capi.c): strings and stLists of anchor tuples
+    in, stLists of (pInt, x, y) tuples out, walked once and destructed -- beside the flat C-ABI on the same subset of the workload.
+    A subset (default 20 000 pairs) because the reference's interface needs ~100 bytes of host heap per aligned pair."""
+    from cpecan_b200 import synth
+
+    exe = os.path.join(ROOT, "cpecan_b200", "lib", "bench_capi")
+    if not os.path.exists(exe):
+        return {"value": None, "note": "cpecan_b200/lib/bench_capi is not built"}
+    sub = synth.subset(packed, range(n))
+    path = "/tmp/cpecan_capi_workload_%d.bin" % os.getpid()
+    with open(path, "wb") as f:
+        np.asarray([n], dtype=np.int64).tofile(f)
+        for k in ("xOff", "yOff", "aOff"):
+            np.ascontiguousarray(sub[k], dtype=np.int64).tofile(f)
+        np.ascontiguousarray(sub["seqX"][: int(sub["xOff"][-1])], dtype=np.uint8).tofile(f)
+        np.ascontiguousarray(sub["seqY"][: int(sub["yOff"][-1])], dtype=np.uint8).tofile(f)
+        np.ascontiguousarray(sub["anchors"][: 3 * int(sub["aOff"][-1])], dtype=np.int64).tofile(f)
+    # the flat C-ABI on the same subset, for the ratio
+    b = cp.Batch(ctx, None, None, packed=sub)
+    b.run(model, params, cp.MODE_ALIGNED_PAIRS)
+    cells = int(b.stats().cells)
+    b.close()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        b = cp.Batch(ctx, None, None, packed=sub)
+        b.run(model, params, cp.MODE_ALIGNED_PAIRS)
+        b.fetch_pairs(0)
+        b.close()
+    flat = (time.perf_counter() - t0) / 2
+    try:
+        out = subprocess.run([exe, path, "2", "1"], capture_output=True, text=True, timeout=600)
+        j = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as ex:
+        return {"value": None, "note": "bench_capi failed: %s" % ex}
+    finally:
+        os.remove(path)
+    return {"value": cells / j["s_per_step"] / 1e9, "unit": UNIT, "pairs": n, "pairs_per_s": n / j["s_per_step"], "tuples": j["tuples"],
+            "s_call": j["s_call"], "s_walk": j["s_walk"], "s_destruct": j["s_destruct"],
+            "flat_abi_same_pairs": {"value": cells / flat / 1e9, "unit": UNIT},
+            "ratio_flat_over_capi": (cells / flat) / (cells / j["s_per_step"]),
+            "api": "getAlignedPairsUsingAnchorsBatch (include/cpecan/pairwiseAligner.h), stList / stIntTuple in and out"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,6 +195,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=100000, help="pairs per GPU (weak scaling)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
+    ap.add_argument("--capi-pairs", type=int, default=20000, help="pairs of the workload sent through the reference-named C API (e2e_capi)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: no end-to-end arm")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: no CPU baseline")
     args = ap.parse_args()
@@ -152,14 +205,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     threads = os.cpu_count() or 1
 
-    import cpecan_b200 as cp
-
-    params = cp.pairwiseAlignmentBandingParameters_construct()
-
     if args.impl == "reference":
-        # the reference's CPU path on all host cores; rank 0 only
+        # the reference's CPU path on all host cores; rank 0 only.  This arm never loads the product's libraries: parameters come from
+        # the oracle, band cells are counted with the oracle's band builder.
         if rank != 0:
             return
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers
+
+        params = helpers.best_oracle().default_params()
         n_sample = max(32 * threads, 256)  # enough pairs per thread for an even load
         packed = make_inputs(n_sample, 0, params)
         ident, dt_probe, _ = cpu_arm(packed, min(8, n_sample), 1)
@@ -168,15 +222,14 @@ def main():
         steps_total = max(args.steps + args.warmup, 1)
         budget = max(args.cpu_seconds * 4 / steps_total, 2.0)
         n_step = int(min(n_sample, max(threads, budget * threads / max(per_pair, 1e-6))))
-        cells = count_cells(packed, n_step) if _has_gpu() else None
+        cells = _cells_by_oracle(packed, n_step, int(params.diagonalExpansion))
         times = []
         for i in range(args.warmup + args.steps):
             _, dt, _ = cpu_arm(packed, n_step, threads)
             if i >= args.warmup:
                 times.append(dt)
         tsum = sum(times)
-        if cells is None:
-            cells = _cells_by_oracle(packed, n_step)
+        assert not any("libcpecan" in line and "oracle" not in line for line in open("/proc/self/maps")), "the reference arm mapped a product library"
         gcups = cells * len(times) / tsum / 1e9
         line = {
             "impl": "reference", "metric": METRIC, "value": gcups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -193,6 +246,9 @@ def main():
 
     import torch
 
+    import cpecan_b200 as cp
+
+    params = cp.pairwiseAlignmentBandingParameters_construct()
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -287,14 +343,25 @@ def main():
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
     e2e_value = cells_all * e2e_steps / float(tw[0]) / 1e9
 
+    e2e_capi = None
+    if rank == 0 and world == 1 and not args.skip_e2e:
+        e2e_capi = capi_arm(cp, ctx, model, params, packed, min(args.pairs, args.capi_pairs), barrier)
     if rank == 0:
         hbm_peak, sm_max, peak_src = read_peaks()
-        # dominant kernels: the forward and backward wavefronts (one launch per width class and chunk)
-        k_ms = (phase["forward"] + phase["backward"]) / args.steps
-        dom = "k_forward+k_backward"
-        achieved_gbs = cells * ALG_BYTES_PER_CELL / (k_ms * 1e-3) / 1e9
-        fp64_peak = 148 * 64 * sm_max * 1e6 / 1e12  # T op/s: 64 FP64 lanes/clk/SM, no FMA (the contract forbids contraction)
-        achieved_tf = cells * OPS_PER_CELL / (k_ms * 1e-3) / 1e12
+        # The dominant kernel is the backward wavefront (one launch per chunk), then the forward one.  Both are bound by the FP64 pipe --
+        # a recurrence of separately rounded adds and multiplies ("compute, not tensor cores, not HBM") -- so the
+        # top-level roofline is that pipe; HBM is the secondary entry, from MEASURED dram bytes per launch.
+        n_launch = max(int(st.nChunks), 1)
+        fwd_ms, bwd_ms = phase["forward"] / args.steps, phase["backward"] / args.steps
+        fp64_peak = 148 * FP64_LANES_PER_SM * sm_max * 1e6 / 1e12  # TFLOP/s of non-fused FP64 operations at the measured maximum clock
+        def leg(ms, ops, alg_bytes, dram_bytes):
+            return {"ms_per_launch": ms / n_launch, "achieved": cells * ops / (ms * 1e-3) / 1e12, "frac": cells * ops / (ms * 1e-3) / 1e12 / fp64_peak,
+                    "ops_per_cell": ops,
+                    "hbm": {"achieved": cells * alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": cells * alg_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_cell": alg_bytes,
+                            "measured_dram_bytes_per_cell": dram_bytes, "traffic_over_algorithmic": dram_bytes / alg_bytes}}
+        bwd, fwd = leg(bwd_ms, OPS_BACKWARD, ALG_BYTES_BACKWARD, DRAM_BYTES_BACKWARD), leg(fwd_ms, OPS_FORWARD, ALG_BYTES_FORWARD, DRAM_BYTES_FORWARD)
+        both_tf = cells * (OPS_FORWARD + OPS_BACKWARD) / ((fwd_ms + bwd_ms) * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -307,14 +374,17 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "pairs_per_s": pairs_all * e2e_steps / float(tw[0])},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": DRAM_BYTES_PER_CELL * cells / max(int(st.nChunks), 1),
-                         "traffic_note": "bytes per launch pair (forward+backward of one chunk), ncu dram bytes per cell x cells per chunk",
-                         "peak_source": peak_src, "algorithmic_bytes_per_cell": ALG_BYTES_PER_CELL,
-                         "launches_per_step": 2 * int(st.nChunks),
-                         "compute": {"bound": "FP64 pipe, separately rounded add/mul (no FMA)", "achieved": achieved_tf, "peak": fp64_peak,
-                                     "unit": "Top/s", "frac": achieved_tf / fp64_peak, "ops_per_cell": OPS_PER_CELL}},
+            "roofline": {"bound": "fp64", "kernel": "k_backward_strip<5,1,true,4>", "achieved": bwd["achieved"], "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": bwd["frac"],
+                         "traffic": DRAM_BYTES_BACKWARD * cells / n_launch,
+                         "note": "non-fused FP64 operations (the reference's arithmetic forbids FMA contraction); peak = 148 SMs x 64 FP64 lanes x "
+                                 "sm_max_mhz of MEASURED_PEAKS.json; traffic = ncu dram__bytes_read+write of one launch (bytes per cell x cells per launch)",
+                         "peak_source": peak_src, "launches_per_step": n_launch,
+                         "k_backward_strip": bwd, "k_forward_strip": fwd,
+                         "forward_plus_backward": {"achieved": both_tf, "frac": both_tf / fp64_peak, "ops_per_cell": OPS_FORWARD + OPS_BACKWARD}},
         }
+        if e2e_capi is not None:
+            line["e2e_capi"] = e2e_capi
         # CPU baseline on a bounded sample of the same workload
         try:
             if args.skip_cpu:
@@ -345,18 +415,17 @@ def _has_gpu():
         return False
 
 
-def _cells_by_oracle(packed, n):
+def _cells_by_oracle(packed, n, expansion):
+    """band cells of the first n pairs from the oracle's band builder (band_construct, impl/pairwiseAligner.c:183-234)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers
     from cpecan_b200 import synth
-    import cpecan_b200 as cp
 
     orc = helpers.best_oracle()
-    p = cp.pairwiseAlignmentBandingParameters_construct()
     total = 0
     for i in range(n):
         sx, sy, a = synth.unpack(packed, i)
-        b = orc.band(a, len(sx), len(sy), int(p.diagonalExpansion))
+        b = orc.band(a, len(sx), len(sy), expansion)
         total += int(((b[:, 2] - b[:, 1]) // 2 + 1).sum())
     return total
 

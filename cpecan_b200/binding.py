@@ -76,6 +76,7 @@ class CpbRunStats(C.Structure):
         ("maxWidth", C.c_int32),
         ("twoPass", C.c_int32),
         ("msCheckpoint", C.c_double),
+        ("pintFixups", C.c_int64),
     ]
 
 
@@ -83,12 +84,19 @@ def hmm_len(S):
     return S * S + S * 16 + 1
 
 
-def _load():
+def _require_built():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             "libcpecan_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
             "or `make -f cpecan_b200/csrc/Makefile`. There is no CPU fallback." % LIB_PATH
         )
+
+
+_require_built()  # importing the package without the built library fails here, loudly
+
+
+def _load():
+    _require_built()
     L = C.CDLL(LIB_PATH)
     P = C.POINTER
     L.cpb_version.restype = C.c_char_p
@@ -122,7 +130,19 @@ def _load():
     return L
 
 
-lib = _load()
+class _LazyLib:
+    """The shared library is mapped on first use, not on import: `import cpecan_b200` (for the synthetic-data generator, say) must not
+    put libcpecan_b200.so into a process that then only runs the CPU reference (bench.py --impl reference)."""
+
+    _lib = None
+
+    def __getattr__(self, name):
+        if _LazyLib._lib is None:
+            _LazyLib._lib = _load()
+        return getattr(_LazyLib._lib, name)
+
+
+lib = _LazyLib()
 
 
 def _check(rc):

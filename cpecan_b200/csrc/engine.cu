@@ -183,6 +183,7 @@ struct cpb_context {
     size_t scratchBudget = 0;
     DevBuf scratch;
     DevBuf boundary, counters, negRecord, progress; /* strip engine: per-warp-slot boundary rings, work-fetch counters, one LOG_ZERO ring record */
+    DevBuf fixups;                                  /* posterior write pass: one counter (first 16 bytes), then PintFixup records */
     int smCount = 148;
     DevPool pool;              /* buffers handed back by destroyed batches */
     PinnedPool pinned;         /* page-locked host staging, same idea */
@@ -259,6 +260,7 @@ extern "C" void cpb_context_destroy(cpb_context *ctx) {
     ctx->boundary.release();
     ctx->negRecord.release();
     ctx->progress.release();
+    ctx->fixups.release();
     ctx->pool.drain();
     ctx->pinned.drain();
     ctx->counters.release();
@@ -566,6 +568,41 @@ static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
         }
     }
     return CPB_OK;
+}
+
+/* The smallest log-probability lp with exp(lp) >= threshold under THIS host's libm -- the reference decides p >= threshold with
+ * p = exp(lp) from libm (impl/pairwiseAligner.c:656, :680), so comparing lp against this value on the device gives the reference's
+ * keep decision exactly, whatever the device's own exp does in the last place.  Bisection over the doubles (libm's exp is monotone
+ * around the crossing; that is verified for the 64 doubles on either side and reported if it ever fails). */
+static double log_threshold_for_host_libm(double threshold) {
+    if (!(threshold > 0.0)) return -INFINITY; /* p >= 0 holds for every cell, also for p = exp(LOG_ZERO) = 0 */
+    auto key = [](double v) { /* order-preserving map of doubles to int64 */
+        int64_t k;
+        memcpy(&k, &v, sizeof(k));
+        return k < 0 ? (int64_t) 0x8000000000000000ull - k : k;
+    };
+    auto unkey = [](int64_t k) {
+        if (k < 0) k = (int64_t) 0x8000000000000000ull - k;
+        double v;
+        memcpy(&v, &k, sizeof(v));
+        return v;
+    };
+    int64_t lo = key(-800.0), hi = key(1.0); /* exp(lo) = 0 < threshold <= 1 < exp(hi) */
+    if (exp(unkey(hi)) < threshold) return INFINITY;
+    while ((uint64_t) hi - (uint64_t) lo > 1) { /* as unsigned: hi - lo does not fit an int64 */
+        const int64_t mid = (lo >> 1) + (hi >> 1) + (lo & hi & 1); /* hi - lo does not fit an int64 */
+        if (exp(unkey(mid)) >= threshold) hi = mid;
+        else lo = mid;
+    }
+    for (int k = 1; k <= 64; k++) {
+        if (exp(unkey(hi + k)) < threshold || exp(unkey(hi - k)) >= threshold) {
+            static bool warned = false;
+            if (!warned) fprintf(stderr, "cpecan_b200: libm exp is not monotone around log(%.17g); posterior keep decisions next to the threshold may differ from the reference by one cell\n", threshold);
+            warned = true;
+            break;
+        }
+    }
+    return unkey(hi);
 }
 
 static int check_params(const CpbParams *p) {
@@ -1078,6 +1115,14 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         }
     }
 
+    /* posterior scan: the keep threshold in log space under the host's libm, and the buffer for weights the host has to recompute */
+    const double logThreshold = nLists > 0 ? log_threshold_for_host_libm(p->threshold) : 0.0;
+    const double pintTolerance = getenv("CPB_PINT_TOLERANCE") != nullptr ? atof(getenv("CPB_PINT_TOLERANCE")) : 2e-8; /* tests: 0.5 sends every weight to the host */
+    const int fixupCap = getenv("CPB_PINT_FIXUP_CAP") != nullptr ? atoi(getenv("CPB_PINT_FIXUP_CAP")) : 4096;
+    if (nLists > 0) {
+        if ((rc = ctx->fixups.reserve(16 + (size_t) fixupCap * sizeof(PintFixup))) != CPB_OK) return rc;
+        CUDA_TRY(cudaMemsetAsync(ctx->fixups.p, 0, 16, st));
+    }
     stamp("strip setup (+ checkpoint pass)");
     std::vector<int64_t> hPairOff;
     int64_t running[3] = { 0, 0, 0 };
@@ -1180,8 +1225,11 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         if (nLists > 0) {
             PostArgs pa;
             memset(&pa, 0, sizeof(pa));
-            pa.threshold = p->threshold;
-            pa.logThresholdLo = p->threshold > 0.0 ? log(p->threshold) - 1e-6 : -INFINITY;
+            pa.logThreshold = logThreshold;
+            pa.pintTolerance = pintTolerance;
+            pa.fixupCap = fixupCap;
+            pa.fixupCount = ctx->fixups.as<unsigned int>();
+            pa.fixups = reinterpret_cast<PintFixup *>(ctx->fixups.as<char>() + 16);
             pa.nLists = nLists;
             pa.nDecades = c.decades;
             pa.maskWords = c.maskWords;
@@ -1274,6 +1322,32 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     }
 #endif
     stamp("chunks");
+    if (nLists > 0) {
+        /* Weights floor(p * 1e7) that sit within pintTolerance of an integer -- a few per 1e8 kept cells -- are recomputed here with the
+         * host's libm, the function the reference itself calls (impl/pairwiseAligner.c:657-661), and patched into the device lists: the
+         * triples are then identical to the reference's, not just equal up to the last place of exp. */
+        unsigned int nFix = 0;
+        CUDA_TRY(cudaMemcpyAsync(&nFix, ctx->fixups.p, sizeof(nFix), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (nFix > (unsigned) fixupCap) {
+            cpb_set_error("posterior scan: %u weights need the host's exp, more than the fix-up buffer holds (%d); raise CPB_PINT_FIXUP_CAP", nFix, fixupCap);
+            return CPB_ERR_MEMORY;
+        }
+        if (nFix > 0) {
+            std::vector<PintFixup> fx(nFix);
+            std::vector<int32_t> weights(nFix);
+            CUDA_TRY(cudaMemcpyAsync(fx.data(), ctx->fixups.as<char>() + 16, nFix * sizeof(PintFixup), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            for (unsigned k = 0; k < nFix; k++) {
+                double pr = exp(fx[k].lp);
+                if (pr > 1.0) pr = 1.0;
+                weights[k] = (int32_t) (int64_t) floor(pr * (double) CPB_PAIR_ALIGNMENT_PROB_1);
+                CUDA_TRY(cudaMemcpyAsync(b->out[fx[k].list].as<int32_t>() + 3 * fx[k].pos, &weights[k], sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            }
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        stx.pintFixups = nFix;
+    }
     finish_events();
     stx.msForward += stx.msCheckpoint; /* the forward phase is both passes */
     for (int l = 0; l < nLists; l++) {
@@ -1340,44 +1414,71 @@ extern "C" int cpb_batch_fetch_pairs_reference_order(cpb_batch *b, int list, int
     const int rc = cpb_batch_fetch_pairs(b, list, offsets, triples);
     if (rc != CPB_OK || triples == nullptr) return rc;
     const std::vector<int64_t> &off = b->pairOff[list];
-    std::vector<int32_t> tmp;
-    std::vector<std::pair<int64_t, int64_t>> runs; /* [first, last) triple of every block of the region */
-    size_t k = 0;                                  /* position in the compact block order */
-    int64_t cur = 0;                               /* regions come in pair order and own ascending ranges of x + y: one sweep */
-    int32_t pair = -1;
-    for (size_t r = 0; r < b->hRegions.size(); r++) {
-        const RegionDev &R = b->hRegions[r];
-        const int64_t pairEnd = off[R.pair + 1];
-        if (R.pair != pair) {
-            pair = R.pair;
-            cur = off[pair];
-        }
-        const int64_t shift = (int64_t) R.ox + R.oy - 2; /* matrix diagonal d holds the sequence coordinates with x + y = d + shift */
-        runs.clear();
-        const int64_t regionFirst = cur;
-        for (int j = 0; j < R.nBlocks; j++, k++) {
-            const int64_t hi = (int64_t) b->hBlocks[k].from + shift;
-            const int64_t first = cur;
-            while (cur < pairEnd && (int64_t) triples[3 * cur + 1] + triples[3 * cur + 2] <= hi) cur++;
-            runs.emplace_back(first, cur);
-        }
-        if (cur == regionFirst) continue;
-        tmp.resize((size_t) (cur - regionFirst) * 3);
-        int64_t w = 0;
-        for (size_t j = runs.size(); j-- > 0;) {
-            for (int64_t g0 = runs[j].first; g0 < runs[j].second;) {
-                const int64_t sum = (int64_t) triples[3 * g0 + 1] + triples[3 * g0 + 2];
-                int64_t g1 = g0 + 1;
-                while (g1 < runs[j].second && (int64_t) triples[3 * g1 + 1] + triples[3 * g1 + 2] == sum) g1++;
-                for (int64_t t = g1; t-- > g0;) {
-                    memcpy(&tmp[3 * w], &triples[3 * t], 3 * sizeof(int32_t));
-                    w++;
-                }
-                g0 = g1;
+    const size_t nRegions = b->hRegions.size();
+    if (nRegions == 0) return CPB_OK;
+    /* position of every region's first block in the compact block order */
+    std::vector<int64_t> firstBlock(nRegions + 1, 0);
+    for (size_t r = 0; r < nRegions; r++) firstBlock[r + 1] = firstBlock[r] + b->hRegions[r].nBlocks;
+    /* regions [r0, r1): r0 starts a pair and r1 ends one, so that every thread owns whole pairs */
+    auto reorder = [&](size_t r0, size_t r1) {
+        std::vector<int32_t> tmp;
+        std::vector<std::pair<int64_t, int64_t>> runs; /* [first, last) triple of every block of the region */
+        int64_t cur = 0;                               /* regions come in pair order and own ascending ranges of x + y: one sweep */
+        int32_t pair = -1;
+        for (size_t r = r0; r < r1; r++) {
+            const RegionDev &R = b->hRegions[r];
+            const int64_t pairEnd = off[R.pair + 1];
+            if (R.pair != pair) {
+                pair = R.pair;
+                cur = off[pair];
             }
+            const int64_t shift = (int64_t) R.ox + R.oy - 2; /* matrix diagonal d holds the sequence coordinates with x + y = d + shift */
+            runs.clear();
+            const int64_t regionFirst = cur;
+            for (int j = 0; j < R.nBlocks; j++) {
+                const int64_t hi = (int64_t) b->hBlocks[firstBlock[r] + j].from + shift;
+                const int64_t first = cur;
+                while (cur < pairEnd && (int64_t) triples[3 * cur + 1] + triples[3 * cur + 2] <= hi) cur++;
+                runs.emplace_back(first, cur);
+            }
+            if (cur == regionFirst) continue;
+            tmp.resize((size_t) (cur - regionFirst) * 3);
+            int64_t w = 0;
+            for (size_t j = runs.size(); j-- > 0;) {
+                for (int64_t g0 = runs[j].first; g0 < runs[j].second;) {
+                    const int64_t sum = (int64_t) triples[3 * g0 + 1] + triples[3 * g0 + 2];
+                    int64_t g1 = g0 + 1;
+                    while (g1 < runs[j].second && (int64_t) triples[3 * g1 + 1] + triples[3 * g1 + 2] == sum) g1++;
+                    for (int64_t t = g1; t-- > g0;) {
+                        memcpy(&tmp[3 * w], &triples[3 * t], 3 * sizeof(int32_t));
+                        w++;
+                    }
+                    g0 = g1;
+                }
+            }
+            memcpy(&triples[3 * regionFirst], tmp.data(), tmp.size() * sizeof(int32_t));
         }
-        memcpy(&triples[3 * regionFirst], tmp.data(), tmp.size() * sizeof(int32_t));
+    };
+    const int64_t total = off[b->n];
+    const int64_t nThreads = std::max<int64_t>(1, std::min<int64_t>({ (int64_t) std::thread::hardware_concurrency(), (int64_t) 16, total >> 20 }));
+    if (nThreads <= 1) {
+        reorder(0, nRegions);
+        return CPB_OK;
     }
+    /* cut the region list where a new pair starts, at about equal numbers of triples */
+    std::vector<std::thread> pool;
+    size_t r0 = 0;
+    for (int64_t t = 0; t < nThreads && r0 < nRegions; t++) {
+        size_t r1 = nRegions;
+        if (t + 1 < nThreads) {
+            const int64_t want = total * (t + 1) / nThreads;
+            r1 = r0;
+            while (r1 < nRegions && (off[b->hRegions[r1].pair] < want || (r1 > 0 && b->hRegions[r1].pair == b->hRegions[r1 - 1].pair))) r1++;
+        }
+        if (r1 > r0) pool.emplace_back(reorder, r0, r1);
+        r0 = r1;
+    }
+    for (auto &t : pool) t.join();
     return CPB_OK;
 }
 
@@ -1465,6 +1566,102 @@ extern "C" int cpb_batch_fetch_expectations(cpb_batch *b, double *perPair, doubl
     if (perPair && b->n > 0) CUDA_TRY(cudaMemcpyAsync(perPair, b->perPair.p, (size_t) b->n * len * sizeof(double), cudaMemcpyDeviceToHost, b->ctx->stream));
     if (total) CUDA_TRY(cudaMemcpyAsync(total, b->hmmTotal.p, len * sizeof(double), cudaMemcpyDeviceToHost, b->ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+    return CPB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * EM reduction across the GPUs of one process: every batch's expectation total (CPB_HMM_LEN(S) doubles in its device's HBM) becomes
+ * the sum over all batches, by ONE ncclAllReduce(ncclDouble, ncclSum) per device inside a group call -- the replacement of
+ * cPecanEm.py:182-188, which sums per-job expectation files.  NCCL is bound at run time (dlopen of libnccl.so.2: the library has no
+ * link-time dependency on it); without it the caller adds the 58 / 106 doubles up on the host.
+ * ---------------------------------------------------------------------------------------------- */
+#include <dlfcn.h>
+namespace {
+struct Nccl {
+    typedef void *Comm;
+    int (*commInitAll)(Comm *, int, const int *) = nullptr;
+    int (*commDestroy)(Comm) = nullptr;
+    int (*allReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*groupStart)() = nullptr;
+    int (*groupEnd)() = nullptr;
+    const char *(*errorString)(int) = nullptr;
+    bool tried = false, ok = false;
+    std::vector<int> devices; /* the communicators below were made for exactly these devices, in this order */
+    std::vector<Comm> comms;
+    bool load() {
+        if (tried) return ok;
+        tried = true;
+        void *h = nullptr;
+        for (const char *name : { "libnccl.so.2", "libnccl.so" }) {
+            if ((h = dlopen(name, RTLD_NOW | RTLD_LOCAL)) != nullptr) break;
+        }
+        if (h == nullptr) return false;
+        commInitAll = (int (*)(Comm *, int, const int *)) dlsym(h, "ncclCommInitAll");
+        commDestroy = (int (*)(Comm)) dlsym(h, "ncclCommDestroy");
+        allReduce = (int (*)(const void *, void *, size_t, int, int, Comm, cudaStream_t)) dlsym(h, "ncclAllReduce");
+        groupStart = (int (*)()) dlsym(h, "ncclGroupStart");
+        groupEnd = (int (*)()) dlsym(h, "ncclGroupEnd");
+        errorString = (const char *(*) (int) ) dlsym(h, "ncclGetErrorString");
+        ok = commInitAll && commDestroy && allReduce && groupStart && groupEnd && errorString;
+        return ok;
+    }
+} g_nccl;
+} // namespace
+
+extern "C" int cpb_expectations_allreduce(cpb_batch *const *batches, int n) {
+    if (batches == nullptr || n < 1) {
+        cpb_set_error("cpb_expectations_allreduce: bad argument");
+        return CPB_ERR_ARGUMENT;
+    }
+    std::vector<int> devices;
+    for (int i = 0; i < n; i++) {
+        if (batches[i] == nullptr || batches[i]->lastMode != CPB_MODE_EXPECTATIONS || batches[i]->lastS != batches[0]->lastS) {
+            cpb_set_error("cpb_expectations_allreduce: batch %d has no expectations of the same model", i);
+            return CPB_ERR_ARGUMENT;
+        }
+        devices.push_back(batches[i]->ctx->device);
+    }
+    if (n == 1) return CPB_OK;
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < i; j++) {
+            if (devices[i] == devices[j]) {
+                cpb_set_error("cpb_expectations_allreduce: batches %d and %d are on the same device", j, i);
+                return CPB_ERR_ARGUMENT;
+            }
+        }
+    }
+    if (!g_nccl.load()) {
+        cpb_set_error("cpb_expectations_allreduce: NCCL (libnccl.so.2) is not available");
+        return CPB_ERR_CUDA;
+    }
+    if (g_nccl.devices != devices) {
+        for (auto c : g_nccl.comms) g_nccl.commDestroy(c);
+        g_nccl.comms.assign(n, nullptr);
+        g_nccl.devices.clear();
+        const int rc = g_nccl.commInitAll(g_nccl.comms.data(), n, devices.data());
+        if (rc != 0) {
+            cpb_set_error("ncclCommInitAll: %s", g_nccl.errorString(rc));
+            g_nccl.comms.clear();
+            return CPB_ERR_CUDA;
+        }
+        g_nccl.devices = devices;
+    }
+    const size_t len = CPB_HMM_LEN(batches[0]->lastS);
+    int rc = g_nccl.groupStart();
+    for (int i = 0; i < n && rc == 0; i++) {
+        cudaSetDevice(devices[i]);
+        rc = g_nccl.allReduce(batches[i]->hmmTotal.p, batches[i]->hmmTotal.p, len, /* ncclDouble */ 8, /* ncclSum */ 0, g_nccl.comms[i], batches[i]->ctx->stream);
+    }
+    const int rcEnd = g_nccl.groupEnd();
+    if (rc == 0) rc = rcEnd;
+    if (rc != 0) {
+        cpb_set_error("ncclAllReduce: %s", g_nccl.errorString(rc));
+        return CPB_ERR_CUDA;
+    }
+    for (int i = 0; i < n; i++) {
+        CUDA_TRY(cudaSetDevice(devices[i]));
+        CUDA_TRY(cudaStreamSynchronize(batches[i]->ctx->stream));
+    }
     return CPB_OK;
 }
 

@@ -36,6 +36,7 @@ static void usage(void) {
     fprintf(stderr, "--tieEmissions : with --trainEmissions, emissions only distinguish match from mismatch\n");
     fprintf(stderr, "--maxAlignmentLengthToSample N : use at most N bases of alignment, sampled without replacement (default 50000000)\n");
     fprintf(stderr, "--seed N : seed of the random start and of the sampling (default: time)\n");
+    fprintf(stderr, "--gpus N : spread the alignments over the first N GPUs; the expectations are summed with one NCCL all-reduce per iteration (default 1)\n");
     fprintf(stderr, "--diagonalExpansion N, --constraintDiagonalTrim N, --splitMatrixBiggerThanThis N : band options, as cPecanRealign\n");
     fprintf(stderr, "    (defaults: cPecanEm.py's --optionsToRealign, diagonalExpansion 10 and splitMatrixBiggerThanThis 3000)\n");
 }
@@ -173,6 +174,7 @@ int main(int argc, char *argv[]) {
                                            { "diagonalExpansion", required_argument, 0, 'r' },
                                            { "constraintDiagonalTrim", required_argument, 0, 't' },
                                            { "splitMatrixBiggerThanThis", required_argument, 0, 'o' },
+                                           { "gpus", required_argument, 0, 'G' },
                                            { 0, 0, 0, 0 } };
     for (;;) {
         int index = 0;
@@ -202,6 +204,12 @@ int main(int argc, char *argv[]) {
         case 'o': {
             const int64_t side = parse_int(optarg, "--splitMatrixBiggerThanThis");
             p->splitMatrixBiggerThanThis = side * side;
+            break;
+        }
+        case 'G': {
+            const int64_t gpus = parse_int(optarg, "--gpus");
+            if (gpus < 1 || gpus > 16) st_errAbort("cPecanEm: --gpus takes 1 to 16");
+            cpecan_setDevices((int) gpus);
             break;
         }
         default: usage(); return 1;

@@ -36,6 +36,7 @@ static void usage(void) {
     fprintf(stderr, "-v --outputExpectations [FILE] : Instead of realigning, switches to calculating expectations, dumping out expectations as matrix in the given file.\n");
     fprintf(stderr, "-y --loadHmm [FILE] : Loads HMM from given file.\n");
     fprintf(stderr, "-b --batchBases : (int > 0) Bases of sequence per device pass (default 200000000; not in the reference)\n");
+    fprintf(stderr, "--gpus N : spread every device pass over the first N GPUs of the box (default $CPECAN_DEVICES or 1; not in the reference)\n");
 }
 
 static int64_t transform_coordinate(int64_t c, int64_t shift, bool flip, int64_t seqLength) { return shift + (flip ? seqLength - 1 - c : c); }
@@ -256,6 +257,7 @@ int main(int argc, char *argv[]) {
                                            { "outputExpectations", required_argument, 0, 'v' },
                                            { "loadHmm", required_argument, 0, 'y' },
                                            { "batchBases", required_argument, 0, 'b' },
+                                           { "gpus", required_argument, 0, 'G' },
                                            { 0, 0, 0, 0 } };
     for (;;) {
         int index = 0;
@@ -291,6 +293,12 @@ int main(int argc, char *argv[]) {
             batchBases = parse_int(optarg, "--batchBases");
             if (batchBases == 0) st_errAbort("cPecanRealign: --batchBases must be positive");
             break;
+        case 'G': {
+            const int64_t gpus = parse_int(optarg, "--gpus");
+            if (gpus < 1 || gpus > 16) st_errAbort("cPecanRealign: --gpus takes 1 to 16");
+            cpecan_setDevices((int) gpus);
+            break;
+        }
         default: usage(); return 1;
         }
     }

@@ -15,10 +15,22 @@ struct _stList {
     void (*destructElement)(void *);
 };
 
+/*
+ * A tuple is its length followed by its values.  Tuples the library returns by the million (one per aligned pair) do not come from
+ * one malloc each: a whole list's tuples are cut from one slab (cpecan_tripleList_construct).  Such a tuple carries, above the low
+ * byte of `length`, its distance from the start of the slab, so that stIntTuple_destruct -- which callers are entitled to call on any
+ * single tuple, in any order -- finds the slab's count of live tuples and frees the slab with the last one.
+ */
 struct _stIntTuple {
-    int64_t length;
+    int64_t length; /* bits 0..7 the length; bit 62 set: cut from a slab, bits 8..61 = byte offset of this tuple in the slab */
     int64_t values[];
 };
+#define TUPLE_IN_SLAB ((int64_t) 1 << 62)
+#define TUPLE_LENGTH(t) ((t)->length & 0xFF)
+typedef struct {
+    int64_t live;     /* tuples not yet destructed */
+    int64_t reserved; /* keeps the tuples 16-byte aligned */
+} TupleSlab;
 
 void st_errAbort(const char *format, ...) {
     va_list ap;
@@ -143,23 +155,60 @@ stIntTuple *stIntTuple_construct4(int64_t a, int64_t b, int64_t c, int64_t d) {
     return t;
 }
 
-void stIntTuple_destruct(stIntTuple *t) { free(t); }
-int64_t stIntTuple_length(stIntTuple *t) { return t->length; }
+void stIntTuple_destruct(stIntTuple *t) {
+    if (t == NULL) return;
+    if (t->length & TUPLE_IN_SLAB) {
+        TupleSlab *slab = (TupleSlab *) ((char *) t - ((t->length & ~TUPLE_IN_SLAB) >> 8));
+        if (--slab->live == 0) free(slab);
+        return;
+    }
+    free(t);
+}
+int64_t stIntTuple_length(stIntTuple *t) { return TUPLE_LENGTH(t); }
 
 int64_t stIntTuple_get(stIntTuple *t, int64_t i) {
-    if (i < 0 || i >= t->length) st_errAbort("stIntTuple_get: index %lld out of range (length %lld)", (long long) i, (long long) t->length);
+    if (i < 0 || i >= TUPLE_LENGTH(t)) st_errAbort("stIntTuple_get: index %lld out of range (length %lld)", (long long) i, (long long) TUPLE_LENGTH(t));
     return t->values[i];
 }
 
 int stIntTuple_cmpFn(const void *a, const void *b) {
     const stIntTuple *x = a, *y = b;
-    const int64_t n = x->length < y->length ? x->length : y->length;
+    const int64_t lx = TUPLE_LENGTH(x), ly = TUPLE_LENGTH(y), n = lx < ly ? lx : ly;
     for (int64_t i = 0; i < n; i++) {
         if (x->values[i] != y->values[i]) return x->values[i] < y->values[i] ? -1 : 1;
     }
-    return x->length == y->length ? 0 : (x->length < y->length ? -1 : 1);
+    return lx == ly ? 0 : (lx < ly ? -1 : 1);
+}
+
+/* n (pInt, x, y) triples as a list of 3-tuples with destructor stIntTuple_destruct: two allocations instead of n + 2 */
+stList *cpecan_tripleList_construct(const int32_t *triples, int64_t n) {
+    stList *l = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    if (n <= 0) return l;
+    const size_t stride = sizeof(stIntTuple) + 3 * sizeof(int64_t); /* 32 bytes */
+    TupleSlab *slab = xmalloc(sizeof(TupleSlab) + (size_t) n * stride);
+    slab->live = n;
+    slab->reserved = 0;
+    reserve(l, n);
+    char *at = (char *) (slab + 1);
+    for (int64_t i = 0; i < n; i++, at += stride) {
+        stIntTuple *t = (stIntTuple *) at;
+        t->length = 3 | TUPLE_IN_SLAB | ((int64_t) (at - (char *) slab) << 8);
+        t->values[0] = triples[3 * i];
+        t->values[1] = triples[3 * i + 1];
+        t->values[2] = triples[3 * i + 2];
+        l->items[i] = t;
+    }
+    l->length = n;
+    return l;
 }
 
 int stIntTuple_equalsFn(const void *a, const void *b) { return stIntTuple_cmpFn(a, b) == 0; }
 
+#else /* CPECAN_USE_SONLIB: sonLib owns the tuple layout, so the triples become tuples one allocation at a time */
+#include "sonLib.h"
+stList *cpecan_tripleList_construct(const int32_t *triples, int64_t n) {
+    stList *l = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    for (int64_t i = 0; i < n; i++) stList_append(l, stIntTuple_construct3(triples[3 * i], triples[3 * i + 1], triples[3 * i + 2]));
+    return l;
+}
 #endif /* !CPECAN_USE_SONLIB */

@@ -16,4 +16,11 @@ typedef struct {
 const CpbModel *cpecan_model_of(StateMachine *sM);
 void *cpecan_malloc(size_t bytes); /* aborts on failure, like st_malloc */
 
+/* containers.c: n (pInt, x, y) triples as a list of 3-tuples (destructor stIntTuple_destruct), the tuples cut from one slab */
+stList *cpecan_tripleList_construct(const int32_t *triples, int64_t n);
+
+/* pairwiseAligner.c: fn(first, last, arg) over [0, n) on up to $CPECAN_HOST_THREADS (default: the online CPUs, at most 32) threads;
+ * the ranges are contiguous and balanced by weight[i+1] - weight[i] (a prefix-sum array of n + 1 entries) when weight is not NULL */
+void cpecan_parallel_for(int64_t n, const int64_t *weight, void (*fn)(int64_t first, int64_t last, void *arg), void *arg);
+
 #endif

@@ -9,9 +9,11 @@
  * (the reference's own signatures) or many (the *Batch forms).  There is no host implementation of the DP here.
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "cpecan/pairwiseAligner.h"
 #include "cpecan_b200.h"
@@ -24,6 +26,69 @@ void *cpecan_malloc(size_t bytes) {
     void *p = malloc(bytes ? bytes : 1);
     if (p == NULL) st_errAbort("cpecan: out of memory allocating %zu bytes", bytes);
     return p;
+}
+
+/* ------------------------------------------------------------------------- host threads for the marshalling */
+
+/* The reference's interface hands every aligned pair over as a heap tuple in a list: for a batch of 100 000 x 1 kb pairs that is 1e8
+ * tuples in and out of the call, which a single thread needs seconds for while the device pass takes one.  Problems are independent,
+ * so the conversions run on a few host threads over contiguous ranges of problems. */
+typedef struct {
+    void (*fn)(int64_t, int64_t, void *);
+    void *arg;
+    int64_t first, last;
+} ParallelTask;
+
+static void *parallel_entry(void *v) {
+    ParallelTask *t = v;
+    t->fn(t->first, t->last, t->arg);
+    return NULL;
+}
+
+void cpecan_parallel_for(int64_t n, const int64_t *weight, void (*fn)(int64_t first, int64_t last, void *arg), void *arg) {
+    long threads = sysconf(_SC_NPROCESSORS_ONLN);
+    const char *e = getenv("CPECAN_HOST_THREADS");
+    if (e != NULL) threads = atol(e);
+    if (threads > 32) threads = 32;
+    const int64_t total = weight != NULL ? weight[n] - weight[0] : n;
+    if (threads > n) threads = (long) n;
+    if (threads <= 1 || total < 200000) { /* not worth a thread */
+        if (n > 0) fn(0, n, arg);
+        return;
+    }
+    ParallelTask tasks[32];
+    pthread_t ids[32];
+    int64_t at = 0;
+    int started = 0;
+    for (long t = 0; t < threads; t++) {
+        int64_t end = n;
+        if (t + 1 < threads) {
+            if (weight == NULL) {
+                end = n * (t + 1) / threads;
+            } else { /* first index whose prefix weight reaches this thread's share */
+                const int64_t want = weight[0] + total * (t + 1) / threads;
+                int64_t lo = at, hi = n;
+                while (lo < hi) {
+                    const int64_t mid = lo + (hi - lo) / 2;
+                    if (weight[mid] < want) lo = mid + 1;
+                    else hi = mid;
+                }
+                end = lo;
+            }
+        }
+        if (end <= at) continue;
+        tasks[started].fn = fn;
+        tasks[started].arg = arg;
+        tasks[started].first = at;
+        tasks[started].last = end;
+        if (pthread_create(&ids[started], NULL, parallel_entry, &tasks[started]) != 0) { /* no thread: do the range here */
+            fn(at, end, arg);
+        } else {
+            started++;
+        }
+        at = end;
+    }
+    for (int t = 0; t < started; t++) pthread_join(ids[t], NULL);
 }
 
 /* ------------------------------------------------------------------------------------ parameters */
@@ -113,19 +178,71 @@ static void to_engine_params(const PairwiseAlignmentParameters *p, CpbParams *q)
 
 /* --------------------------------------------------------------------------------- device context */
 
-static cpb_context *g_ctx = NULL;
-static int g_device = -1;
+/* The devices this process computes on: one engine context (stream, buffer pools) per GPU, created on first use.  One device by
+ * default ($CPECAN_DEVICE or 0); cpecan_setDevices(n) or $CPECAN_DEVICES=n spreads every batch over the first n GPUs.  The library is
+ * single threaded towards its callers, as the reference's callers are; inside a call it runs one host thread
+ * per device. */
+#define CPECAN_MAX_DEVICES 16
+static cpb_context *g_ctx[CPECAN_MAX_DEVICES];
+static int g_devices[CPECAN_MAX_DEVICES];
+static int g_nDevices = 0; /* 0: not chosen yet */
+static int64_t g_liveResidentBatches = 0;
 static CpecanAnchorProvider g_anchorProvider = NULL;
 static void *g_anchorExtra = NULL;
 
+static int any_context(void) {
+    for (int i = 0; i < CPECAN_MAX_DEVICES; i++)
+        if (g_ctx[i] != NULL) return 1;
+    return 0;
+}
+
 void cpecan_setDevice(int device) {
-    if (g_ctx != NULL && device != g_device) st_errAbort("cpecan_setDevice: the device context already exists on device %d", g_device);
-    g_device = device;
+    if (any_context() && !(g_nDevices == 1 && g_devices[0] == device)) st_errAbort("cpecan_setDevice: device contexts already exist; call cpecan_shutdown first");
+    g_nDevices = 1;
+    g_devices[0] = device;
+}
+
+void cpecan_setDevices(int n) {
+    if (n < 1 || n > CPECAN_MAX_DEVICES) st_errAbort("cpecan_setDevices: %d devices asked for (1 to %d)", n, CPECAN_MAX_DEVICES);
+    if (any_context() && g_nDevices != n) st_errAbort("cpecan_setDevices: device contexts already exist; call cpecan_shutdown first");
+    g_nDevices = n;
+    for (int i = 0; i < n; i++) g_devices[i] = i;
+}
+
+void cpecan_setDeviceList(const int *devices, int n) {
+    if (n < 1 || n > CPECAN_MAX_DEVICES) st_errAbort("cpecan_setDeviceList: %d devices asked for (1 to %d)", n, CPECAN_MAX_DEVICES);
+    if (any_context()) st_errAbort("cpecan_setDeviceList: device contexts already exist; call cpecan_shutdown first");
+    g_nDevices = n;
+    for (int i = 0; i < n; i++) g_devices[i] = devices[i];
+}
+
+int cpecan_getDeviceCount(void) {
+    if (g_nDevices == 0) {
+        const char *list = getenv("CPECAN_DEVICE_LIST"), *many = getenv("CPECAN_DEVICES"), *one = getenv("CPECAN_DEVICE");
+        if (list != NULL && *list != '\0') { /* "0,1,2": explicit ordinals; one may appear twice (two contexts on one GPU, for tests) */
+            int devices[CPECAN_MAX_DEVICES], n = 0;
+            for (const char *q = list; *q != '\0' && n < CPECAN_MAX_DEVICES;) {
+                devices[n++] = atoi(q);
+                while (*q != '\0' && *q != ',') q++;
+                if (*q == ',') q++;
+            }
+            cpecan_setDeviceList(devices, n);
+        } else if (many != NULL && atoi(many) > 1) {
+            cpecan_setDevices(atoi(many));
+        } else {
+            cpecan_setDevice(one != NULL ? atoi(one) : 0);
+        }
+    }
+    return g_nDevices;
 }
 
 void cpecan_shutdown(void) {
-    if (g_ctx != NULL) cpb_context_destroy(g_ctx);
-    g_ctx = NULL;
+    if (g_liveResidentBatches > 0)
+        st_errAbort("cpecan_shutdown: %lld resident batches still hold device memory of the contexts; destruct them first", (long long) g_liveResidentBatches);
+    for (int i = 0; i < CPECAN_MAX_DEVICES; i++) {
+        if (g_ctx[i] != NULL) cpb_context_destroy(g_ctx[i]);
+        g_ctx[i] = NULL;
+    }
 }
 
 void cpecan_setAnchorProvider(CpecanAnchorProvider provider, void *extra) {
@@ -133,17 +250,16 @@ void cpecan_setAnchorProvider(CpecanAnchorProvider provider, void *extra) {
     g_anchorExtra = extra;
 }
 
-static cpb_context *context(void) {
-    if (g_ctx == NULL) {
-        if (g_device < 0) {
-            const char *e = getenv("CPECAN_DEVICE");
-            g_device = e != NULL ? atoi(e) : 0;
-        }
-        if (cpb_context_create(g_device, NULL, &g_ctx) != CPB_OK)
-            st_errAbort("cpecan: cannot use CUDA device %d: %s (this library has no CPU implementation of the pair-HMM)", g_device, cpb_last_error());
+/* called from the calling thread only (before the per-device threads start), so creation needs no lock */
+static cpb_context *context_of(int slot) {
+    cpecan_getDeviceCount();
+    if (g_ctx[slot] == NULL) {
+        if (cpb_context_create(g_devices[slot], NULL, &g_ctx[slot]) != CPB_OK)
+            st_errAbort("cpecan: cannot use CUDA device %d: %s (this library has no CPU implementation of the pair-HMM)", g_devices[slot], cpb_last_error());
     }
-    return g_ctx;
+    return g_ctx[slot];
 }
+static cpb_context *context(void) { return context_of(0); }
 
 /* ----------------------------------------------------------------------------- batch marshalling */
 
@@ -163,6 +279,31 @@ static void packed_free(Packed *k) {
     free(k->anchors);
     free(k->rl);
     free(k->rr);
+}
+
+typedef struct {
+    Packed *k;
+    const char *const *sX, *const *sY;
+    stList *const *anchorPairs;
+    int64_t defaultExpansion;
+} PackJob;
+
+static void pack_range(int64_t first, int64_t last, void *arg) {
+    PackJob *j = arg;
+    Packed *k = j->k;
+    for (int64_t i = first; i < last; i++) {
+        memcpy(k->seqX + k->xOff[i], j->sX[i], (size_t) (k->xOff[i + 1] - k->xOff[i]));
+        memcpy(k->seqY + k->yOff[i], j->sY[i], (size_t) (k->yOff[i + 1] - k->yOff[i]));
+        const int64_t nA = k->aOff[i + 1] - k->aOff[i];
+        for (int64_t a = 0; a < nA; a++) {
+            stIntTuple *t = stList_get(j->anchorPairs[i], a);
+            int64_t *out = k->anchors + 3 * (k->aOff[i] + a);
+            out[0] = stIntTuple_get(t, 0);
+            out[1] = stIntTuple_get(t, 1);
+            /* anchors are (x, y, expansion); two-element tuples (as the reference's tests build them) use p->diagonalExpansion */
+            out[2] = stIntTuple_length(t) > 2 ? stIntTuple_get(t, 2) : j->defaultExpansion;
+        }
+    }
 }
 
 static void pack(Packed *k, int64_t n, const char *const *sX, const char *const *sY, stList *const *anchorPairs, const bool *raggedLeft,
@@ -185,24 +326,12 @@ static void pack(Packed *k, int64_t n, const char *const *sX, const char *const 
     k->seqX = cpecan_malloc((size_t) k->xOff[n] + 1);
     k->seqY = cpecan_malloc((size_t) k->yOff[n] + 1);
     k->anchors = cpecan_malloc((size_t) (3 * k->aOff[n] + 3) * sizeof(int64_t));
-    for (int64_t i = 0; i < n; i++) {
-        memcpy(k->seqX + k->xOff[i], sX[i], (size_t) (k->xOff[i + 1] - k->xOff[i]));
-        memcpy(k->seqY + k->yOff[i], sY[i], (size_t) (k->yOff[i + 1] - k->yOff[i]));
-        const int64_t nA = k->aOff[i + 1] - k->aOff[i];
-        for (int64_t a = 0; a < nA; a++) {
-            stIntTuple *t = stList_get(anchorPairs[i], a);
-            int64_t *out = k->anchors + 3 * (k->aOff[i] + a);
-            out[0] = stIntTuple_get(t, 0);
-            out[1] = stIntTuple_get(t, 1);
-            /* anchors are (x, y, expansion); two-element tuples (as the reference's tests build them) use p->diagonalExpansion */
-            out[2] = stIntTuple_length(t) > 2 ? stIntTuple_get(t, 2) : defaultExpansion;
-        }
-    }
+    PackJob job = { k, sX, sY, anchorPairs, defaultExpansion };
+    cpecan_parallel_for(n, k->aOff, pack_range, &job);
 }
 
 /* runs one engine pass over the packed problems; aborts with the engine's message on failure (the reference has no error codes either) */
-static cpb_batch *run(Packed *k, StateMachine *sM, PairwiseAlignmentParameters *p, int mode) {
-    cpb_context *ctx = context();
+static cpb_batch *run(cpb_context *ctx, Packed *k, StateMachine *sM, PairwiseAlignmentParameters *p, int mode) {
     cpb_batch *b = NULL;
     if (cpb_batch_create(ctx, k->n, k->seqX, k->xOff, k->seqY, k->yOff, k->anchors, k->aOff, k->rl, k->rr, &b) != CPB_OK)
         st_errAbort("cpecan: %s", cpb_last_error());
@@ -215,6 +344,17 @@ static cpb_batch *run(Packed *k, StateMachine *sM, PairwiseAlignmentParameters *
 }
 
 /* list `which` of the last run as n stLists of (pInt, x, y) tuples */
+typedef struct {
+    stList **lists;
+    const int64_t *off;
+    const int32_t *tri;
+} ListJob;
+
+static void lists_range(int64_t first, int64_t last, void *arg) {
+    ListJob *j = arg;
+    for (int64_t i = first; i < last; i++) j->lists[i] = cpecan_tripleList_construct(j->tri + 3 * j->off[i], j->off[i + 1] - j->off[i]);
+}
+
 static stList **fetch_lists(cpb_batch *b, int64_t n, int which) {
     const int64_t total = cpb_batch_result_count(b, which);
     int64_t *off = cpecan_malloc((size_t) (n + 1) * sizeof(int64_t));
@@ -222,10 +362,8 @@ static stList **fetch_lists(cpb_batch *b, int64_t n, int which) {
     /* same list order as the reference's own lists (its callers may depend on it, e.g. the MEA walk-back) */
     if (cpb_batch_fetch_pairs_reference_order(b, which, off, tri) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
     stList **lists = cpecan_malloc((size_t) (n > 0 ? n : 1) * sizeof(stList *));
-    for (int64_t i = 0; i < n; i++) {
-        lists[i] = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
-        for (int64_t t = off[i]; t < off[i + 1]; t++) stList_append(lists[i], stIntTuple_construct3(tri[3 * t], tri[3 * t + 1], tri[3 * t + 2]));
-    }
+    ListJob job = { lists, off, tri };
+    cpecan_parallel_for(n, off, lists_range, &job);
     free(off);
     free(tri);
     return lists;
@@ -233,42 +371,227 @@ static stList **fetch_lists(cpb_batch *b, int64_t n, int which) {
 
 /* ------------------------------------------------------------------------------- batched entries */
 
+/*
+ * One batch over the device set.  Problems are independent, so they are dealt to the devices by longest-processing-time-first on an
+ * estimate of their band cells (diagonals x (mean anchor gap + expansion)): the most expensive problem goes to the least loaded
+ * device, and so on down the list.  Every device then gets one host thread that marshals its share, runs the engine pass on its own
+ * context and stream, and writes its results into the caller's arrays at the problems' own indices -- no data-path traffic between
+ * GPUs.  The only exchange is the EM reduction of the expectation totals (cpb_expectations_allreduce, NCCL).
+ */
+typedef struct {
+    int slot;
+    cpb_context *ctx;
+    int64_t n;          /* problems of this device */
+    const int64_t *idx; /* their indices in the caller's arrays, ascending */
+    /* the call */
+    StateMachine *sM;
+    PairwiseAlignmentParameters *p;
+    int mode, reweight, keepBatch;
+    double gapGamma;
+    const char *const *sX, *const *sY;
+    stList *const *anchorPairs;
+    const bool *raggedLeft, *raggedRight;
+    /* results, in the caller's indexing */
+    stList **lists[3];
+    double *logProbs;
+    cpb_batch *batch; /* expectation mode / keepBatch: left alive for the reduction */
+} DeviceJob;
+
+static void *device_job(void *v) {
+    DeviceJob *j = v;
+    const int64_t n = j->n;
+    const char **sX = cpecan_malloc((size_t) (n + 1) * sizeof(char *)), **sY = cpecan_malloc((size_t) (n + 1) * sizeof(char *));
+    stList **an = cpecan_malloc((size_t) (n + 1) * sizeof(stList *));
+    bool *rl = cpecan_malloc((size_t) n + 1), *rr = cpecan_malloc((size_t) n + 1);
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t g = j->idx != NULL ? j->idx[i] : i;
+        sX[i] = j->sX[g];
+        sY[i] = j->sY[g];
+        an[i] = j->anchorPairs != NULL ? j->anchorPairs[g] : NULL;
+        rl[i] = j->raggedLeft != NULL && j->raggedLeft[g];
+        rr[i] = j->raggedRight != NULL && j->raggedRight[g];
+    }
+    Packed k;
+    pack(&k, n, sX, sY, an, rl, rr, j->p->diagonalExpansion);
+    cpb_batch *b = NULL;
+    if (j->mode < 0) { /* resident batch: inputs to the device, no run yet */
+        if (cpb_batch_create(j->ctx, k.n, k.seqX, k.xOff, k.seqY, k.yOff, k.anchors, k.aOff, k.rl, k.rr, &b) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
+    } else {
+        b = run(j->ctx, &k, j->sM, j->p, j->mode);
+    }
+    if (j->mode == CPB_MODE_ALIGNED_PAIRS || j->mode == CPB_MODE_ALIGNED_PAIRS_INDELS) {
+        if (j->reweight && cpb_batch_reweight_pairs(b, j->gapGamma) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
+        const int nLists = j->mode == CPB_MODE_ALIGNED_PAIRS ? 1 : 3;
+        for (int l = 0; l < nLists; l++) {
+            stList **mine = fetch_lists(b, n, l);
+            for (int64_t i = 0; i < n; i++) j->lists[l][j->idx != NULL ? j->idx[i] : i] = mine[i];
+            free(mine);
+        }
+    } else if (j->mode == CPB_MODE_FORWARD) {
+        double *lp = cpecan_malloc((size_t) (n + 1) * sizeof(double));
+        if (cpb_batch_fetch_forward(b, lp) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
+        for (int64_t i = 0; i < n; i++) j->logProbs[j->idx != NULL ? j->idx[i] : i] = lp[i];
+        free(lp);
+    }
+    if (j->mode == CPB_MODE_EXPECTATIONS || j->keepBatch) j->batch = b;
+    else cpb_batch_destroy(b);
+    packed_free(&k);
+    free(sX);
+    free(sY);
+    free(an);
+    free(rl);
+    free(rr);
+    return NULL;
+}
+
+/* longest-processing-time-first: idx[d] / count[d] = the problems of device d, ascending */
+typedef struct {
+    int64_t cost, index;
+} CostItem;
+static int cost_descending(const void *a, const void *b) {
+    const CostItem *x = a, *y = b;
+    if (x->cost != y->cost) return x->cost > y->cost ? -1 : 1;
+    return x->index < y->index ? -1 : (x->index > y->index ? 1 : 0);
+}
+static int index_ascending(const void *a, const void *b) {
+    const int64_t x = *(const int64_t *) a, y = *(const int64_t *) b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+static void deal_problems(int64_t n, const char *const *sX, const char *const *sY, stList *const *anchorPairs, int64_t expansion, int nDev, int64_t **idx,
+                          int64_t *count) {
+    CostItem *items = cpecan_malloc((size_t) (n + 1) * sizeof(CostItem));
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t lX = (int64_t) strlen(sX[i]), lY = (int64_t) strlen(sY[i]);
+        const int64_t nA = anchorPairs != NULL && anchorPairs[i] != NULL ? stList_length(anchorPairs[i]) : 0;
+        int64_t gap = (lX + lY) / (2 * (nA + 1)), cap = (lX < lY ? lX : lY) + 1;
+        if (gap > cap) gap = cap;
+        items[i].cost = (lX + lY + 1) * (gap + expansion + 1);
+        items[i].index = i;
+    }
+    qsort(items, (size_t) n, sizeof(CostItem), cost_descending);
+    int64_t load[CPECAN_MAX_DEVICES];
+    for (int d = 0; d < nDev; d++) {
+        idx[d] = cpecan_malloc((size_t) (n + 1) * sizeof(int64_t));
+        count[d] = 0;
+        load[d] = 0;
+    }
+    for (int64_t i = 0; i < n; i++) {
+        int best = 0;
+        for (int d = 1; d < nDev; d++)
+            if (load[d] < load[best]) best = d;
+        idx[best][count[best]++] = items[i].index;
+        load[best] += items[i].cost;
+    }
+    for (int d = 0; d < nDev; d++) qsort(idx[d], (size_t) count[d], sizeof(int64_t), index_ascending);
+    free(items);
+}
+
+/* runs `proto` (the call's arguments) over the device set; jobs[] keeps the per-device state for the caller (batches of expectation runs) */
+static int run_on_devices(DeviceJob *proto, int64_t n, DeviceJob *jobs, int64_t **idxOut) {
+    const int nDev = (int) (cpecan_getDeviceCount() < n ? cpecan_getDeviceCount() : (n > 0 ? n : 1));
+    int64_t *idx[CPECAN_MAX_DEVICES], count[CPECAN_MAX_DEVICES];
+    if (nDev <= 1) {
+        jobs[0] = *proto;
+        jobs[0].slot = 0;
+        jobs[0].ctx = context_of(0);
+        jobs[0].n = n;
+        jobs[0].idx = NULL;
+        device_job(&jobs[0]);
+        if (idxOut != NULL) idxOut[0] = NULL;
+        return 1;
+    }
+    deal_problems(n, proto->sX, proto->sY, proto->anchorPairs, proto->p->diagonalExpansion, nDev, idx, count);
+    pthread_t ids[CPECAN_MAX_DEVICES];
+    for (int d = 0; d < nDev; d++) {
+        jobs[d] = *proto;
+        jobs[d].slot = d;
+        jobs[d].ctx = context_of(d); /* created here, in the calling thread */
+        jobs[d].n = count[d];
+        jobs[d].idx = idx[d];
+    }
+    for (int d = 0; d < nDev; d++)
+        if (pthread_create(&ids[d], NULL, device_job, &jobs[d]) != 0) st_errAbort("cpecan: cannot start the host thread of device %d", g_devices[d]);
+    for (int d = 0; d < nDev; d++) pthread_join(ids[d], NULL);
+    for (int d = 0; d < nDev; d++) {
+        if (idxOut != NULL) idxOut[d] = idx[d];
+        else free(idx[d]);
+    }
+    return nDev;
+}
+
+static DeviceJob job_of(StateMachine *sM, const char *const *sX, const char *const *sY, stList *const *anchorPairs, PairwiseAlignmentParameters *p,
+                        const bool *raggedLeft, const bool *raggedRight, int mode) {
+    DeviceJob j;
+    memset(&j, 0, sizeof(j));
+    j.sM = sM;
+    j.p = p;
+    j.mode = mode;
+    j.sX = sX;
+    j.sY = sY;
+    j.anchorPairs = anchorPairs;
+    j.raggedLeft = raggedLeft;
+    j.raggedRight = raggedRight;
+    return j;
+}
+
+static stList **new_list_array(int64_t n) {
+    stList **l = cpecan_malloc((size_t) (n > 0 ? n : 1) * sizeof(stList *));
+    memset(l, 0, (size_t) (n > 0 ? n : 1) * sizeof(stList *));
+    return l;
+}
+
 stList **getAlignedPairsUsingAnchorsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY,
                                           stList *const *anchorPairs, PairwiseAlignmentParameters *p, const bool *raggedLeft,
                                           const bool *raggedRight) {
-    Packed k;
-    pack(&k, n, sX, sY, anchorPairs, raggedLeft, raggedRight, p->diagonalExpansion);
-    cpb_batch *b = run(&k, sM, p, CPB_MODE_ALIGNED_PAIRS);
-    stList **lists = fetch_lists(b, n, 0);
-    cpb_batch_destroy(b);
-    packed_free(&k);
-    return lists;
+    DeviceJob proto = job_of(sM, sX, sY, anchorPairs, p, raggedLeft, raggedRight, CPB_MODE_ALIGNED_PAIRS), jobs[CPECAN_MAX_DEVICES];
+    proto.lists[0] = new_list_array(n);
+    run_on_devices(&proto, n, jobs, NULL);
+    return proto.lists[0];
 }
 
 stList **getReweightedAlignedPairsUsingAnchorsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY,
                                                     stList *const *anchorPairs, PairwiseAlignmentParameters *p, const bool *raggedLeft,
                                                     const bool *raggedRight, double gapGamma) {
-    Packed k;
-    pack(&k, n, sX, sY, anchorPairs, raggedLeft, raggedRight, p->diagonalExpansion);
-    cpb_batch *b = run(&k, sM, p, CPB_MODE_ALIGNED_PAIRS);
-    if (cpb_batch_reweight_pairs(b, gapGamma) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
-    stList **lists = fetch_lists(b, n, 0);
-    cpb_batch_destroy(b);
-    packed_free(&k);
-    return lists;
+    DeviceJob proto = job_of(sM, sX, sY, anchorPairs, p, raggedLeft, raggedRight, CPB_MODE_ALIGNED_PAIRS), jobs[CPECAN_MAX_DEVICES];
+    proto.lists[0] = new_list_array(n);
+    proto.reweight = 1;
+    proto.gapGamma = gapGamma;
+    run_on_devices(&proto, n, jobs, NULL);
+    return proto.lists[0];
 }
 
 void getAlignedPairsWithIndelsUsingAnchorsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY,
                                                 stList *const *anchorPairs, PairwiseAlignmentParameters *p, stList ***alignedPairs,
                                                 stList ***gapXPairs, stList ***gapYPairs, const bool *raggedLeft, const bool *raggedRight) {
-    Packed k;
-    pack(&k, n, sX, sY, anchorPairs, raggedLeft, raggedRight, p->diagonalExpansion);
-    cpb_batch *b = run(&k, sM, p, CPB_MODE_ALIGNED_PAIRS_INDELS);
-    *alignedPairs = fetch_lists(b, n, 0);
-    *gapXPairs = fetch_lists(b, n, 1);
-    *gapYPairs = fetch_lists(b, n, 2);
-    cpb_batch_destroy(b);
-    packed_free(&k);
+    DeviceJob proto = job_of(sM, sX, sY, anchorPairs, p, raggedLeft, raggedRight, CPB_MODE_ALIGNED_PAIRS_INDELS), jobs[CPECAN_MAX_DEVICES];
+    for (int l = 0; l < 3; l++) proto.lists[l] = new_list_array(n);
+    run_on_devices(&proto, n, jobs, NULL);
+    *alignedPairs = proto.lists[0];
+    *gapXPairs = proto.lists[1];
+    *gapYPairs = proto.lists[2];
+}
+
+/* the expectation totals of nDev finished expectation runs, summed: NCCL all-reduce across the devices when there are several (every
+ * device then holds the sum; device 0's copy is read), else the one total as it is */
+static void add_expectations(Hmm *hmmExpectations, int64_t S, cpb_batch **batches, int nDev) {
+    double total[CPB_HMM_LEN(5)];
+    if (nDev > 1 && cpb_expectations_allreduce(batches, nDev) != CPB_OK) {
+        /* no NCCL in this process: the 58 / 106 doubles per device are added up here instead (in device order) */
+        static int told = 0;
+        if (!told) fprintf(stderr, "cpecan: %s; summing the expectation totals of the %d devices on the host\n", cpb_last_error(), nDev);
+        told = 1;
+        double part[CPB_HMM_LEN(5)];
+        memset(total, 0, sizeof(total));
+        for (int d = 0; d < nDev; d++) {
+            if (cpb_batch_fetch_expectations(batches[d], NULL, part) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
+            for (int64_t i = 0; i < CPB_HMM_LEN(S); i++) total[i] += part[i];
+        }
+    } else if (cpb_batch_fetch_expectations(batches[0], NULL, total) != CPB_OK) {
+        st_errAbort("cpecan: %s", cpb_last_error());
+    }
+    for (int64_t i = 0; i < S * S; i++) hmmExpectations->transitions[i] += total[i];
+    for (int64_t i = 0; i < S * 16; i++) hmmExpectations->emissions[i] += total[S * S + i];
+    hmmExpectations->likelihood += total[S * S + S * 16];
 }
 
 void getExpectationsUsingAnchorsBatch(StateMachine *sM, Hmm *hmmExpectations, int64_t n, const char *const *sX, const char *const *sY,
@@ -277,43 +600,53 @@ void getExpectationsUsingAnchorsBatch(StateMachine *sM, Hmm *hmmExpectations, in
     if (hmmExpectations->stateNumber != sM->stateNumber)
         st_errAbort("getExpectations: the Hmm has %lld states, the state machine %lld", (long long) hmmExpectations->stateNumber,
                     (long long) sM->stateNumber);
-    Packed k;
-    pack(&k, n, sX, sY, anchorPairs, raggedLeft, raggedRight, p->diagonalExpansion);
-    cpb_batch *b = run(&k, sM, p, CPB_MODE_EXPECTATIONS);
-    const int64_t S = sM->stateNumber;
-    double total[CPB_HMM_LEN(5)];
-    if (cpb_batch_fetch_expectations(b, NULL, total) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
-    for (int64_t i = 0; i < S * S; i++) hmmExpectations->transitions[i] += total[i];
-    for (int64_t i = 0; i < S * 16; i++) hmmExpectations->emissions[i] += total[S * S + i];
-    hmmExpectations->likelihood += total[S * S + S * 16];
-    cpb_batch_destroy(b);
-    packed_free(&k);
+    DeviceJob proto = job_of(sM, sX, sY, anchorPairs, p, raggedLeft, raggedRight, CPB_MODE_EXPECTATIONS), jobs[CPECAN_MAX_DEVICES];
+    const int nDev = run_on_devices(&proto, n, jobs, NULL);
+    cpb_batch *batches[CPECAN_MAX_DEVICES];
+    for (int d = 0; d < nDev; d++) batches[d] = jobs[d].batch;
+    add_expectations(hmmExpectations, sM->stateNumber, batches, nDev);
+    for (int d = 0; d < nDev; d++) cpb_batch_destroy(batches[d]);
 }
 
-/* ---- resident batches: the inputs go to the device once, every EM iteration is one more pass with a new model ---- */
+/* ---- resident batches: the inputs go to the devices once, every EM iteration is one more pass with a new model ---- */
 
 struct _cpecanResidentBatch {
-    cpb_batch *b;
+    cpb_batch *b[CPECAN_MAX_DEVICES];
+    int nDev;
     int64_t n;
 };
 
 CpecanResidentBatch *cpecanResidentBatch_construct(int64_t n, const char *const *sX, const char *const *sY, stList *const *anchorPairs,
                                                    PairwiseAlignmentParameters *p, const bool *raggedLeft, const bool *raggedRight) {
-    Packed k;
-    pack(&k, n, sX, sY, anchorPairs, raggedLeft, raggedRight, p->diagonalExpansion);
+    DeviceJob proto = job_of(NULL, sX, sY, anchorPairs, p, raggedLeft, raggedRight, -1), jobs[CPECAN_MAX_DEVICES];
+    proto.keepBatch = 1;
     CpecanResidentBatch *r = cpecan_malloc(sizeof(*r));
+    memset(r, 0, sizeof(*r));
     r->n = n;
-    r->b = NULL;
-    if (cpb_batch_create(context(), k.n, k.seqX, k.xOff, k.seqY, k.yOff, k.anchors, k.aOff, k.rl, k.rr, &r->b) != CPB_OK)
-        st_errAbort("cpecan: %s", cpb_last_error());
-    packed_free(&k);
+    r->nDev = run_on_devices(&proto, n, jobs, NULL);
+    for (int d = 0; d < r->nDev; d++) r->b[d] = jobs[d].batch;
+    g_liveResidentBatches++;
     return r;
 }
 
 void cpecanResidentBatch_destruct(CpecanResidentBatch *r) {
     if (r == NULL) return;
-    cpb_batch_destroy(r->b);
+    for (int d = 0; d < r->nDev; d++) cpb_batch_destroy(r->b[d]);
+    g_liveResidentBatches--;
     free(r);
+}
+
+typedef struct {
+    cpb_batch *b;
+    const CpbModel *model;
+    const CpbParams *q;
+} ResidentRun;
+static void *resident_run(void *v) {
+    ResidentRun *r = v;
+    const int rc = cpb_batch_run(r->b, r->model, r->q, CPB_MODE_EXPECTATIONS);
+    if (rc == CPB_ERR_BAND) st_errAbort("%s: %s", PAIRWISE_ALIGNMENT_EXCEPTION_ID, cpb_last_error());
+    if (rc != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
+    return NULL;
 }
 
 void cpecanResidentBatch_getExpectations(CpecanResidentBatch *r, StateMachine *sM, Hmm *hmmExpectations, PairwiseAlignmentParameters *p) {
@@ -322,25 +655,28 @@ void cpecanResidentBatch_getExpectations(CpecanResidentBatch *r, StateMachine *s
                     (long long) sM->stateNumber);
     CpbParams q;
     to_engine_params(p, &q);
-    const int rc = cpb_batch_run(r->b, cpecan_model_of(sM), &q, CPB_MODE_EXPECTATIONS);
-    if (rc == CPB_ERR_BAND) st_errAbort("%s: %s", PAIRWISE_ALIGNMENT_EXCEPTION_ID, cpb_last_error());
-    if (rc != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
-    const int64_t S = sM->stateNumber;
-    double total[CPB_HMM_LEN(5)];
-    if (cpb_batch_fetch_expectations(r->b, NULL, total) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
-    for (int64_t i = 0; i < S * S; i++) hmmExpectations->transitions[i] += total[i];
-    for (int64_t i = 0; i < S * 16; i++) hmmExpectations->emissions[i] += total[S * S + i];
-    hmmExpectations->likelihood += total[S * S + S * 16];
+    ResidentRun runs[CPECAN_MAX_DEVICES];
+    pthread_t ids[CPECAN_MAX_DEVICES];
+    for (int d = 0; d < r->nDev; d++) {
+        runs[d].b = r->b[d];
+        runs[d].model = cpecan_model_of(sM);
+        runs[d].q = &q;
+    }
+    if (r->nDev == 1) {
+        resident_run(&runs[0]);
+    } else {
+        for (int d = 0; d < r->nDev; d++)
+            if (pthread_create(&ids[d], NULL, resident_run, &runs[d]) != 0) st_errAbort("cpecan: cannot start a host thread");
+        for (int d = 0; d < r->nDev; d++) pthread_join(ids[d], NULL);
+    }
+    add_expectations(hmmExpectations, sM->stateNumber, r->b, r->nDev);
 }
 
 void computeForwardProbabilityBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY, stList *const *anchorPairs,
                                     PairwiseAlignmentParameters *p, const bool *raggedLeft, const bool *raggedRight, double *logProbs) {
-    Packed k;
-    pack(&k, n, sX, sY, anchorPairs, raggedLeft, raggedRight, p->diagonalExpansion);
-    cpb_batch *b = run(&k, sM, p, CPB_MODE_FORWARD);
-    if (cpb_batch_fetch_forward(b, logProbs) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
-    cpb_batch_destroy(b);
-    packed_free(&k);
+    DeviceJob proto = job_of(sM, sX, sY, anchorPairs, p, raggedLeft, raggedRight, CPB_MODE_FORWARD), jobs[CPECAN_MAX_DEVICES];
+    proto.logProbs = logProbs;
+    run_on_devices(&proto, n, jobs, NULL);
 }
 
 /* ---------------------------------------------------------------- the reference's one-pair forms */

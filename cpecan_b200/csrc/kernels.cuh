@@ -301,7 +301,7 @@ __device__ __forceinline__ double log_add(double x, double y, const LaTable la) 
 #define CPB_FWD_MIN_BLOCKS CPB_STRIP_MIN_BLOCKS
 #endif
 #ifndef CPB_BWD_MIN_BLOCKS
-#define CPB_BWD_MIN_BLOCKS CPB_STRIP_MIN_BLOCKS
+#define CPB_BWD_MIN_BLOCKS 6 /* backward gains 8 % from 24 resident warps per SM (80 registers); forward loses 5 %: it keeps 128 registers */
 #endif
 
 /* ---------------------------------------------------------------------------------------------
@@ -434,27 +434,44 @@ __global__ void __launch_bounds__(128) k_totals(const DpArgs a, int nBlocks) {
  * ------------------------------------------------------------------------------------------- */
 constexpr int POST_WARPS = 8;
 
-struct PostArgs {
-    double threshold;
-    double logThresholdLo;   /* log(threshold) minus a safety margin: cells below it cannot pass p >= threshold */
-    int32_t nLists;          /* 1 or 3 */
+/* A kept cell whose integer weight floor(p * 1e7) is not safe against the last-place difference between this device's exp and the
+ * host's libm (the reference computes p with libm): the host recomputes it from the exact log-probability and patches the triple. */
+struct PintFixup {
+    double lp;    /* (F.M + B.M) - total, bit-identical to the reference's argument of exp */
+    int64_t pos;  /* triple index in the output list */
+    int32_t list; /* 0 match, 1 gap X, 2 gap Y */
     int32_t pad_;
+};
+
+struct PostArgs {
+    double logThreshold;     /* smallest log-probability lp with exp(lp) >= threshold under the HOST's libm (host bisection, engine.cu):
+                              * the keep decision is a comparison in log space, so it cannot differ from the reference's p >= threshold */
+    double pintTolerance;    /* distance of p * 1e7 from an integer below which the host recomputes the weight (2e-8: three times the worst
+                              * case of a 1-ulp device exp against a 1-ulp libm exp) */
+    int32_t nLists;          /* 1 or 3 */
+    int32_t fixupCap;
     int64_t nDecades;        /* decades in this chunk (stride between lists in counts/offsets) */
     int64_t maskWords;       /* mask words per list */
     int32_t *counts;         /* [nLists][nDecades] */
     const int64_t *offsets;  /* [nLists][nDecades] exclusive, global (WRITE) */
     uint32_t *masks;         /* [nLists][maskWords] */
     int32_t *out[3];
+    unsigned int *fixupCount; /* WRITE: number of PintFixup records requested (may exceed fixupCap: the host then reports it) */
+    PintFixup *fixups;
 };
 
-__device__ __forceinline__ bool posterior_keep(double z, double total, const PostArgs &p, int &pInt) {
-    const double lp = z - total;
-    if (!(lp >= p.logThresholdLo)) return false;
+/* addPosteriorProb's test (impl/pairwiseAligner.c:656): p >= threshold, decided in log space (see PostArgs.logThreshold) */
+__device__ __forceinline__ bool posterior_keep(double z, double total, const PostArgs &p) { return z - total >= p.logThreshold; }
+/* addPosteriorProb's weight (:657-661): floor(min(p, 1) * 1e7); `safe` = the host's libm would give the same integer */
+__device__ __forceinline__ int posterior_weight(double lp, const PostArgs &p, bool &safe) {
     double pr = exp(lp);
-    if (!(pr >= p.threshold)) return false;
     if (pr > 1.0) pr = 1.0;
-    pInt = (int) floor(pr * (double) CPB_PAIR_ALIGNMENT_PROB_1);
-    return true;
+    const double v = pr * (double) CPB_PAIR_ALIGNMENT_PROB_1, fl = floor(v);
+    /* lp >= 0 (F + B and the total agree to the last place, as they do for every confidently aligned cell: both are ~ -1e3 and their
+     * difference is a multiple of 2e-13): exp gives >= 1 under any libm, the clamp makes it 1, the weight is 1e7 on both sides */
+    /* (and below 1 - tolerance the weight is 0 on both sides however small p is: exp is never negative) */
+    safe = lp >= 0.0 || ((fl == 0.0 || v - fl >= p.pintTolerance) && fl + 1.0 - v >= p.pintTolerance);
+    return (int) fl;
 }
 
 template <bool WRITE>
@@ -498,8 +515,7 @@ __global__ void __launch_bounds__(32 * POST_WARPS) k_posterior(const DpArgs a, c
                     }
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        int pInt;
-                        const unsigned m = __ballot_sync(0xFFFFFFFFu, valid[u] && alive && posterior_keep(z[u], total, p, pInt));
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, valid[u] && alive && posterior_keep(z[u], total, p));
                         if (C + 32 * u < c1) {
                             if (lane == 0) masks[(C >> 5) + u] = m;
                             cnt += __popc(m);
@@ -560,8 +576,20 @@ __global__ void __launch_bounds__(32 * POST_WARPS) k_posterior(const DpArgs a, c
                         for (int q = 1; q < nd; q++) k = cell >= R.cellBase + sCoff[warp][q] ? q : k;
                         const int d = dLow + k;
                         const int x = ((d + sXmyL[warp][k]) >> 1) + (int) (cell - R.cellBase - sCoff[warp][k]), y = d - x;
-                        int pInt = 0;
-                        posterior_keep(plane[cell], total, p, pInt);
+                        bool safe;
+                        const double lp = plane[cell] - total;
+                        const int pInt = posterior_weight(lp, p, safe);
+                        if (!safe) {
+                            const unsigned k = atomicAdd(p.fixupCount, 1u);
+                            if (k < (unsigned) p.fixupCap) {
+                                PintFixup f;
+                                f.lp = lp;
+                                f.pos = pos;
+                                f.list = l;
+                                f.pad_ = 0;
+                                p.fixups[k] = f;
+                            }
+                        }
                         int32_t *o = p.out[l] + 3 * pos;
                         o[0] = pInt;
                         o[1] = x - 1 + R.ox;

@@ -147,7 +147,25 @@ template <int N> __device__ __forceinline__ void load_record(double *v, const do
 }
 template <int N> __device__ __forceinline__ void store_record(double *rec, const double *v) {
     __stcg(reinterpret_cast<double2 *>(rec), make_double2(v[0], v[1]));
-    if (N > 2) __stcg(rec + 2, v[2]);
+    __stcg(reinterpret_cast<double2 *>(rec) + 1, N > 2 ? make_double2(v[2], v[2]) : make_double2(v[1], v[1])); /* the whole sector, see store_record_if */
+}
+
+/* The edge lane's ring store as PREDICATED instructions.  Written as `if (lane == edge) store_record(...)` the store becomes a branch
+ * that ptxas cannot prove reconvergent; every shuffle after it is then guarded by a BRA.DIV whose slow-path re-entry ends the basic
+ * block, and the paired step body falls apart into scheduling blocks in which the four-deep middle fold of one step can no longer
+ * overlap the other step (tools/sass_sched.py: ~2000 cycles per pair for one warp against ~1000 as one block; forward -12 % on
+ * the B200).  The whole 32-byte record is written (the fourth double is padding): a full sector, so L2 never has to read the
+ * sector back from HBM to merge a partial write when the line is evicted. */
+template <int N> __device__ __forceinline__ void store_record_if(bool edge, double *rec, const double *v) {
+    if (N > 2) {
+        asm volatile("{ .reg .pred p; setp.ne.s32 p, %0, 0; @p st.global.cg.v2.f64 [%1], {%2, %3}; @p st.global.cg.v2.f64 [%1+16], {%4, %4}; }" ::"r"((int) edge),
+                     "l"(rec), "d"(v[0]), "d"(v[1]), "d"(v[2])
+                     : "memory");
+    } else {
+        asm volatile("{ .reg .pred p; setp.ne.s32 p, %0, 0; @p st.global.cg.v2.f64 [%1], {%2, %3}; @p st.global.cg.v2.f64 [%1+16], {%3, %3}; }" ::"r"((int) edge),
+                     "l"(rec), "d"(v[0]), "d"(v[1])
+                     : "memory");
+    }
 }
 
 template <int N> __device__ __forceinline__ void load_row(double *v, const double *row) {
@@ -426,10 +444,8 @@ __global__ void __launch_bounds__(32 * WPC, CPB_FWD_MIN_BLOCKS) k_forward_strip(
                 /* message for diagonal d+1: middle fold of cell d-1, lower folds of cell d */
                 send[0] = mPrev;
                 lower_folds<S>(send + 1, out, tlD, la);
-                if (lane == 31) {
-                    store_record<NSH>(bOut + (size_t) (d & rm) * BND_REC, send);
-                    if (TEAM && (d & CPB_TEAM_PUBLISH_MASK) == CPB_TEAM_PUBLISH_MASK) team_publish(myWord, mySerial, (unsigned) (d + 2)); /* messages up to d are out */
-                }
+                store_record_if<NSH>(lane == 31, bOut + (size_t) (d & rm) * BND_REC, send);
+                if (TEAM && lane == 31 && (d & CPB_TEAM_PUBLISH_MASK) == CPB_TEAM_PUBLISH_MASK) team_publish(myWord, mySerial, (unsigned) (d + 2)); /* messages up to d are out */
 #pragma unroll
                 for (int k = 0; k < S; k++) own[k] = out[k];
             };
@@ -712,7 +728,7 @@ __global__ void __launch_bounds__(32 * WPC, CPB_BWD_MIN_BLOCKS) k_backward_strip
                 send[0] = own[0];
 #pragma unroll
                 for (int k = 1; k < NSH; k++) send[k] = out[BwdShare<S>::state(k)];
-                if (lane == 0) store_record<NSH>(bOut + (size_t) (d & rm) * BND_REC, send);
+                store_record_if<NSH>(lane == 0, bOut + (size_t) (d & rm) * BND_REC, send);
 #pragma unroll
                 for (int k = 0; k < S; k++) own[k] = out[k];
             };

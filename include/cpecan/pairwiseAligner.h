@@ -192,6 +192,13 @@ void cpecan_setAnchorProvider(CpecanAnchorProvider provider, void *extra);
 
 /* CUDA device used by this process (default: $CPECAN_DEVICE or 0).  Must be called before the first alignment. */
 void cpecan_setDevice(int device);
+/* The first n CUDA devices of the box (default: $CPECAN_DEVICES, else one device): every *Batch call and every resident batch then
+ * deals its problems over the n GPUs -- longest first, by estimated band cells -- with one host thread, context and stream per GPU and
+ * the results back at the problems' own indices; expectation totals are summed across the GPUs with one NCCL all-reduce. */
+void cpecan_setDevices(int n);
+/* the same with explicit device ordinals ($CPECAN_DEVICE_LIST="0,2,3") */
+void cpecan_setDeviceList(const int *devices, int n);
+int cpecan_getDeviceCount(void);
 /* releases the device context (optional; also safe to never call) */
 void cpecan_shutdown(void);
 

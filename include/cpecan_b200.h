@@ -138,6 +138,7 @@ typedef struct {
     int32_t maxWidth;
     int32_t twoPass;       /* 1 if the forward sweep ran as checkpoint pass + per-block recomputation (chunked runs of long regions) */
     double msCheckpoint;   /* part of msForward spent in the plane-less checkpoint pass (0 unless twoPass) */
+    int64_t pintFixups;    /* weights floor(p * 1e7) the host recomputed with its own libm (cells within 2e-8 of an integer) */
 } CpbRunStats;
 void cpb_batch_stats(const cpb_batch *b, CpbRunStats *out);
 
@@ -163,6 +164,12 @@ const int32_t *cpb_batch_device_triples(const cpb_batch *b, int list);
  * (the sum over pairs, in pair order). */
 int cpb_batch_fetch_expectations(cpb_batch *b, double *perPair, double *total);
 const double *cpb_batch_device_expectation_total(const cpb_batch *b);
+/* EM over several GPUs of one process: replaces every batch's device-resident expectation total by the sum over all n batches (one
+ * per device, all from expectation-mode runs with the same model) with one ncclAllReduce(ncclDouble, ncclSum) per device
+ * (cPecanEm.py:182-188 sums expectation files).  NCCL is loaded at run time; CPB_ERR_CUDA with a message if it is not there, and the
+ * caller may then sum the per-batch totals itself. */
+int cpb_expectations_allreduce(cpb_batch *const *batches, int n);
+
 /* FORWARD mode: n log-probabilities */
 int cpb_batch_fetch_forward(cpb_batch *b, double *logProb);
 

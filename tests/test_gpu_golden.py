@@ -33,7 +33,7 @@ def test_golden_cases(ctx):
         for got, key in zip(res, ("alignedPairs", "gapXPairs", "gapYPairs")):
             g, w = helpers.sort_triples(got), helpers.sort_triples(c[key])
             assert g.shape == w.shape and np.array_equal(g[:, 1:], w[:, 1:]), "%s %s" % (c["name"], key)
-            assert g.shape[0] == 0 or np.abs(g[:, 0] - w[:, 0]).max() <= 1
+            assert np.array_equal(g[:, 0], w[:, 0])  # weights bit-exact (host libm recomputes the few next to an integer)
             npairs += g.shape[0]
         only = helpers.sort_triples(cp.getAlignedPairsUsingAnchors(m, c["sX"], c["sY"], a, p, c["raggedLeft"], c["raggedRight"], ctx=ctx))
         assert np.array_equal(only[:, 1:], helpers.sort_triples(c["alignedPairs"])[:, 1:])

@@ -119,3 +119,47 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def critical_path(ins):
+    """Longest register-dependency chain of a straight-line region (RAW through registers and predicates; fixed latencies
+    FP64 8, ALU/FMA 4-5, variable ones from VAR_LAT) -- the floor no schedule of the region can beat."""
+    lat_fixed = {"DADD": 8, "DMUL": 8, "DFMA": 8, "DSETP": 10}
+    ready = {}
+    best = 0
+    for i in ins:
+        text = re.sub(r"^@!?U?P\d+\s+", "", i["text"])
+        guard = re.match(r"^@!?(U?P\d+)", i["text"])
+        parts = text.split(None, 1)
+        ops = parts[1] if len(parts) > 1 else ""
+        toks = re.findall(r"\b(UR\d+|R\d+|UP\d+|P\d+)\b", ops)
+        if not toks:
+            continue
+        is_store = i["op"] in ("STG", "STS", "STL", "ST", "BRA", "EXIT", "ISETP", "DSETP", "FSETP", "PLOP3") and False
+        dst = [toks[0]]
+        if i["op"] in ("ISETP", "DSETP", "FSETP", "PLOP3", "VOTE", "LOP3", "IADD3", "SHFL") and len(toks) > 1 and toks[1].startswith("P") and toks[0].startswith("P"):
+            dst = [toks[0], toks[1]]
+        src = toks[len(dst):]
+        if i["op"] in ("STG", "STS", "STL", "BRA", "RED", "ATOMG"):
+            dst, src = [], toks
+        if guard:
+            src = src + [guard.group(1)]
+        wide = 2 if i["op"] in ("DADD", "DMUL", "DFMA", "DSETP") or ".64" in i["text"] else (4 if ".128" in i["text"] else 1)
+
+        def expand(r, n):
+            m = re.match(r"R(\d+)$", r)
+            if not m:
+                return [r]
+            return ["R%d" % (int(m.group(1)) + k) for k in range(n)]
+
+        s_all = []
+        for r in src:
+            s_all += expand(r, 2 if i["op"] in ("DADD", "DMUL", "DFMA", "DSETP") else 1)
+        start = max([ready.get(r, 0) for r in s_all] or [0])
+        lat = lat_fixed.get(i["op"], VAR_LAT.get(i["op"], 5 if i["op"] not in ("IMAD",) else 5))
+        done = start + lat
+        for r in dst:
+            for rr in expand(r, wide):
+                ready[rr] = done
+        best = max(best, done)
+    return best
