@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 
 #include "cpecan/pairwiseAligner.h"
@@ -26,6 +27,12 @@ void *cpecan_malloc(size_t bytes) {
     void *p = malloc(bytes ? bytes : 1);
     if (p == NULL) st_errAbort("cpecan: out of memory allocating %zu bytes", bytes);
     return p;
+}
+
+static double wall_seconds(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
 }
 
 /* ------------------------------------------------------------------------- host threads for the marshalling */
@@ -360,10 +367,15 @@ static stList **fetch_lists(cpb_batch *b, int64_t n, int which) {
     int64_t *off = cpecan_malloc((size_t) (n + 1) * sizeof(int64_t));
     int32_t *tri = cpecan_malloc((size_t) (3 * total + 3) * sizeof(int32_t));
     /* same list order as the reference's own lists (its callers may depend on it, e.g. the MEA walk-back) */
+    const int timing = getenv("CPECAN_HOST_TIMING") != NULL;
+    double t0 = timing ? wall_seconds() : 0.0;
     if (cpb_batch_fetch_pairs_reference_order(b, which, off, tri) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
+    if (timing) fprintf(stderr, "    copy + reference order of %lld triples %8.1f ms\n", (long long) total, 1e3 * (wall_seconds() - t0));
     stList **lists = cpecan_malloc((size_t) (n > 0 ? n : 1) * sizeof(stList *));
     ListJob job = { lists, off, tri };
+    t0 = timing ? wall_seconds() : 0.0;
     cpecan_parallel_for(n, off, lists_range, &job);
+    if (timing) fprintf(stderr, "    lists of slab tuples               %8.1f ms\n", 1e3 * (wall_seconds() - t0));
     free(off);
     free(tri);
     return lists;
@@ -400,6 +412,14 @@ typedef struct {
 static void *device_job(void *v) {
     DeviceJob *j = v;
     const int64_t n = j->n;
+    const int timing = getenv("CPECAN_HOST_TIMING") != NULL; /* stage times of the marshalling on stderr */
+    double t0 = wall_seconds(), t1;
+#define STAGE(what)                                                                                          \
+    if (timing) {                                                                                            \
+        t1 = wall_seconds();                                                                                 \
+        fprintf(stderr, "  [cpecan device %d] %-28s %8.1f ms\n", g_devices[j->slot], what, 1e3 * (t1 - t0)); \
+        t0 = t1;                                                                                             \
+    }
     const char **sX = cpecan_malloc((size_t) (n + 1) * sizeof(char *)), **sY = cpecan_malloc((size_t) (n + 1) * sizeof(char *));
     stList **an = cpecan_malloc((size_t) (n + 1) * sizeof(stList *));
     bool *rl = cpecan_malloc((size_t) n + 1), *rr = cpecan_malloc((size_t) n + 1);
@@ -413,12 +433,14 @@ static void *device_job(void *v) {
     }
     Packed k;
     pack(&k, n, sX, sY, an, rl, rr, j->p->diagonalExpansion);
+    STAGE("pack (tuples -> flat arrays)");
     cpb_batch *b = NULL;
     if (j->mode < 0) { /* resident batch: inputs to the device, no run yet */
         if (cpb_batch_create(j->ctx, k.n, k.seqX, k.xOff, k.seqY, k.yOff, k.anchors, k.aOff, k.rl, k.rr, &b) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
     } else {
         b = run(j->ctx, &k, j->sM, j->p, j->mode);
     }
+    STAGE("device pass (create + run)");
     if (j->mode == CPB_MODE_ALIGNED_PAIRS || j->mode == CPB_MODE_ALIGNED_PAIRS_INDELS) {
         if (j->reweight && cpb_batch_reweight_pairs(b, j->gapGamma) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
         const int nLists = j->mode == CPB_MODE_ALIGNED_PAIRS ? 1 : 3;
@@ -433,6 +455,7 @@ static void *device_job(void *v) {
         for (int64_t i = 0; i < n; i++) j->logProbs[j->idx != NULL ? j->idx[i] : i] = lp[i];
         free(lp);
     }
+    STAGE("fetch (copy, order, lists)");
     if (j->mode == CPB_MODE_EXPECTATIONS || j->keepBatch) j->batch = b;
     else cpb_batch_destroy(b);
     packed_free(&k);
@@ -441,6 +464,8 @@ static void *device_job(void *v) {
     free(an);
     free(rl);
     free(rr);
+    STAGE("release");
+#undef STAGE
     return NULL;
 }
 
@@ -719,13 +744,34 @@ double computeForwardProbability(char *seqX, char *seqY, stList *anchorPairs, Pa
 /* anchors for the forms that take none (getBlastPairsForPairwiseAlignmentParameters, impl/pairwiseAligner.c:1162-1196) */
 static stList *anchors_for(const char *sX, const char *sY, PairwiseAlignmentParameters *p) {
     const int64_t lX = (int64_t) strlen(sX), lY = (int64_t) strlen(sY);
-    if (lX * lY <= p->anchorMatrixBiggerThanThis) return stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
-    if (g_anchorProvider == NULL)
-        st_errAbort("cpecan: a %lld x %lld matrix is bigger than anchorMatrixBiggerThanThis (%lld) and needs anchors; the reference gets them "
-                    "from a LASTZ subprocess, which is outside this library: pass anchors to the ...UsingAnchors form or register a provider "
-                    "with cpecan_setAnchorProvider",
-                    (long long) lX, (long long) lY, (long long) p->anchorMatrixBiggerThanThis);
-    return g_anchorProvider(sX, sY, lX, lY, p, g_anchorExtra);
+    if (g_anchorProvider != NULL && lX * lY > p->anchorMatrixBiggerThanThis) return g_anchorProvider(sX, sY, lX, lY, p, g_anchorExtra);
+    return getBlastPairsForPairwiseAlignmentParameters(sX, sY, lX, lY, p);
+}
+
+/* anchors of many problems on the host threads, then ONE device pass: what makeAllPairwiseAlignments' loop (impl/multipleAligner.c:
+ * 653-681: getAlignedPairs per pair of sequences) becomes */
+typedef struct {
+    const char *const *sX, *const *sY;
+    PairwiseAlignmentParameters *p;
+    stList **anchors;
+} AnchorJob;
+static void anchors_range(int64_t first, int64_t last, void *arg) {
+    AnchorJob *j = arg;
+    for (int64_t i = first; i < last; i++) j->anchors[i] = anchors_for(j->sX[i], j->sY[i], j->p);
+}
+stList **getAlignedPairsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY, PairwiseAlignmentParameters *p,
+                              const bool *raggedLeft, const bool *raggedRight) {
+    stList **anchors = new_list_array(n);
+    int64_t *weight = cpecan_malloc((size_t) (n + 1) * sizeof(int64_t)); /* anchoring costs about the sequence length */
+    weight[0] = 0;
+    for (int64_t i = 0; i < n; i++) weight[i + 1] = weight[i] + (int64_t) strlen(sX[i]) + (int64_t) strlen(sY[i]) + 1;
+    AnchorJob job = { sX, sY, p, anchors };
+    cpecan_parallel_for(n, weight, anchors_range, &job);
+    free(weight);
+    stList **out = getAlignedPairsUsingAnchorsBatch(sM, n, sX, sY, anchors, p, raggedLeft, raggedRight);
+    for (int64_t i = 0; i < n; i++) stList_destruct(anchors[i]);
+    free(anchors);
+    return out;
 }
 
 stList *getAlignedPairs(StateMachine *sM, const char *string1, const char *string2, PairwiseAlignmentParameters *p,

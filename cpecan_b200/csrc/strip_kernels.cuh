@@ -147,7 +147,11 @@ template <int N> __device__ __forceinline__ void load_record(double *v, const do
 }
 template <int N> __device__ __forceinline__ void store_record(double *rec, const double *v) {
     __stcg(reinterpret_cast<double2 *>(rec), make_double2(v[0], v[1]));
+#ifdef CPB_RECORD_24
+    if (N > 2) __stcg(rec + 2, v[2]);
+#else
     __stcg(reinterpret_cast<double2 *>(rec) + 1, N > 2 ? make_double2(v[2], v[2]) : make_double2(v[1], v[1])); /* the whole sector, see store_record_if */
+#endif
 }
 
 /* The edge lane's ring store as PREDICATED instructions.  Written as `if (lane == edge) store_record(...)` the store becomes a branch
@@ -728,7 +732,13 @@ __global__ void __launch_bounds__(32 * WPC, CPB_BWD_MIN_BLOCKS) k_backward_strip
                 send[0] = own[0];
 #pragma unroll
                 for (int k = 1; k < NSH; k++) send[k] = out[BwdShare<S>::state(k)];
+#ifdef CPB_BWD_PREDICATED_STORE
                 store_record_if<NSH>(lane == 0, bOut + (size_t) (d & rm) * BND_REC, send);
+#else
+                /* (not the predicated form of the forward kernel: compiled for 6 CTAs per SM -- 80 registers -- it spills twice as much,
+                 * and the 24 resident warps are worth more here than one scheduling block per step pair: 66.5 against 71-75 ms) */
+                if (lane == 0) store_record<NSH>(bOut + (size_t) (d & rm) * BND_REC, send);
+#endif
 #pragma unroll
                 for (int k = 0; k < S; k++) own[k] = out[k];
             };

@@ -50,11 +50,10 @@ double computeForwardProbability(char *seqX, char *seqY, stList *anchorPairs, Pa
                                  bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd);
 
 /*
- * :62 / :69 -- as the ...UsingAnchors forms with anchors found by the registered anchor provider.  The reference
- * shells out to LASTZ here (impl/pairwiseAligner.c:1005-1080, only for matrices bigger than
- * p->anchorMatrixBiggerThanThis); that subprocess is outside this library.  Without a
- * provider, matrices up to anchorMatrixBiggerThanThis are aligned unanchored exactly as the reference does, and
- * larger ones abort asking for anchors.
+ * :62 / :69 -- as the ...UsingAnchors forms with anchors from getBlastPairsForPairwiseAlignmentParameters (below): matrices up
+ * to p->anchorMatrixBiggerThanThis are aligned unanchored exactly as the reference does; larger ones are anchored in process
+ * (the reference shells out to LASTZ here, impl/pairwiseAligner.c:1005-1080), or by the provider registered with
+ * cpecan_setAnchorProvider if there is one.
  */
 stList *getAlignedPairs(StateMachine *sM, const char *string1, const char *string2, PairwiseAlignmentParameters *p,
                         bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd);
@@ -156,6 +155,13 @@ void getPosteriorProbsWithBandingSplittingAlignmentsByLargeGaps(StateMachine *sM
                                                                 bool alignmentHasRaggedRightEnd, DiagonalPosteriorProbFn diagonalPosteriorProbFn,
                                                                 void (*coordinateCorrectionFn)(), void *extraArgs);
 
+/* :251-257 -- anchors found in process by a seed-and-chain aligner (host/anchors.c) where the reference shells out to LASTZ; same
+ * contract: (x, y, diagonalExpansion) tuples sorted by x + y, every match run given column by column with `trim` columns dropped at
+ * both ends; repeatMask: lower-case bases do not seed.  filterToRemoveOverlap and the two-level scheme are the reference's own. */
+stList *getBlastPairs(const char *sX, const char *sY, int64_t lX, int64_t lY, int64_t trim, int64_t diagonalExpansion, bool repeatMask);
+stList *getBlastPairsForPairwiseAlignmentParameters(const char *sX, const char *sY, const int64_t lX, const int64_t lY, PairwiseAlignmentParameters *p);
+stList *filterToRemoveOverlap(stList *overlappingPairs);
+
 /* :261 -- list of stIntTuple (x1, y1, x2, y2) */
 stList *getSplitPoints(stList *anchorPairs, int64_t lX, int64_t lY, int64_t maxMatrixSize, bool alignmentHasRaggedLeftEnd,
                        bool alignmentHasRaggedRightEnd);
@@ -207,6 +213,9 @@ void cpecan_shutdown(void);
 stList **getAlignedPairsUsingAnchorsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY,
                                           stList *const *anchorPairs, PairwiseAlignmentParameters *p, const bool *raggedLeft,
                                           const bool *raggedRight);
+/* the same from raw sequences: every problem is anchored as getAlignedPairs does (on the host threads), then all run in one device pass */
+stList **getAlignedPairsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY, PairwiseAlignmentParameters *p,
+                              const bool *raggedLeft, const bool *raggedRight);
 /* the same followed by reweightAlignedPairs2(pairs, lX, lY, gapGamma) (:278) for every problem, done on the device before the
  * pairs come back */
 stList **getReweightedAlignedPairsUsingAnchorsBatch(StateMachine *sM, int64_t n, const char *const *sX, const char *const *sY,
