@@ -268,6 +268,17 @@ extern "C" void cpb_context_destroy(cpb_context *ctx) {
     delete ctx;
 }
 
+/* page-locked host memory from the context's pool (result staging of the host layer: a device-to-host copy into pageable memory runs at a
+ * fraction of the link's rate) */
+extern "C" void *cpb_pinned_alloc(cpb_context *ctx, size_t bytes) {
+    if (ctx == nullptr) return nullptr;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+    return ctx->pinned.take(bytes > 0 ? bytes : 1);
+}
+extern "C" void cpb_pinned_free(cpb_context *ctx, void *p) {
+    if (ctx != nullptr && p != nullptr) ctx->pinned.give(p);
+}
+
 extern "C" void cpb_context_set_scratch_budget(cpb_context *ctx, size_t bytes) {
     if (ctx) ctx->scratchBudget = bytes;
 }

@@ -362,10 +362,13 @@ static void lists_range(int64_t first, int64_t last, void *arg) {
     for (int64_t i = first; i < last; i++) j->lists[i] = cpecan_tripleList_construct(j->tri + 3 * j->off[i], j->off[i + 1] - j->off[i]);
 }
 
-static stList **fetch_lists(cpb_batch *b, int64_t n, int which) {
+static stList **fetch_lists(cpb_context *ctx, cpb_batch *b, int64_t n, int which) {
     const int64_t total = cpb_batch_result_count(b, which);
     int64_t *off = cpecan_malloc((size_t) (n + 1) * sizeof(int64_t));
-    int32_t *tri = cpecan_malloc((size_t) (3 * total + 3) * sizeof(int32_t));
+    const size_t triBytes = (size_t) (3 * total + 3) * sizeof(int32_t);
+    int32_t *tri = cpb_pinned_alloc(ctx, triBytes); /* page-locked staging from the context's pool; pageable memory if there is none */
+    const int pinned = tri != NULL;
+    if (!pinned) tri = cpecan_malloc(triBytes);
     /* same list order as the reference's own lists (its callers may depend on it, e.g. the MEA walk-back) */
     const int timing = getenv("CPECAN_HOST_TIMING") != NULL;
     double t0 = timing ? wall_seconds() : 0.0;
@@ -377,7 +380,8 @@ static stList **fetch_lists(cpb_batch *b, int64_t n, int which) {
     cpecan_parallel_for(n, off, lists_range, &job);
     if (timing) fprintf(stderr, "    lists of slab tuples               %8.1f ms\n", 1e3 * (wall_seconds() - t0));
     free(off);
-    free(tri);
+    if (pinned) cpb_pinned_free(ctx, tri);
+    else free(tri);
     return lists;
 }
 
@@ -445,7 +449,7 @@ static void *device_job(void *v) {
         if (j->reweight && cpb_batch_reweight_pairs(b, j->gapGamma) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
         const int nLists = j->mode == CPB_MODE_ALIGNED_PAIRS ? 1 : 3;
         for (int l = 0; l < nLists; l++) {
-            stList **mine = fetch_lists(b, n, l);
+            stList **mine = fetch_lists(j->ctx, b, n, l);
             for (int64_t i = 0; i < n; i++) j->lists[l][j->idx != NULL ? j->idx[i] : i] = mine[i];
             free(mine);
         }

@@ -105,6 +105,10 @@ int64_t cpb_split_points(const int64_t *anchors, int64_t nAnchors, int64_t lX, i
 int cpb_context_create(int device, void *stream, cpb_context **out);
 void cpb_context_destroy(cpb_context *ctx);
 /* upper bound on scratch HBM per chunk (bytes); 0 = 70% of free memory at first use */
+/* Page-locked host memory from the context's pool, for results the caller wants at the link's full rate (cpb_batch_fetch_* accept
+ * any host pointer; into pageable memory the copy is several times slower).  NULL if it cannot be had.  Not thread safe per context. */
+void *cpb_pinned_alloc(cpb_context *ctx, size_t bytes);
+void cpb_pinned_free(cpb_context *ctx, void *p);
 void cpb_context_set_scratch_budget(cpb_context *ctx, size_t bytes);
 
 /* Device-side band builder for one region (what kernel K1 computes), copied back for inspection:
