@@ -142,7 +142,7 @@ def count_cells(packed, n_sample):
     return int(cells)
 
 
-def capi_arm(cp, ctx, model, params, packed, n, barrier):
+def capi_arm(cp, device, stream, model, params, packed, n, barrier):
     """The same pass through the reference-named batch call of libcpecan.so (tools/bench_capi.c): strings and stLists of anchor tuples
     in, stLists of (pInt, x, y) tuples out, walked once and destructed -- beside the flat C-ABI on the same subset of the workload.
     A subset (default 20 000 pairs) because the reference's interface needs ~100 bytes of host heap per aligned pair."""
@@ -160,9 +160,17 @@ def capi_arm(cp, ctx, model, params, packed, n, barrier):
         np.ascontiguousarray(sub["seqX"][: int(sub["xOff"][-1])], dtype=np.uint8).tofile(f)
         np.ascontiguousarray(sub["seqY"][: int(sub["yOff"][-1])], dtype=np.uint8).tofile(f)
         np.ascontiguousarray(sub["anchors"][: 3 * int(sub["aOff"][-1])], dtype=np.int64).tofile(f)
-    # the flat C-ABI on the same subset, for the ratio
+    try:
+        out = subprocess.run([exe, path, "2", "1"], capture_output=True, text=True, timeout=600)
+        j = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as ex:
+        return {"value": None, "note": "bench_capi failed: %s" % ex}
+    finally:
+        os.remove(path)
+    # the flat C-ABI on the same subset, for the ratio (a fresh context: same conditions as the subprocess had)
     import torch
 
+    ctx = cp.Context(device, stream=stream.cuda_stream)
     b = cp.Batch(ctx, None, None, packed=sub)
     b.run(model, params, cp.MODE_ALIGNED_PAIRS)
     cells, n_tri = int(b.stats().cells), int(b.stats().outputTriples)
@@ -176,13 +184,7 @@ def capi_arm(cp, ctx, model, params, packed, n, barrier):
         b.fetch_pairs(0, out=out_pinned.numpy())
         b.close()
     flat = (time.perf_counter() - t0) / 2
-    try:
-        out = subprocess.run([exe, path, "2", "1"], capture_output=True, text=True, timeout=600)
-        j = json.loads(out.stdout.strip().splitlines()[-1])
-    except Exception as ex:
-        return {"value": None, "note": "bench_capi failed: %s" % ex}
-    finally:
-        os.remove(path)
+    ctx.close()
     # value: the call plus giving the lists back (what the library costs its caller); the caller's own walk over the tuples is beside it
     s_lib = j["s_call"] + j["s_destruct"]
     return {"value": cells / s_lib / 1e9, "unit": UNIT, "pairs": n, "pairs_per_s": n / s_lib, "tuples": j["tuples"],
@@ -350,7 +352,8 @@ def main():
 
     e2e_capi = None
     if rank == 0 and world == 1 and not args.skip_e2e:
-        e2e_capi = capi_arm(cp, ctx, model, params, packed, min(args.pairs, args.capi_pairs), barrier)
+        ctx.close()  # the C API arm runs in its own process: give it the whole GPU (this context holds 70 % of HBM as scratch)
+        e2e_capi = capi_arm(cp, local_rank, stream, model, params, packed, min(args.pairs, args.capi_pairs), barrier)
     if rank == 0:
         hbm_peak, sm_max, peak_src = read_peaks()
         # The dominant kernel is the backward wavefront (one launch per chunk), then the forward one.  Both are bound by the FP64 pipe --
@@ -386,7 +389,10 @@ def main():
                                  "sm_max_mhz of MEASURED_PEAKS.json; traffic = ncu dram__bytes_read+write of one launch (bytes per cell x cells per launch)",
                          "peak_source": peak_src, "launches_per_step": n_launch,
                          "k_backward_strip": bwd, "k_forward_strip": fwd,
-                         "forward_plus_backward": {"achieved": both_tf, "frac": both_tf / fp64_peak, "ops_per_cell": OPS_FORWARD + OPS_BACKWARD}},
+                         "forward_plus_backward": {"achieved": both_tf, "frac": both_tf / fp64_peak, "ops_per_cell": OPS_FORWARD + OPS_BACKWARD,
+                                                   # round 1 counted 170 FP64 instructions per cell (with the directed-rounding add of the
+                                                   # segment lookup): the same time on that count, for comparison with its 0.26
+                                                   "frac_counting_170": both_tf / fp64_peak * 170.0 / (OPS_FORWARD + OPS_BACKWARD)}},
         }
         if e2e_capi is not None:
             line["e2e_capi"] = e2e_capi

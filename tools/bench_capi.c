@@ -5,6 +5,7 @@
  * figure as `e2e_capi` beside the flat C-ABI `e2e`.
  *
  *   bench_capi WORKLOAD.bin STEPS WARMUP        -> one JSON line on stdout
+ *   bench_capi WORKLOAD.bin STEPS WARMUP em     -> EM iterations over a resident batch instead (expectation pass + all-reduce)
  *   WORKLOAD.bin: int64 n; int64 xOff[n+1], yOff[n+1], aOff[n+1]; char seqX[xOff[n]], seqY[yOff[n]]; int64 anchors[3 * aOff[n]]
  */
 #include <inttypes.h>
@@ -64,6 +65,26 @@ int main(int argc, char **argv) {
     StateMachine *sM = stateMachine5_construct(fiveState);
     PairwiseAlignmentParameters *p = pairwiseAlignmentBandingParameters_construct();
 
+    if (argc >= 5 && strcmp(argv[4], "em") == 0) {
+        /* EM iterations over a resident batch (cpecanResidentBatch_*): the alignments go to the devices once; an iteration is one
+         * expectation pass per device and one NCCL all-reduce of the expectation totals ($CPECAN_DEVICES GPUs) */
+        CpecanResidentBatch *rb = cpecanResidentBatch_construct(n, (const char *const *) sX, (const char *const *) sY, anchorLists, p, NULL, NULL);
+        double tIter = 0.0, likelihood = 0.0, t00 = 0.0;
+        for (int it = 0; it < warmup + steps; it++) {
+            Hmm *hmm = hmm_constructEmpty(0.0, fiveState);
+            const double t0 = now();
+            cpecanResidentBatch_getExpectations(rb, sM, hmm, p);
+            if (it >= warmup) tIter += now() - t0;
+            likelihood = hmm->likelihood;
+            t00 = hmm->transitions[0];
+            hmm_destruct(hmm);
+        }
+        printf("{\"pairs\": %" PRIi64 ", \"devices\": %d, \"steps\": %d, \"s_per_em_iteration\": %.6f, \"likelihood\": %.17g, \"t00\": %.17g}\n", n,
+               cpecan_getDeviceCount(), steps, tIter / steps, likelihood, t00);
+        cpecanResidentBatch_destruct(rb);
+        cpecan_shutdown();
+        return 0;
+    }
     int64_t tuples = 0, checksum = 0;
     double tCall = 0.0, tWalk = 0.0, tFree = 0.0;
     for (int it = 0; it < warmup + steps; it++) {
@@ -89,8 +110,8 @@ int main(int argc, char **argv) {
         checksum = sum;
     }
     printf("{\"pairs\": %" PRIi64 ", \"steps\": %d, \"tuples\": %" PRIi64 ", \"weight_sum\": %" PRIi64
-           ", \"s_per_step\": %.6f, \"s_call\": %.6f, \"s_walk\": %.6f, \"s_destruct\": %.6f}\n",
-           n, steps, tuples, checksum, (tCall + tWalk + tFree) / steps, tCall / steps, tWalk / steps, tFree / steps);
+           ", \"s_per_step\": %.6f, \"s_call\": %.6f, \"s_walk\": %.6f, \"s_destruct\": %.6f, \"devices\": %d}\n",
+           n, steps, tuples, checksum, (tCall + tWalk + tFree) / steps, tCall / steps, tWalk / steps, tFree / steps, cpecan_getDeviceCount());
     cpecan_shutdown();
     return 0;
 }
