@@ -118,6 +118,7 @@ def _load():
     L.cpb_batch_result_count.restype = C.c_int64
     L.cpb_batch_result_count.argtypes = [C.c_void_p, C.c_int]
     L.cpb_batch_fetch_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.cpb_batch_set_result_sink.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
     L.cpb_batch_fetch_pairs_reference_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.cpb_batch_reweight_pairs.argtypes = [C.c_void_p, C.c_double]
     L.cpb_batch_alignment_scores.argtypes = [C.c_void_p, C.c_void_p]
@@ -304,6 +305,16 @@ class Batch:
         fetch = lib.cpb_batch_fetch_pairs_reference_order if reference_order else lib.cpb_batch_fetch_pairs
         _check(fetch(self.h, which, C.c_void_p(off.ctypes.data), C.c_void_p(tri.ctypes.data)))
         return off, tri[:cnt]
+
+    def set_result_sink(self, which, out):
+        """out: int32 array [capacity, 3] in page-locked host memory that the next runs fill with list `which` while they compute;
+        fetch_pairs(which, out=out) then only returns the offsets (None removes the sink)"""
+        if out is None:
+            _check(lib.cpb_batch_set_result_sink(self.h, which, None, 0))
+        else:
+            assert out.dtype == np.int32 and out.flags["C_CONTIGUOUS"]
+            _check(lib.cpb_batch_set_result_sink(self.h, which, C.c_void_p(out.ctypes.data), out.shape[0]))
+        self._sink = out
 
     def reweight_pairs(self, gap_gamma):
         """reweightAlignedPairs2 (impl/pairwiseAligner.c:1519-1560) on the device, in place on list 0"""

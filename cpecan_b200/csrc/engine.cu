@@ -184,12 +184,14 @@ struct cpb_context {
     DevBuf scratch;
     DevBuf boundary, counters, negRecord, progress; /* strip engine: per-warp-slot boundary rings, work-fetch counters, one LOG_ZERO ring record */
     DevBuf fixups;                                  /* posterior write pass: one counter (first 16 bytes), then PintFixup records */
+    cudaStream_t copyStream = nullptr;              /* result sinks: device-to-host copies of finished chunks beside the next chunk's kernels */
     int smCount = 148;
     DevPool pool;              /* buffers handed back by destroyed batches */
     PinnedPool pinned;         /* page-locked host staging, same idea */
 };
 
 static const int kStripWPC = 4; /* warps per CTA of the strip kernels */
+static const int kBwdWideBand = 1500; /* widest diagonal (cells) from which the backward kernel runs in its 4-CTAs-per-SM build */
 static const int64_t kSymPad = 64; /* bytes of 'n' before and after the symbol arrays */
 
 static int configure_kernels() {
@@ -261,6 +263,7 @@ extern "C" void cpb_context_destroy(cpb_context *ctx) {
     ctx->negRecord.release();
     ctx->progress.release();
     ctx->fixups.release();
+    if (ctx->copyStream != nullptr) cudaStreamDestroy(ctx->copyStream);
     ctx->pool.drain();
     ctx->pinned.drain();
     ctx->counters.release();
@@ -301,6 +304,9 @@ struct cpb_batch {
     int32_t *anchors = nullptr;      /* host copy of the anchor triples as the device has them (page-locked, from ctx->pinned) */
     std::vector<int32_t> anchorsOwn; /* fallback if page-locked memory cannot be had */
     std::vector<uint8_t> rl, rr;
+    int32_t *sink[3] = { nullptr, nullptr, nullptr }; /* host buffers that receive the triples of each list while the run goes on */
+    int64_t sinkCap[3] = { 0, 0, 0 };                 /* their capacity in triples */
+    bool sunk[3] = { false, false, false };           /* the last run delivered the whole list into its sink */
     int64_t oddExpansionPair = -1;   /* first pair with an odd anchor expansion: only an error for runs with dynamicAnchorExpansion (:166) */
     DevBuf symX, symY, dAnchors;
     /* run state */
@@ -934,30 +940,33 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     /* strip engine: persistent grid of independent warps, boundary rings, work counters */
     typedef void (*StripKernel)(const DpArgs, const CpbModel, const StripArgs);
     StripKernel kFwdStrip = nullptr, kFwdTeam = nullptr, kFwdBlocks = nullptr, kBwdStrip = nullptr;
+    /* the backward kernel exists compiled for 6 and for 4 resident CTAs per SM: see strip_kernels.cuh ($CPB_BWD_WIDE=0/1 forces one) */
+    bool bwdWide = stx.maxWidth > kBwdWideBand;
+    if (getenv("CPB_BWD_WIDE") != nullptr) bwdWide = atoi(getenv("CPB_BWD_WIDE")) != 0;
     StripKernel kCkStrip = k_forward_strip<S, 0, kStripWPC, FWD_REGIONS>, kCkTeam = k_forward_strip<S, 0, kStripWPC, FWD_TEAMS>; /* first pass of two */
     switch (mode) {
     case CPB_MODE_FORWARD:
         kFwdStrip = k_forward_strip<S, 0, kStripWPC, FWD_REGIONS>;
         kFwdTeam = k_forward_strip<S, 0, kStripWPC, FWD_TEAMS>;
-        kBwdStrip = k_backward_strip<S, 0, true, kStripWPC>;
+        kBwdStrip = bwdWide ? k_backward_strip<S, 0, true, kStripWPC, 4> : k_backward_strip<S, 0, true, kStripWPC, CPB_BWD_MIN_BLOCKS>;
         break;
     case CPB_MODE_ALIGNED_PAIRS:
         kFwdStrip = k_forward_strip<S, 1, kStripWPC, FWD_REGIONS>;
         kFwdTeam = k_forward_strip<S, 1, kStripWPC, FWD_TEAMS>;
         kFwdBlocks = k_forward_strip<S, 1, kStripWPC, FWD_BLOCKS>;
-        kBwdStrip = k_backward_strip<S, 1, true, kStripWPC>;
+        kBwdStrip = bwdWide ? k_backward_strip<S, 1, true, kStripWPC, 4> : k_backward_strip<S, 1, true, kStripWPC, CPB_BWD_MIN_BLOCKS>;
         break;
     case CPB_MODE_ALIGNED_PAIRS_INDELS:
         kFwdStrip = k_forward_strip<S, 3, kStripWPC, FWD_REGIONS>;
         kFwdTeam = k_forward_strip<S, 3, kStripWPC, FWD_TEAMS>;
         kFwdBlocks = k_forward_strip<S, 3, kStripWPC, FWD_BLOCKS>;
-        kBwdStrip = k_backward_strip<S, 3, true, kStripWPC>;
+        kBwdStrip = bwdWide ? k_backward_strip<S, 3, true, kStripWPC, 4> : k_backward_strip<S, 3, true, kStripWPC, CPB_BWD_MIN_BLOCKS>;
         break;
     default:
         kFwdStrip = k_forward_strip<S, S, kStripWPC, FWD_REGIONS>;
         kFwdTeam = k_forward_strip<S, S, kStripWPC, FWD_TEAMS>;
         kFwdBlocks = k_forward_strip<S, S, kStripWPC, FWD_BLOCKS>;
-        kBwdStrip = k_backward_strip<S, S, false, kStripWPC>;
+        kBwdStrip = bwdWide ? k_backward_strip<S, S, false, kStripWPC, 4> : k_backward_strip<S, S, false, kStripWPC, CPB_BWD_MIN_BLOCKS>;
         break;
     }
     /* narrow bands: groups of 8 or 16 lanes per region / block (narrow_kernels.cuh) */
@@ -1136,7 +1145,10 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     }
     stamp("strip setup (+ checkpoint pass)");
     std::vector<int64_t> hPairOff;
-    int64_t running[3] = { 0, 0, 0 };
+    int64_t running[3] = { 0, 0, 0 }, sinkFrom[3] = { 0, 0, 0 };
+    for (int l = 0; l < 3; l++) b->sunk[l] = l < nLists && b->sink[l] != nullptr;
+    if (nLists > 0 && (b->sink[0] != nullptr || b->sink[1] != nullptr || b->sink[2] != nullptr) && ctx->copyStream == nullptr)
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
     int64_t chunkIndex = -1;
 
     int64_t totalChunkCells = 0, cellsDone = 0;
@@ -1284,16 +1296,34 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
                     if (b->out[l].p && running[l] > 0)
                         CUDA_TRY(cudaMemcpyAsync(bigger.p, b->out[l].p, (size_t) running[l] * 3 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
                     CUDA_TRY(cudaStreamSynchronize(st));
+                    if (ctx->copyStream != nullptr) CUDA_TRY(cudaStreamSynchronize(ctx->copyStream)); /* copies out of the old buffer */
                     b->out[l].release();
                     b->out[l].adopt(bigger);
                 }
                 pa.out[l] = b->out[l].as<int32_t>();
+                sinkFrom[l] = running[l];
                 running[l] = newTotals[l];
             }
             ev = tic(&stx.msPosterior);
             k_posterior<true><<<(unsigned) nb, 32 * POST_WARPS, 0, st>>>(a, pa);
             stx.kernelLaunches++;
             toc(ev);
+            /* result sinks: this chunk's triples go to the host on the copy stream while the next chunk's kernels run */
+            for (int l = 0; l < nLists; l++) {
+                if (b->sink[l] == nullptr || !b->sunk[l]) continue;
+                if (running[l] > b->sinkCap[l]) {
+                    b->sunk[l] = false; /* too small: cpb_batch_fetch_pairs will copy the list the ordinary way */
+                    continue;
+                }
+                if (running[l] == sinkFrom[l]) continue;
+                cudaEvent_t done;
+                CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+                CUDA_TRY(cudaEventRecord(done, st));
+                CUDA_TRY(cudaStreamWaitEvent(ctx->copyStream, done, 0));
+                CUDA_TRY(cudaEventDestroy(done));
+                CUDA_TRY(cudaMemcpyAsync(b->sink[l] + 3 * sinkFrom[l], b->out[l].as<int32_t>() + 3 * sinkFrom[l], (size_t) (running[l] - sinkFrom[l]) * 3 * sizeof(int32_t),
+                                         cudaMemcpyDeviceToHost, ctx->copyStream));
+            }
         } else if (mode == CPB_MODE_EXPECTATIONS) {
             const size_t smem = ((sizeof(Tables<S>) + 15) & ~size_t(15)) + (size_t) S * 16 * EXPECT_COLS * sizeof(double);
             ev = tic(&stx.msPosterior);
@@ -1349,14 +1379,17 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             std::vector<int32_t> weights(nFix);
             CUDA_TRY(cudaMemcpyAsync(fx.data(), ctx->fixups.as<char>() + 16, nFix * sizeof(PintFixup), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
+            if (ctx->copyStream != nullptr) CUDA_TRY(cudaStreamSynchronize(ctx->copyStream)); /* the sinks are complete before they are patched */
             for (unsigned k = 0; k < nFix; k++) {
                 double pr = exp(fx[k].lp);
                 if (pr > 1.0) pr = 1.0;
                 weights[k] = (int32_t) (int64_t) floor(pr * (double) CPB_PAIR_ALIGNMENT_PROB_1);
                 CUDA_TRY(cudaMemcpyAsync(b->out[fx[k].list].as<int32_t>() + 3 * fx[k].pos, &weights[k], sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                if (b->sunk[fx[k].list]) b->sink[fx[k].list][3 * fx[k].pos] = weights[k];
             }
             CUDA_TRY(cudaStreamSynchronize(st));
         }
+        if (ctx->copyStream != nullptr) CUDA_TRY(cudaStreamSynchronize(ctx->copyStream));
         stx.pintFixups = nFix;
     }
     finish_events();
@@ -1388,6 +1421,17 @@ extern "C" int cpb_batch_run(cpb_batch *b, const CpbModel *m, const CpbParams *p
     return CPB_ERR_ARGUMENT;
 }
 
+extern "C" int cpb_batch_set_result_sink(cpb_batch *b, int list, int32_t *hostTriples, int64_t capacityTriples) {
+    if (b == nullptr || list < 0 || list > 2 || capacityTriples < 0) {
+        cpb_set_error("cpb_batch_set_result_sink: bad argument");
+        return CPB_ERR_ARGUMENT;
+    }
+    b->sink[list] = capacityTriples > 0 ? hostTriples : nullptr;
+    b->sinkCap[list] = b->sink[list] != nullptr ? capacityTriples : 0;
+    b->sunk[list] = false;
+    return CPB_OK;
+}
+
 extern "C" void cpb_batch_stats(const cpb_batch *b, CpbRunStats *out) {
     if (b && out) *out = b->stats;
 }
@@ -1409,6 +1453,7 @@ extern "C" int cpb_batch_fetch_pairs(cpb_batch *b, int list, int64_t *offsets, i
     }
     CUDA_TRY(cudaSetDevice(b->ctx->device));
     if (offsets) memcpy(offsets, b->pairOff[list].data(), (b->n + 1) * sizeof(int64_t));
+    if (triples != nullptr && triples == b->sink[list] && b->sunk[list]) return CPB_OK; /* the run already delivered them there */
     if (triples && b->outCount[list] > 0) {
         CUDA_TRY(cudaMemcpyAsync(triples, b->out[list].p, (size_t) b->outCount[list] * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, b->ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));

@@ -338,10 +338,25 @@ static void pack(Packed *k, int64_t n, const char *const *sX, const char *const 
 }
 
 /* runs one engine pass over the packed problems; aborts with the engine's message on failure (the reference has no error codes either) */
-static cpb_batch *run(cpb_context *ctx, Packed *k, StateMachine *sM, PairwiseAlignmentParameters *p, int mode) {
+/* Page-locked buffers the run fills with the aligned-pair lists while it computes (cpb_batch_set_result_sink): sized by a guess --
+ * the reference's threshold keeps about one cell per base -- and simply not used by a run that produces more. */
+typedef struct {
+    int32_t *tri[3];
+    int64_t cap[3];
+} Sinks;
+
+static cpb_batch *run(cpb_context *ctx, Packed *k, StateMachine *sM, PairwiseAlignmentParameters *p, int mode, Sinks *sinks) {
     cpb_batch *b = NULL;
     if (cpb_batch_create(ctx, k->n, k->seqX, k->xOff, k->seqY, k->yOff, k->anchors, k->aOff, k->rl, k->rr, &b) != CPB_OK)
         st_errAbort("cpecan: %s", cpb_last_error());
+    if (sinks != NULL) {
+        const int nLists = mode == CPB_MODE_ALIGNED_PAIRS ? 1 : (mode == CPB_MODE_ALIGNED_PAIRS_INDELS ? 3 : 0);
+        for (int l = 0; l < nLists; l++) {
+            sinks->cap[l] = 2 * (k->xOff[k->n] < k->yOff[k->n] ? k->xOff[k->n] : k->yOff[k->n]) + 4096;
+            sinks->tri[l] = cpb_pinned_alloc(ctx, (size_t) sinks->cap[l] * 3 * sizeof(int32_t));
+            if (sinks->tri[l] != NULL) cpb_batch_set_result_sink(b, l, sinks->tri[l], sinks->cap[l]);
+        }
+    }
     CpbParams q;
     to_engine_params(p, &q);
     const int rc = cpb_batch_run(b, cpecan_model_of(sM), &q, mode);
@@ -362,11 +377,14 @@ static void lists_range(int64_t first, int64_t last, void *arg) {
     for (int64_t i = first; i < last; i++) j->lists[i] = cpecan_tripleList_construct(j->tri + 3 * j->off[i], j->off[i + 1] - j->off[i]);
 }
 
-static stList **fetch_lists(cpb_context *ctx, cpb_batch *b, int64_t n, int which) {
+static stList **fetch_lists(cpb_context *ctx, cpb_batch *b, int64_t n, int which, Sinks *sinks) {
     const int64_t total = cpb_batch_result_count(b, which);
     int64_t *off = cpecan_malloc((size_t) (n + 1) * sizeof(int64_t));
     const size_t triBytes = (size_t) (3 * total + 3) * sizeof(int32_t);
-    int32_t *tri = cpb_pinned_alloc(ctx, triBytes); /* page-locked staging from the context's pool; pageable memory if there is none */
+    /* the sink the run filled, if the list fitted; else page-locked staging from the context's pool; pageable memory if there is none */
+    int32_t *tri = sinks != NULL && sinks->tri[which] != NULL && total <= sinks->cap[which] ? sinks->tri[which] : NULL;
+    const int fromSink = tri != NULL;
+    if (!fromSink) tri = cpb_pinned_alloc(ctx, triBytes);
     const int pinned = tri != NULL;
     if (!pinned) tri = cpecan_malloc(triBytes);
     /* same list order as the reference's own lists (its callers may depend on it, e.g. the MEA walk-back) */
@@ -380,8 +398,12 @@ static stList **fetch_lists(cpb_context *ctx, cpb_batch *b, int64_t n, int which
     cpecan_parallel_for(n, off, lists_range, &job);
     if (timing) fprintf(stderr, "    lists of slab tuples               %8.1f ms\n", 1e3 * (wall_seconds() - t0));
     free(off);
-    if (pinned) cpb_pinned_free(ctx, tri);
-    else free(tri);
+    if (fromSink) { /* released with the other sinks */
+    } else if (pinned) {
+        cpb_pinned_free(ctx, tri);
+    } else {
+        free(tri);
+    }
     return lists;
 }
 
@@ -436,20 +458,22 @@ static void *device_job(void *v) {
         rr[i] = j->raggedRight != NULL && j->raggedRight[g];
     }
     Packed k;
+    Sinks sinks;
+    memset(&sinks, 0, sizeof(sinks));
     pack(&k, n, sX, sY, an, rl, rr, j->p->diagonalExpansion);
     STAGE("pack (tuples -> flat arrays)");
     cpb_batch *b = NULL;
     if (j->mode < 0) { /* resident batch: inputs to the device, no run yet */
         if (cpb_batch_create(j->ctx, k.n, k.seqX, k.xOff, k.seqY, k.yOff, k.anchors, k.aOff, k.rl, k.rr, &b) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
     } else {
-        b = run(j->ctx, &k, j->sM, j->p, j->mode);
+        b = run(j->ctx, &k, j->sM, j->p, j->mode, j->reweight ? NULL : &sinks); /* (reweighting rewrites the list on the device after the run) */
     }
     STAGE("device pass (create + run)");
     if (j->mode == CPB_MODE_ALIGNED_PAIRS || j->mode == CPB_MODE_ALIGNED_PAIRS_INDELS) {
         if (j->reweight && cpb_batch_reweight_pairs(b, j->gapGamma) != CPB_OK) st_errAbort("cpecan: %s", cpb_last_error());
         const int nLists = j->mode == CPB_MODE_ALIGNED_PAIRS ? 1 : 3;
         for (int l = 0; l < nLists; l++) {
-            stList **mine = fetch_lists(j->ctx, b, n, l);
+            stList **mine = fetch_lists(j->ctx, b, n, l, &sinks);
             for (int64_t i = 0; i < n; i++) j->lists[l][j->idx != NULL ? j->idx[i] : i] = mine[i];
             free(mine);
         }
@@ -459,6 +483,8 @@ static void *device_job(void *v) {
         for (int64_t i = 0; i < n; i++) j->logProbs[j->idx != NULL ? j->idx[i] : i] = lp[i];
         free(lp);
     }
+    for (int l = 0; l < 3; l++)
+        if (sinks.tri[l] != NULL) cpb_pinned_free(j->ctx, sinks.tri[l]);
     STAGE("fetch (copy, order, lists)");
     if (j->mode == CPB_MODE_EXPECTATIONS || j->keepBatch) j->batch = b;
     else cpb_batch_destroy(b);

@@ -515,7 +515,9 @@ __global__ void __launch_bounds__(32 * WPC, CPB_FWD_MIN_BLOCKS) k_forward_strip(
 }
 
 /* ---------------------------------------------------------------------------------------------
- * k_backward_strip<S, NP, ZSUM, WPC> : one warp per traceback block, strips in descending row order.
+ * k_backward_strip<S, NP, ZSUM, WPC, MINB> : one warp per traceback block, strips in descending row order.
+ * MINB: resident CTAs per SM it is compiled for (the engine picks 6 -- 80 registers -- for ordinary bands, where the 24 warps per SM
+ * are worth 8 %, and 4 -- 128 registers -- for very wide ones, where they cost 15 %).
  * ZSUM: the planes written are F + B per state (what the posterior scan needs); otherwise raw B (expectations).
  * ------------------------------------------------------------------------------------------- */
 template <int S> struct BwdShare; /* states of row x+1 that row x needs: M (for the middle step) and the gap-X states */
@@ -549,8 +551,8 @@ __device__ __forceinline__ void cell_backward(double *out, double t2m, const dou
     }
 }
 
-template <int S, int NP, bool ZSUM, int WPC>
-__global__ void __launch_bounds__(32 * WPC, CPB_BWD_MIN_BLOCKS) k_backward_strip(const DpArgs a, const CpbModel model, const StripArgs sa) {
+template <int S, int NP, bool ZSUM, int WPC, int MINB>
+__global__ void __launch_bounds__(32 * WPC, MINB) k_backward_strip(const DpArgs a, const CpbModel model, const StripArgs sa) {
     __shared__ __align__(128) StripTables<S> tab;
     fill_strip_tables<S>(tab, model, threadIdx.x, 32 * WPC);
     __syncthreads();

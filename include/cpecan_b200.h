@@ -144,6 +144,13 @@ typedef struct {
     double msCheckpoint;   /* part of msForward spent in the plane-less checkpoint pass (0 unless twoPass) */
     int64_t pintFixups;    /* weights floor(p * 1e7) the host recomputed with its own libm (cells within 2e-8 of an integer) */
 } CpbRunStats;
+/* Result sink: a host buffer (page-locked for full speed: cpb_pinned_alloc, cudaHostAlloc, torch pin_memory) of capacityTriples
+ * (pInt, x, y) int32 triples that the next runs fill with list `list` WHILE they compute -- every chunk's triples are copied out on a
+ * second stream beside the next chunk's kernels, so the device-to-host copy of the whole list (1.3 GB per 100 000 x 1 kb pairs)
+ * is off the critical path.  cpb_batch_fetch_pairs called with that same pointer then only hands over the offsets.  If a run
+ * produces more than the capacity the sink is skipped for that run and the fetch copies as usual.  NULL / 0 removes the sink. */
+int cpb_batch_set_result_sink(cpb_batch *b, int list, int32_t *hostTriples, int64_t capacityTriples);
+
 void cpb_batch_stats(const cpb_batch *b, CpbRunStats *out);
 
 /* Results of the last run.  list: 0 = match, 1 = gapX, 2 = gapY (the latter two only in INDELS mode).

@@ -541,3 +541,40 @@ def test_threshold_is_decided_in_log_space(ctx, oracle):
         for t in (w / 1e7, np.nextafter(w / 1e7, 1.0), np.nextafter(w / 1e7, 0.0), min((w + 1) / 1e7, 1.0)):
             p.threshold = float(t)
             check_aligned_pairs(ctx, oracle, spec, p, cases[:2], "threshold %r" % t)
+
+
+def test_result_sink_delivers_the_same_lists(ctx, oracle):
+    """cpb_batch_set_result_sink: the run copies every chunk's triples to a host buffer on a second stream while the next chunk
+    computes; the lists must be what an ordinary fetch returns -- over several chunks, with weights the host had to recompute, and
+    when the sink is too small (then the fetch copies as usual)."""
+    import torch
+
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    packed = synth.evolved_pairs(48, 600, seed=21, trim=int(p.constraintDiagonalTrim), expansion=int(p.diagonalExpansion))
+    spec = helpers.ModelSpec(cp.fiveState)
+    b = cp.Batch(ctx, None, None, packed=packed)
+    b.run(spec.cpb(), p, cp.MODE_ALIGNED_PAIRS)
+    off0, tri0 = b.fetch_pairs(0)
+    tri0 = tri0.copy()
+    n = int(off0[-1])
+    ctx.set_scratch_budget(48 << 20)  # a few chunks
+    try:
+        sink = torch.zeros((n + 100, 3), dtype=torch.int32).pin_memory().numpy()
+        b.set_result_sink(0, sink)
+        b.run(spec.cpb(), p, cp.MODE_ALIGNED_PAIRS)
+        assert b.stats().nChunks > 1
+        off1, tri1 = b.fetch_pairs(0, out=sink)
+        assert np.array_equal(off0, off1) and np.array_equal(tri0, tri1)
+        off2, tri2 = b.fetch_pairs(0)  # an ordinary fetch into another buffer still works
+        assert np.array_equal(tri0, tri2)
+        off3, tri3 = b.fetch_pairs(0, out=sink, reference_order=True)
+        b.set_result_sink(0, None)
+        b.run(spec.cpb(), p, cp.MODE_ALIGNED_PAIRS)
+        assert np.array_equal(b.fetch_pairs(0, reference_order=True)[1], tri3)
+        small = torch.zeros((n // 2, 3), dtype=torch.int32).pin_memory().numpy()
+        b.set_result_sink(0, small)
+        b.run(spec.cpb(), p, cp.MODE_ALIGNED_PAIRS)
+        assert np.array_equal(b.fetch_pairs(0)[1], tri0)
+    finally:
+        ctx.set_scratch_budget(0)
+        b.close()
