@@ -307,6 +307,7 @@ struct cpb_batch {
     int32_t *sink[3] = { nullptr, nullptr, nullptr }; /* host buffers that receive the triples of each list while the run goes on */
     int64_t sinkCap[3] = { 0, 0, 0 };                 /* their capacity in triples */
     bool sunk[3] = { false, false, false };           /* the last run delivered the whole list into its sink */
+    bool reweighted = false;         /* cpb_batch_reweight_pairs has rewritten list 0 of the last run in place */
     int64_t oddExpansionPair = -1;   /* first pair with an odd anchor expansion: only an error for runs with dynamicAnchorExpansion (:166) */
     DevBuf symX, symY, dAnchors;
     /* run state */
@@ -681,6 +682,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     m = &finiteModel;
 #endif
     stx.nPairs = b->n;
+    b->reweighted = false;
     struct EventList { /* an early error return destroys the events that finish_events() has not collected */
         std::vector<EventPair> v;
         ~EventList() {
@@ -1556,6 +1558,10 @@ extern "C" int cpb_batch_reweight_pairs(cpb_batch *b, double gapGamma) {
         return CPB_ERR_ARGUMENT;
     }
     if (!(gapGamma > 0.0) || b->outCount[0] == 0) return CPB_OK; /* reweightAlignedPairs2 returns its input for gapGamma <= 0 */
+    if (b->reweighted) {
+        cpb_set_error("cpb_batch_reweight_pairs: list 0 of this run has already been reweighted (the weights are rewritten in place; run the batch again first)");
+        return CPB_ERR_ARGUMENT;
+    }
     CUDA_TRY(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->stream;
     DevBuf dOff, dX, dY, gX, gY;
@@ -1579,6 +1585,10 @@ extern "C" int cpb_batch_reweight_pairs(cpb_batch *b, double gapGamma) {
         if (e != cudaSuccess) {
             cpb_set_error("cpb_batch_reweight_pairs: %s", cudaGetErrorString(e));
             rc = CPB_ERR_CUDA;
+        } else {
+            b->reweighted = true;
+            b->stats.reweighted = 1;
+            b->sunk[0] = false; /* a result sink holds the posteriors of the run, not these weights: the next fetch copies the list */
         }
     }
     for (DevBuf *d : { &dOff, &dX, &dY, &gX, &gY }) d->release();

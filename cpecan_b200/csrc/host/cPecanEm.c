@@ -222,32 +222,37 @@ int main(int argc, char *argv[]) {
     srand48(seed);
     read_sequence_files(argc, argv, optind);
 
-    /* all alignments; then a random sample of at most maxSample bases of alignment length (cPecanEm.py:148-160) */
-    Job *jobs = NULL;
+    /* All alignments are read, shuffled (so that a sample is not just the head of the file) and sampled up to maxSample bases of
+     * alignment length (cPecanEm.py:148-160); only the sampled ones have their sub-sequences cut and their anchors built. */
+    struct PairwiseAlignment **all = NULL;
     int64_t n = 0, cap = 0;
     struct PairwiseAlignment *pA;
     while ((pA = cigarRead(stdin)) != NULL) {
         if (n == cap) {
             cap = cap ? 2 * cap : 1024;
-            jobs = realloc(jobs, (size_t) cap * sizeof(Job));
-            if (jobs == NULL) st_errAbort("cPecanEm: out of memory");
+            all = realloc(all, (size_t) cap * sizeof(*all));
+            if (all == NULL) st_errAbort("cPecanEm: out of memory");
         }
-        job_prepare(&jobs[n++], pA, p);
+        all[n++] = pA;
     }
     if (n == 0) st_errAbort("cPecanEm: no alignments on the standard input");
-    for (int64_t i = n - 1; i > 0; i--) { /* shuffle, so that a sample is not just the head of the file */
+    for (int64_t i = n - 1; i > 0; i--) {
         const int64_t k = (int64_t) (drand48() * (double) (i + 1));
-        const Job t = jobs[i];
-        jobs[i] = jobs[k];
-        jobs[k] = t;
+        struct PairwiseAlignment *t = all[i];
+        all[i] = all[k];
+        all[k] = t;
     }
     int64_t used = 0;
     double sampled = 0.0;
     while (used < n && sampled < (double) maxSample) {
-        sampled += (double) (jobs[used].pA->end1 + jobs[used].pA->end2) / 2.0;
+        sampled += (double) (llabs((long long) (all[used]->end1 - all[used]->start1)) + llabs((long long) (all[used]->end2 - all[used]->start2))) / 2.0;
         used++;
     }
     log_info("We sampled: %.0f bases of alignment length and %" PRIi64 " alignments of %" PRIi64 "\n", sampled, used, n);
+    Job *jobs = xmalloc((size_t) used * sizeof(Job));
+    for (int64_t i = 0; i < used; i++) job_prepare(&jobs[i], all[i], p);
+    for (int64_t i = used; i < n; i++) destructPairwiseAlignment(all[i]);
+    free(all);
     const char **sX = xmalloc((size_t) used * sizeof(char *)), **sY = xmalloc((size_t) used * sizeof(char *));
     stList **anchors = xmalloc((size_t) used * sizeof(stList *));
     bool *ragged = xmalloc((size_t) used * sizeof(bool));
@@ -258,7 +263,7 @@ int main(int argc, char *argv[]) {
         ragged[i] = 1;
     }
     CpecanResidentBatch *batch = cpecanResidentBatch_construct(used, sX, sY, anchors, p, ragged, ragged);
-    for (int64_t i = 0; i < n; i++) job_release(&jobs[i]);
+    for (int64_t i = 0; i < used; i++) job_release(&jobs[i]);
     free(jobs);
     free(sX);
     free(sY);

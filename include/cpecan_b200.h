@@ -143,6 +143,7 @@ typedef struct {
     int32_t twoPass;       /* 1 if the forward sweep ran as checkpoint pass + per-block recomputation (chunked runs of long regions) */
     double msCheckpoint;   /* part of msForward spent in the plane-less checkpoint pass (0 unless twoPass) */
     int64_t pintFixups;    /* weights floor(p * 1e7) the host recomputed with its own libm (cells within 2e-8 of an integer) */
+    int64_t reweighted;    /* 1 once cpb_batch_reweight_pairs has rewritten list 0 of this run: fetches and scores then see those weights */
 } CpbRunStats;
 /* Result sink: a host buffer (page-locked for full speed: cpb_pinned_alloc, cudaHostAlloc, torch pin_memory) of capacityTriples
  * (pInt, x, y) int32 triples that the next runs fill with list `list` WHILE they compute -- every chunk's triples are copied out on a
@@ -165,7 +166,8 @@ int cpb_batch_fetch_pairs_reference_order(cpb_batch *b, int list, int64_t *offse
 /* Post-posterior filters on the device (list 0 of the last ALIGNED_PAIRS / ALIGNED_PAIRS_INDELS run).
  * cpb_batch_reweight_pairs: every weight becomes weight - gapGamma * (gap weight of its x + gap weight of its y), where the gap
  * weight of a position is PAIR_ALIGNMENT_PROB_1 minus the weights aligned to it, floored at 0 -- reweightAlignedPairs2 of
- * impl/pairwiseAligner.c:1519-1560, in place, before the pairs are fetched; gapGamma <= 0 leaves them alone, as there.
+ * impl/pairwiseAligner.c:1519-1560, in place, before the pairs are fetched; gapGamma <= 0 leaves them alone, as there.  Once per
+ * run: CpbRunStats.reweighted says that list 0 now holds these weights, a second call is an error, cpb_batch_run resets it.
  * cpb_batch_alignment_scores: per pair, getAlignmentScore of impl/multipleAligner.c:604-619 (n int64 values to the host). */
 int cpb_batch_reweight_pairs(cpb_batch *b, double gapGamma);
 int cpb_batch_alignment_scores(cpb_batch *b, int64_t *scores);

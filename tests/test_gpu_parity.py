@@ -444,7 +444,13 @@ def test_device_reweighting_and_alignment_scores(ctx):
     scores = b.alignment_scores()
     for gamma in (0.0, 0.5, 0.9):
         b.run(cp.stateMachine5_construct(), p, cp.MODE_ALIGNED_PAIRS)
+        assert b.stats().reweighted == 0
         b.reweight_pairs(gamma)
+        assert b.stats().reweighted == (1 if gamma > 0 else 0)
+        if gamma > 0:
+            # the weights were rewritten in place: a second call would apply the gap weighting twice, and is refused
+            with pytest.raises(cp.CpbError, match="already been reweighted"):
+                b.reweight_pairs(gamma)
         off2, after = b.fetch_pairs(0)
         assert np.array_equal(off, off2) and np.array_equal(before[:, 1:], after[:, 1:])
         for i in range(40):
