@@ -207,6 +207,9 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: no CPU baseline")
     args = ap.parse_args()
 
+    # Every timed pass plans its run anew (regions, bands, traceback schedule, chunks, work lists), as the first call on a new batch
+    # does: the engine would otherwise keep the plan of a batch that is run again with the same parameters (what EM iterations do).
+    os.environ["CPB_NO_PLAN_CACHE"] = "1"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -77,6 +77,7 @@ class CpbRunStats(C.Structure):
         ("twoPass", C.c_int32),
         ("msCheckpoint", C.c_double),
         ("pintFixups", C.c_int64),
+        ("planReused", C.c_int64),
         ("reweighted", C.c_int64),
     ]
 

@@ -297,6 +297,10 @@ struct Chunk {
     int64_t pair0, pair1;                /* pairs touched: [pair0, pair1] inclusive */
 };
 
+struct PlanKey { /* what a run's regions, bands, schedule, chunks and work lists depend on, apart from the batch itself */
+    int64_t mode, states, split, expansion, dynamic, minDiags, traceBack, budget;
+};
+
 struct cpb_batch {
     cpb_context *ctx = nullptr;
     int64_t n = 0;
@@ -321,6 +325,12 @@ struct cpb_batch {
     CpbRunStats stats;
     std::vector<RegionDev> hRegions;
     std::vector<BlockRec> hBlocks; /* compact, region order */
+    /* the plan of the last run, kept for the next one with the same key (run_impl) */
+    std::vector<Chunk> chunks;
+    PlanKey planKey;
+    bool planValid = false;
+    size_t planScratch = 0;
+    CpbRunStats planStats;
 };
 
 extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *seqX, const int64_t *xOff, const char *seqY, const int64_t *yOff,
@@ -508,11 +518,20 @@ static int64_t split_points32(const int32_t *anchors, int64_t nAnchors, int64_t 
 }
 
 static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
-    /* Pairs are independent: the split points and region records of every pair are made by a pool of host threads (this is a scan over
-     * all anchors, ~1 ms per 300 k anchors per thread), then one serial pass assigns the offsets into the device arrays. */
+    /* Pairs are independent: every host thread of a pool makes the split points and region records of a contiguous range of pairs
+     * (a scan over all anchors, ~1 ms per 300 k anchors per thread) with the offsets into the device arrays counted from the start
+     * of its range; the ranges' totals are then prefix-summed and every thread moves its records to their place in the batch's table. */
     const int64_t n = b->n;
-    std::vector<std::vector<RegionDev>> perPair((size_t) n);
-    auto work = [&](int64_t i0, int64_t i1) {
+    struct Part {
+        std::vector<RegionDev> regs;
+        int64_t diags = 0, blocks = 0, strips = 0; /* totals of the range */
+    };
+    const int64_t nThreads = std::max<int64_t>(1, std::min<int64_t>({ (int64_t) std::thread::hardware_concurrency(), (int64_t) 16, n / 256 }));
+    std::vector<Part> parts((size_t) nThreads);
+    auto work = [&](int64_t t) {
+        const int64_t i0 = n * t / nThreads, i1 = n * (t + 1) / nThreads;
+        Part &part = parts[(size_t) t];
+        part.regs.reserve((size_t) (i1 - i0) + 16);
         std::vector<int64_t> split;
         for (int64_t i = i0; i < i1; i++) {
             const int64_t lX = b->xOff[i + 1] - b->xOff[i], lY = b->yOff[i + 1] - b->yOff[i];
@@ -529,8 +548,6 @@ static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
                     nReg = split_points32(an, nA, lX, lY, p->splitMatrixBiggerThanThis, b->rl[i], b->rr[i], split.data(), nReg);
                 }
             }
-            std::vector<RegionDev> &out = perPair[(size_t) i];
-            out.reserve((size_t) nReg);
             int64_t j = 0;
             for (int64_t r = 0; r < nReg; r++) {
                 const int64_t x1 = split[4 * r], y1 = split[4 * r + 1], x2 = split[4 * r + 2], y2 = split[4 * r + 3];
@@ -540,6 +557,12 @@ static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
                 R.yBase = b->yOff[i] + y1;
                 R.anchorBase = a0 + j;
                 int64_t cnt = 0;
+                if (nReg == 1 && nA > 0 && an[3 * (nA - 1)] + an[3 * (nA - 1) + 1] < x2 + y2) {
+                    /* the only region of the pair: x + y grows along the anchors (checked by cpb_batch_create), the last one lies before the
+                     * region's last diagonal, so they all do -- no need to walk them */
+                    cnt = nA;
+                    j = nA;
+                }
                 /* anchors of this region: up to the first one on or past the region's last diagonal (impl/pairwiseAligner.c:1296-1308) */
                 while (j < nA && an[3 * j] + an[3 * j + 1] < x2 + y2) {
                     j++;
@@ -560,31 +583,48 @@ static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
                 }
                 /* consecutive traceback points are at least minDiags - (traceBack+1) diagonals apart (T moves to d - traceBack - 1) */
                 R.blockCap = (int32_t) (((int64_t) R.lX + R.lY) / (p->minDiagsBetweenTraceBack - p->traceBackDiagonals - 1) + 2);
-                out.push_back(R);
+                R.diagBase = part.diags;
+                R.blockBase = part.blocks;
+                R.stripBase = part.strips;
+                part.strips += (R.lX >> 5) + 1;
+                part.diags += (int64_t) R.lX + R.lY + 3; /* lX+lY+1 diagonals and two sentinels */
+                part.blocks += R.blockCap;
+                part.regs.push_back(R);
             }
         }
     };
-    const int64_t nThreads = std::max<int64_t>(1, std::min<int64_t>({ (int64_t) std::thread::hardware_concurrency(), (int64_t) 16, n / 256 }));
-    if (nThreads <= 1) {
-        work(0, n);
-    } else {
-        std::vector<std::thread> pool;
-        for (int64_t t = 0; t < nThreads; t++) pool.emplace_back(work, n * t / nThreads, n * (t + 1) / nThreads);
-        for (auto &t : pool) t.join();
-    }
-    b->hRegions.clear();
-    int64_t diagBase = 0, blockBase = 0, stripBase = 0;
-    for (int64_t i = 0; i < n; i++) {
-        for (RegionDev &R : perPair[(size_t) i]) {
-            R.diagBase = diagBase;
-            R.blockBase = blockBase;
-            R.stripBase = stripBase;
-            stripBase += (R.lX >> 5) + 1;
-            diagBase += (int64_t) R.lX + R.lY + 3; /* lX+lY+1 diagonals and two sentinels */
-            blockBase += R.blockCap;
-            b->hRegions.push_back(R);
+    auto run_pool = [&](auto &&fn) {
+        if (nThreads <= 1) {
+            fn((int64_t) 0);
+        } else {
+            std::vector<std::thread> pool;
+            for (int64_t t = 0; t < nThreads; t++) pool.emplace_back(fn, t);
+            for (auto &t : pool) t.join();
         }
+    };
+    run_pool(work);
+    std::vector<int64_t> first((size_t) nThreads + 1, 0), diag0((size_t) nThreads, 0), block0((size_t) nThreads, 0), strip0((size_t) nThreads, 0);
+    int64_t diagBase = 0, blockBase = 0, stripBase = 0;
+    for (int64_t t = 0; t < nThreads; t++) {
+        first[(size_t) t + 1] = first[(size_t) t] + (int64_t) parts[(size_t) t].regs.size();
+        diag0[(size_t) t] = diagBase;
+        block0[(size_t) t] = blockBase;
+        strip0[(size_t) t] = stripBase;
+        diagBase += parts[(size_t) t].diags;
+        blockBase += parts[(size_t) t].blocks;
+        stripBase += parts[(size_t) t].strips;
     }
+    b->hRegions.resize((size_t) first[(size_t) nThreads]);
+    run_pool([&](int64_t t) {
+        RegionDev *out = b->hRegions.data() + first[(size_t) t];
+        for (const RegionDev &R0 : parts[(size_t) t].regs) {
+            RegionDev R = R0;
+            R.diagBase += diag0[(size_t) t];
+            R.blockBase += block0[(size_t) t];
+            R.stripBase += strip0[(size_t) t];
+            *out++ = R;
+        }
+    });
     return CPB_OK;
 }
 
@@ -730,12 +770,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     const int nLists = mode == CPB_MODE_ALIGNED_PAIRS ? 1 : (mode == CPB_MODE_ALIGNED_PAIRS_INDELS ? 3 : 0);
     const int hmmLen = CPB_HMM_LEN(S);
 
-    int rc = build_regions(b, p, mode);
-    if (rc != CPB_OK) return rc;
-    stamp("build_regions");
-    std::vector<RegionDev> &regs = b->hRegions;
-    const int64_t nReg = (int64_t) regs.size();
-    stx.nRegions = nReg;
+    int rc = CPB_OK;
     for (int l = 0; l < 3; l++) {
         b->outCount[l] = 0;
         b->pairOff[l].assign(b->n + 1, 0);
@@ -748,174 +783,225 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         CUDA_TRY(cudaMemsetAsync(b->perPair.p, 0, std::max<int64_t>(b->n, 1) * hmmLen * sizeof(double), st));
         CUDA_TRY(cudaMemsetAsync(b->hmmTotal.p, 0, hmmLen * sizeof(double), st));
     }
+
+    /* The plan of a run -- regions, bands, traceback schedule, chunks, work lists -- depends on the batch, the mode, the state count
+     * and the banding parameters, not on the model's numbers: a batch that is run again with the same ones (every EM iteration of a
+     * resident batch) keeps its plan, host tables and device tables alike.  $CPB_NO_PLAN_CACHE=1 plans every run anew. */
+    std::vector<RegionDev> &regs = b->hRegions;
+    std::vector<BlockRec> &hBlocks = b->hBlocks;
+    std::vector<Chunk> &chunks = b->chunks;
+    int64_t nReg = 0, nDiagRecs = 0, totalBlocks = 0;
+    size_t scratchNeed = 0;
+    PlanKey key;
+    memset(&key, 0, sizeof(key));
+    key.mode = mode;
+    key.states = S;
+    key.split = p->splitMatrixBiggerThanThis;
+    key.expansion = p->diagonalExpansion;
+    key.dynamic = p->dynamicAnchorExpansion != 0;
+    key.minDiags = p->minDiagsBetweenTraceBack;
+    key.traceBack = p->traceBackDiagonals;
+    key.budget = (int64_t) ctx->scratchBudget;
+    auto make_plan = [&]() -> int {
+        int rc = build_regions(b, p, mode);
+        if (rc != CPB_OK) return rc;
+        stamp("build_regions");
+        nReg = (int64_t) regs.size();
+        stx.nRegions = nReg;
+        if (nReg == 0) return CPB_OK;
+        nDiagRecs = regs.back().diagBase + regs.back().lX + regs.back().lY + 3;
+        const int64_t blockSlots = regs.back().blockBase + regs.back().blockCap;
+        stx.diagonals = nDiagRecs - 2 * nReg; /* lX+lY+1 per region */
+
+        if ((rc = b->regions.reserve(nReg * sizeof(RegionDev))) != CPB_OK) return rc;
+        if ((rc = b->diags.reserve(nDiagRecs * sizeof(DiagRec))) != CPB_OK) return rc;
+        if ((rc = b->blocks.reserve(blockSlots * sizeof(BlockRec))) != CPB_OK) return rc;
+        const int64_t nStripRecs = regs.back().stripBase + (regs.back().lX >> 5) + 1;
+        if ((rc = b->strips.reserve(nStripRecs * sizeof(StripRec))) != CPB_OK) return rc;
+        if (mode != CPB_MODE_FORWARD) {
+            if ((rc = b->totals.reserve(nDiagRecs * sizeof(double))) != CPB_OK) return rc;
+        } else {
+            if ((rc = b->forwardOut.reserve(nReg * sizeof(double))) != CPB_OK) return rc;
+        }
+        CUDA_TRY(cudaMemcpyAsync(b->regions.p, regs.data(), nReg * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
+
+        /* K1: band + schedule */
+        {
+            BandArgs ba;
+            ba.regions = b->regions.as<RegionDev>();
+            ba.anchors = b->dAnchors.as<int32_t>();
+            ba.diags = b->diags.as<DiagRec>();
+            ba.blocks = b->blocks.as<BlockRec>();
+            ba.strips = b->strips.as<StripRec>();
+            ba.nRegions = (int32_t) nReg;
+            ba.expansion = (int32_t) p->diagonalExpansion;
+            ba.dynamic = (mode == CPB_MODE_FORWARD) ? 0 : (p->dynamicAnchorExpansion != 0); /* forward prob always uses the static band (:894) */
+            ba.minDiags = (int32_t) p->minDiagsBetweenTraceBack;
+            ba.traceBack = (int32_t) p->traceBackDiagonals;
+            ba.auxF = auxF;
+            ba.scheduleOn = mode != CPB_MODE_FORWARD;
+            size_t ev = tic(&stx.msBand);
+            k_band<<<(unsigned) ((nReg + BAND_WARPS - 1) / BAND_WARPS), 32 * BAND_WARPS, 0, st>>>(ba);
+            toc(ev);
+            stx.kernelLaunches++;
+        }
+        CUDA_TRY(cudaMemcpyAsync(regs.data(), b->regions.p, nReg * sizeof(RegionDev), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+
+        stamp("k_band + region sizes");
+        /* validate, gather the block table in compact region order */
+        totalBlocks = 0;
+        for (int64_t r = 0; r < nReg; r++) {
+            if (regs[r].err == 1) {
+                cpb_set_error("pair %d: anchors produce an invalid band diagonal (PAIRWISE_ALIGNMENT_EXCEPTION in the reference)", regs[r].pair);
+                finish_events();
+                return CPB_ERR_BAND;
+            }
+            if (regs[r].err == 2) {
+                cpb_set_error("internal: traceback block table overflow for pair %d", regs[r].pair);
+                finish_events();
+                return CPB_ERR_BAND;
+            }
+            if (regs[r].cells >= ((int64_t) 1 << 31)) {
+                cpb_set_error("pair %d: a single region has %lld band cells (limit 2^31)", regs[r].pair, (long long) regs[r].cells);
+                finish_events();
+                return CPB_ERR_ARGUMENT;
+            }
+            totalBlocks += regs[r].nBlocks;
+            stx.cells += regs[r].cells;
+            stx.maxWidth = std::max(stx.maxWidth, regs[r].maxW);
+        }
+        stx.nBlocks = totalBlocks;
+        hBlocks.resize(totalBlocks);
+        std::vector<int64_t> regionBlock0(nReg + 1, 0);
+        if (totalBlocks > 0) {
+            std::vector<BlockRec> slots(blockSlots);
+            CUDA_TRY(cudaMemcpy(slots.data(), b->blocks.p, blockSlots * sizeof(BlockRec), cudaMemcpyDeviceToHost));
+            int64_t k = 0;
+            for (int64_t r = 0; r < nReg; r++) {
+                regionBlock0[r] = k;
+                for (int j = 0; j < regs[r].nBlocks; j++) {
+                    hBlocks[k] = slots[regs[r].blockBase + j];
+                    hBlocks[k++].ckBase = -1;
+                }
+            }
+            regionBlock0[nReg] = k;
+            CUDA_TRY(cudaMemcpyAsync(b->blocks.p, hBlocks.data(), totalBlocks * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
+        }
+
+        stamp("block table");
+        /* chunk planning */
+        const int64_t bytesPerCell = (int64_t) sizeof(double) * 2 * nPlanes;
+        size_t budget = ctx->scratchBudget;
+        if (budget == 0) {
+            /* 70 % of what is free; a run that fits the scratch buffer already there does not need to ask the driver (cudaMemGetInfo
+             * costs tens of milliseconds once a few hundred buffers are live) */
+            size_t wholeRun = 0;
+            for (int64_t r = 0; r < nReg; r++) wholeRun += (size_t) ((regs[r].cells + 36) * bytesPerCell + (regs[r].auxDoubles + 6) * 8);
+            if (wholeRun + 256 <= ctx->scratch.cap) {
+                budget = ctx->scratch.cap;
+            } else {
+                size_t freeB = 0, totalB = 0;
+                CUDA_TRY(cudaMemGetInfo(&freeB, &totalB));
+                budget = (size_t) ((double) (freeB + ctx->scratch.cap) * 0.70);
+            }
+        }
+        chunks.clear();
+        {
+            int64_t r = 0;
+            while (r < nReg) {
+                Chunk c;
+                memset(&c, 0, sizeof(c));
+                c.region0 = r;
+                int64_t cells = 0, aux = 0, words = 0;
+                while (r < nReg) {
+                    const int64_t nc = cells + regs[r].cells + 32, na = aux + regs[r].auxDoubles + 4;
+                    if (r > c.region0 && (size_t) (nc * bytesPerCell + na * 8) > budget) break;
+                    regs[r].cellBase = cells;
+                    regs[r].auxBase = aux;
+                    regs[r].maskBase = words;
+                    cells = (nc + 3) & ~int64_t(3);
+                    aux = (na + 1) & ~int64_t(1);
+                    words += (regs[r].cells >> 5) + regs[r].lX + regs[r].lY + 4;
+                    r++;
+                }
+                c.region1 = r;
+                c.cells = cells;
+                c.aux = aux;
+                c.maskWords = words; /* provisional; final value below once the decades are counted */
+                c.stride = (cells + 31) & ~int64_t(31);
+                c.block0 = regionBlock0[c.region0];
+                c.block1 = regionBlock0[c.region1];
+                c.pair0 = regs[c.region0].pair;
+                c.pair1 = regs[c.region1 - 1].pair;
+                /* decades: ceil(owned diagonals / 10) per block, numbered consecutively inside the chunk */
+                int64_t dec = 0;
+                for (int64_t k = c.block0; k < c.block1; k++) {
+                    hBlocks[k].decadeBase = dec;
+                    dec += (hBlocks[k].from - hBlocks[k].T + 9) / 10;
+                }
+                c.decades = dec;
+                c.maskWords = (c.cells >> 5) + dec + 2; /* k_posterior: word of chunk cell C in decade g is (C >> 5) + g */
+                chunks.push_back(c);
+            }
+        }
+        stx.nChunks = (int64_t) chunks.size();
+        stamp("chunk planning");
+        if (totalBlocks > 0) CUDA_TRY(cudaMemcpyAsync(b->blocks.p, hBlocks.data(), totalBlocks * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
+        scratchNeed = 0;
+        for (auto &c : chunks) scratchNeed = std::max(scratchNeed, (size_t) (c.stride * bytesPerCell + c.aux * 8 + 256));
+        if ((rc = ctx->scratch.reserve(std::max<size_t>(scratchNeed, 256))) != CPB_OK) return rc;
+
+        stamp("scratch");
+        /* launch lists: forward regions per class, backward blocks per class, all blocks in order */
+        std::vector<int32_t> lists;
+        for (auto &c : chunks) {
+            c.allBlocksOff = (int64_t) lists.size();
+            for (int64_t k = c.block0; k < c.block1; k++) lists.push_back((int32_t) k);
+            /* strip engine: one list of regions and one of blocks, most expensive first (work is fetched dynamically) */
+            c.stripFwdOff = (int64_t) lists.size();
+            for (int64_t r = c.region0; r < c.region1; r++) lists.push_back((int32_t) r);
+            order_by_cost_descending(lists.data() + c.stripFwdOff, c.region1 - c.region0, [&](int32_t x) { return (int64_t) regs[x].cells; });
+            c.stripBwdOff = (int64_t) lists.size();
+            for (int64_t k = c.block0; k < c.block1; k++) lists.push_back((int32_t) k);
+            order_by_cost_descending(lists.data() + c.stripBwdOff, c.block1 - c.block0, [&](int32_t k) { return (int64_t) hBlocks[k].cells; });
+        }
+        if ((rc = b->lists.reserve(std::max<size_t>(lists.size(), 1) * sizeof(int32_t))) != CPB_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(b->lists.p, lists.data(), lists.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->regions.p, regs.data(), nReg * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
+
+        stamp("lists");
+        return CPB_OK;
+    };
+    if (b->planValid && memcmp(&key, &b->planKey, sizeof(key)) == 0 && getenv("CPB_NO_PLAN_CACHE") == nullptr) {
+        nReg = (int64_t) regs.size();
+        nDiagRecs = regs.back().diagBase + regs.back().lX + regs.back().lY + 3;
+        totalBlocks = (int64_t) hBlocks.size();
+        scratchNeed = b->planScratch;
+        stx.nRegions = b->planStats.nRegions;
+        stx.diagonals = b->planStats.diagonals;
+        stx.cells = b->planStats.cells;
+        stx.maxWidth = b->planStats.maxWidth;
+        stx.nBlocks = b->planStats.nBlocks;
+        stx.nChunks = b->planStats.nChunks;
+        stx.planReused = 1;
+        if ((rc = ctx->scratch.reserve(std::max<size_t>(scratchNeed, 256))) != CPB_OK) return rc; /* the context's scratch may have served another batch since */
+        stamp("plan reused");
+    } else {
+        b->planValid = false;
+        if ((rc = make_plan()) != CPB_OK) return rc;
+        if (nReg > 0) {
+            b->planKey = key;
+            b->planStats = stx;
+            b->planScratch = scratchNeed;
+            b->planValid = true;
+        }
+    }
     if (nReg == 0) {
         CUDA_TRY(cudaStreamSynchronize(st));
         return CPB_OK;
     }
-    const int64_t nDiagRecs = regs.back().diagBase + regs.back().lX + regs.back().lY + 3;
-    const int64_t blockSlots = regs.back().blockBase + regs.back().blockCap;
-    stx.diagonals = nDiagRecs - 2 * nReg; /* lX+lY+1 per region */
-
-    if ((rc = b->regions.reserve(nReg * sizeof(RegionDev))) != CPB_OK) return rc;
-    if ((rc = b->diags.reserve(nDiagRecs * sizeof(DiagRec))) != CPB_OK) return rc;
-    if ((rc = b->blocks.reserve(blockSlots * sizeof(BlockRec))) != CPB_OK) return rc;
-    const int64_t nStripRecs = regs.back().stripBase + (regs.back().lX >> 5) + 1;
-    if ((rc = b->strips.reserve(nStripRecs * sizeof(StripRec))) != CPB_OK) return rc;
-    if (mode != CPB_MODE_FORWARD) {
-        if ((rc = b->totals.reserve(nDiagRecs * sizeof(double))) != CPB_OK) return rc;
-    } else {
-        if ((rc = b->forwardOut.reserve(nReg * sizeof(double))) != CPB_OK) return rc;
-    }
-    CUDA_TRY(cudaMemcpyAsync(b->regions.p, regs.data(), nReg * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
-
-    /* K1: band + schedule */
-    {
-        BandArgs ba;
-        ba.regions = b->regions.as<RegionDev>();
-        ba.anchors = b->dAnchors.as<int32_t>();
-        ba.diags = b->diags.as<DiagRec>();
-        ba.blocks = b->blocks.as<BlockRec>();
-        ba.strips = b->strips.as<StripRec>();
-        ba.nRegions = (int32_t) nReg;
-        ba.expansion = (int32_t) p->diagonalExpansion;
-        ba.dynamic = (mode == CPB_MODE_FORWARD) ? 0 : (p->dynamicAnchorExpansion != 0); /* forward prob always uses the static band (:894) */
-        ba.minDiags = (int32_t) p->minDiagsBetweenTraceBack;
-        ba.traceBack = (int32_t) p->traceBackDiagonals;
-        ba.auxF = auxF;
-        ba.scheduleOn = mode != CPB_MODE_FORWARD;
-        size_t ev = tic(&stx.msBand);
-        k_band<<<(unsigned) ((nReg + BAND_WARPS - 1) / BAND_WARPS), 32 * BAND_WARPS, 0, st>>>(ba);
-        toc(ev);
-        stx.kernelLaunches++;
-    }
-    CUDA_TRY(cudaMemcpyAsync(regs.data(), b->regions.p, nReg * sizeof(RegionDev), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    CUDA_TRY(cudaGetLastError());
-
-    stamp("k_band + region sizes");
-    /* validate, gather the block table in compact region order */
-    int64_t totalBlocks = 0;
-    for (int64_t r = 0; r < nReg; r++) {
-        if (regs[r].err == 1) {
-            cpb_set_error("pair %d: anchors produce an invalid band diagonal (PAIRWISE_ALIGNMENT_EXCEPTION in the reference)", regs[r].pair);
-            finish_events();
-            return CPB_ERR_BAND;
-        }
-        if (regs[r].err == 2) {
-            cpb_set_error("internal: traceback block table overflow for pair %d", regs[r].pair);
-            finish_events();
-            return CPB_ERR_BAND;
-        }
-        if (regs[r].cells >= ((int64_t) 1 << 31)) {
-            cpb_set_error("pair %d: a single region has %lld band cells (limit 2^31)", regs[r].pair, (long long) regs[r].cells);
-            finish_events();
-            return CPB_ERR_ARGUMENT;
-        }
-        totalBlocks += regs[r].nBlocks;
-        stx.cells += regs[r].cells;
-        stx.maxWidth = std::max(stx.maxWidth, regs[r].maxW);
-    }
-    stx.nBlocks = totalBlocks;
-    std::vector<BlockRec> &hBlocks = b->hBlocks;
-    hBlocks.resize(totalBlocks);
-    std::vector<int64_t> regionBlock0(nReg + 1, 0);
-    if (totalBlocks > 0) {
-        std::vector<BlockRec> slots(blockSlots);
-        CUDA_TRY(cudaMemcpy(slots.data(), b->blocks.p, blockSlots * sizeof(BlockRec), cudaMemcpyDeviceToHost));
-        int64_t k = 0;
-        for (int64_t r = 0; r < nReg; r++) {
-            regionBlock0[r] = k;
-            for (int j = 0; j < regs[r].nBlocks; j++) {
-                hBlocks[k] = slots[regs[r].blockBase + j];
-                hBlocks[k++].ckBase = -1;
-            }
-        }
-        regionBlock0[nReg] = k;
-        CUDA_TRY(cudaMemcpyAsync(b->blocks.p, hBlocks.data(), totalBlocks * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
-    }
-
-    stamp("block table");
-    /* chunk planning */
-    const int64_t bytesPerCell = (int64_t) sizeof(double) * 2 * nPlanes;
-    size_t budget = ctx->scratchBudget;
-    if (budget == 0) {
-        /* 70 % of what is free; a run that fits the scratch buffer already there does not need to ask the driver (cudaMemGetInfo
-         * costs tens of milliseconds once a few hundred buffers are live) */
-        size_t wholeRun = 0;
-        for (int64_t r = 0; r < nReg; r++) wholeRun += (size_t) ((regs[r].cells + 36) * bytesPerCell + (regs[r].auxDoubles + 6) * 8);
-        if (wholeRun + 256 <= ctx->scratch.cap) {
-            budget = ctx->scratch.cap;
-        } else {
-            size_t freeB = 0, totalB = 0;
-            CUDA_TRY(cudaMemGetInfo(&freeB, &totalB));
-            budget = (size_t) ((double) (freeB + ctx->scratch.cap) * 0.70);
-        }
-    }
-    std::vector<Chunk> chunks;
-    {
-        int64_t r = 0;
-        while (r < nReg) {
-            Chunk c;
-            memset(&c, 0, sizeof(c));
-            c.region0 = r;
-            int64_t cells = 0, aux = 0, words = 0;
-            while (r < nReg) {
-                const int64_t nc = cells + regs[r].cells + 32, na = aux + regs[r].auxDoubles + 4;
-                if (r > c.region0 && (size_t) (nc * bytesPerCell + na * 8) > budget) break;
-                regs[r].cellBase = cells;
-                regs[r].auxBase = aux;
-                regs[r].maskBase = words;
-                cells = (nc + 3) & ~int64_t(3);
-                aux = (na + 1) & ~int64_t(1);
-                words += (regs[r].cells >> 5) + regs[r].lX + regs[r].lY + 4;
-                r++;
-            }
-            c.region1 = r;
-            c.cells = cells;
-            c.aux = aux;
-            c.maskWords = words; /* provisional; final value below once the decades are counted */
-            c.stride = (cells + 31) & ~int64_t(31);
-            c.block0 = regionBlock0[c.region0];
-            c.block1 = regionBlock0[c.region1];
-            c.pair0 = regs[c.region0].pair;
-            c.pair1 = regs[c.region1 - 1].pair;
-            /* decades: ceil(owned diagonals / 10) per block, numbered consecutively inside the chunk */
-            int64_t dec = 0;
-            for (int64_t k = c.block0; k < c.block1; k++) {
-                hBlocks[k].decadeBase = dec;
-                dec += (hBlocks[k].from - hBlocks[k].T + 9) / 10;
-            }
-            c.decades = dec;
-            c.maskWords = (c.cells >> 5) + dec + 2; /* k_posterior: word of chunk cell C in decade g is (C >> 5) + g */
-            chunks.push_back(c);
-        }
-    }
-    stx.nChunks = (int64_t) chunks.size();
-    stamp("chunk planning");
-    if (totalBlocks > 0) CUDA_TRY(cudaMemcpyAsync(b->blocks.p, hBlocks.data(), totalBlocks * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
-    size_t scratchNeed = 0;
-    for (auto &c : chunks) scratchNeed = std::max(scratchNeed, (size_t) (c.stride * bytesPerCell + c.aux * 8 + 256));
-    if ((rc = ctx->scratch.reserve(std::max<size_t>(scratchNeed, 256))) != CPB_OK) return rc;
-
-    stamp("scratch");
-    /* launch lists: forward regions per class, backward blocks per class, all blocks in order */
-    std::vector<int32_t> lists;
-    for (auto &c : chunks) {
-        c.allBlocksOff = (int64_t) lists.size();
-        for (int64_t k = c.block0; k < c.block1; k++) lists.push_back((int32_t) k);
-        /* strip engine: one list of regions and one of blocks, most expensive first (work is fetched dynamically) */
-        c.stripFwdOff = (int64_t) lists.size();
-        for (int64_t r = c.region0; r < c.region1; r++) lists.push_back((int32_t) r);
-        order_by_cost_descending(lists.data() + c.stripFwdOff, c.region1 - c.region0, [&](int32_t x) { return (int64_t) regs[x].cells; });
-        c.stripBwdOff = (int64_t) lists.size();
-        for (int64_t k = c.block0; k < c.block1; k++) lists.push_back((int32_t) k);
-        order_by_cost_descending(lists.data() + c.stripBwdOff, c.block1 - c.block0, [&](int32_t k) { return (int64_t) hBlocks[k].cells; });
-    }
-    if ((rc = b->lists.reserve(std::max<size_t>(lists.size(), 1) * sizeof(int32_t))) != CPB_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(b->lists.p, lists.data(), lists.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(b->regions.p, regs.data(), nReg * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
-
-    stamp("lists");
     int64_t maxChunkBlocks = 1, maxDecades = 1, maxMaskWords = 1, maxChunkPairs = 1;
     for (auto &c : chunks) {
         maxChunkBlocks = std::max(maxChunkBlocks, c.block1 - c.block0);

@@ -143,6 +143,8 @@ typedef struct {
     int32_t twoPass;       /* 1 if the forward sweep ran as checkpoint pass + per-block recomputation (chunked runs of long regions) */
     double msCheckpoint;   /* part of msForward spent in the plane-less checkpoint pass (0 unless twoPass) */
     int64_t pintFixups;    /* weights floor(p * 1e7) the host recomputed with its own libm (cells within 2e-8 of an integer) */
+    int64_t planReused;    /* 1 if this run kept the regions, bands, schedule, chunks and work lists of the batch's previous run (same mode,
+                            * state count, banding parameters and scratch budget; $CPB_NO_PLAN_CACHE=1 turns that off) */
     int64_t reweighted;    /* 1 once cpb_batch_reweight_pairs has rewritten list 0 of this run: fetches and scores then see those weights */
 } CpbRunStats;
 /* Result sink: a host buffer (page-locked for full speed: cpb_pinned_alloc, cudaHostAlloc, torch pin_memory) of capacityTriples

@@ -584,3 +584,53 @@ def test_result_sink_delivers_the_same_lists(ctx, oracle):
     finally:
         ctx.set_scratch_budget(0)
         b.close()
+
+
+def test_plan_is_kept_between_runs_with_the_same_parameters(ctx, oracle, monkeypatch):
+    """A batch that is run again with the same mode, state count and banding parameters keeps its regions, bands, schedule,
+    chunks and work lists (CpbRunStats.planReused) -- what every EM iteration of a resident batch does, with a new model each
+    time.  The results must be those of a fresh batch; any change of the key plans anew."""
+    rng = np.random.default_rng(77)
+    cases = small_cases(rng, 24, max_len=260, ragged=True)
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    p.minDiagsBetweenTraceBack, p.traceBackDiagonals, p.splitMatrixBiggerThanThis = 60, 20, 40 * 40
+
+    def fresh(spec, q, mode):
+        b = run_batch(ctx, spec, q, cases, mode)
+        assert b.stats().planReused == 0
+        out = (b.fetch_pairs(0)[1].copy(), b.fetch_pairs(0)[0].copy()) if mode == cp.MODE_ALIGNED_PAIRS else b.fetch_expectations()
+        b.close()
+        return out
+
+    five, three = helpers.ModelSpec(cp.fiveState), helpers.ModelSpec(cp.threeState)
+    b = run_batch(ctx, five, p, cases, cp.MODE_ALIGNED_PAIRS)
+    first = b.fetch_pairs(0)[1].copy()
+    b.run(five.cpb(), p, cp.MODE_ALIGNED_PAIRS)
+    assert b.stats().planReused == 1 and b.stats().cells > 0 and b.stats().nBlocks > 0
+    assert np.array_equal(b.fetch_pairs(0)[1], first) and np.array_equal(first, fresh(five, p, cp.MODE_ALIGNED_PAIRS)[0])
+    # another state count, another mode, other banding parameters: each plans anew, and gives what a fresh batch gives
+    b.run(three.cpb(), p, cp.MODE_ALIGNED_PAIRS)
+    assert b.stats().planReused == 0
+    assert np.array_equal(b.fetch_pairs(0)[1], fresh(three, p, cp.MODE_ALIGNED_PAIRS)[0])
+    b.run(three.cpb(), p, cp.MODE_EXPECTATIONS)
+    assert b.stats().planReused == 0
+    per0, tot0 = b.fetch_expectations()
+    # EM: the same plan, a different model
+    other = helpers.ModelSpec.random(rng, cp.threeState)
+    b.run(other.cpb(), p, cp.MODE_EXPECTATIONS)
+    assert b.stats().planReused == 1
+    per1, tot1 = b.fetch_expectations()
+    perF, totF = fresh(other, p, cp.MODE_EXPECTATIONS)
+    assert np.array_equal(per1, perF, equal_nan=True) and np.array_equal(tot1, totF, equal_nan=True)
+    assert not np.array_equal(per0, per1, equal_nan=True)
+    q = cp.pairwiseAlignmentBandingParameters_construct()
+    q.minDiagsBetweenTraceBack, q.traceBackDiagonals, q.splitMatrixBiggerThanThis, q.diagonalExpansion = 60, 20, 40 * 40, 12
+    b.run(five.cpb(), q, cp.MODE_ALIGNED_PAIRS)
+    assert b.stats().planReused == 0
+    assert np.array_equal(b.fetch_pairs(0)[1], fresh(five, q, cp.MODE_ALIGNED_PAIRS)[0])
+    b.run(five.cpb(), q, cp.MODE_ALIGNED_PAIRS)
+    assert b.stats().planReused == 1
+    monkeypatch.setenv("CPB_NO_PLAN_CACHE", "1")
+    b.run(five.cpb(), q, cp.MODE_ALIGNED_PAIRS)
+    assert b.stats().planReused == 0
+    b.close()

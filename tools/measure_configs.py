@@ -21,7 +21,13 @@ import cpecan_b200 as cp  # noqa: E402
 from cpecan_b200 import synth  # noqa: E402
 
 
-def timed(batch, model, p, mode, steps=2):
+def timed(batch, model, p, mode, steps=2, keep_plan=False):
+    # keep_plan: the batch keeps its regions / bands / chunks between runs (EM iterations of a resident batch); otherwise every pass
+    # plans anew, as the one call on a new batch does
+    if keep_plan:
+        os.environ.pop("CPB_NO_PLAN_CACHE", None)
+    else:
+        os.environ["CPB_NO_PLAN_CACHE"] = "1"
     batch.run(model, p, mode)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -91,6 +97,8 @@ def main():
         for name, m in (("SM5", sm5), ("SM3", sm3)):
             dt = timed(b, m, pe, cp.MODE_EXPECTATIONS)
             line("C4: %d x 2 kb expectations %s (e=10)" % (n, name), n, b.stats(), dt)
+            dt = timed(b, m, pe, cp.MODE_EXPECTATIONS, keep_plan=True)
+            line("C4: %d x 2 kb expectations %s (e=10), plan kept between EM iterations" % (n, name), n, b.stats(), dt)
         b.close()
     if on("C5"):
         k = max(4, int(round(64 * args.scale ** 0.5)))
