@@ -2,7 +2,7 @@
  * engine.cu -- host orchestration of libcpecan_b200 (C-ABI in include/cpecan_b200.h).
  *
  * One batch run =
- *   host : split every pair at large anchor gaps into regions (cpb_split_points; reference
+ *   k_split_flags + host : split every pair at large anchor gaps into regions (cpb_split_points; reference
  *          getPosteriorProbsWithBandingSplittingAlignmentsByLargeGaps, impl/pairwiseAligner.c:1273-1326)
  *   K1   : device band builder + traceback schedule, one small D2H of per-region sizes
  *   host : pack regions into chunks that fit the scratch budget, bucket work by band width
@@ -314,6 +314,8 @@ struct cpb_batch {
     bool reweighted = false;         /* cpb_batch_reweight_pairs has rewritten list 0 of the last run in place */
     int64_t oddExpansionPair = -1;   /* first pair with an odd anchor expansion: only an error for runs with dynamicAnchorExpansion (:166) */
     DevBuf symX, symY, dAnchors;
+    DevBuf dPairTab;   /* aOff, xOff, yOff as the device needs them for k_split_flags: 3 x (n + 1) int64 */
+    DevBuf splitFlags; /* one bit per gap between anchors: 1 = getSplitPoints cuts the pair there; word 0 of the buffer counts the pairs with a cut */
     /* run state */
     DevBuf strips;
     DevBuf regions, diags, blocks, totals, lists, counts, offsets, masks, tileSums, pairCounts, partials, pairBlockOff, perPair, hmmTotal, forwardOut;
@@ -462,6 +464,13 @@ extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *se
         }
         CUDA_TRY(cudaMemcpyAsync(b->dAnchors.p, b->anchors, bytes, cudaMemcpyHostToDevice, st));
     }
+    if (nPairs > 0) {
+        const size_t tab = (size_t) (nPairs + 1) * sizeof(int64_t);
+        if ((rc = b->dPairTab.reserve(3 * tab)) != CPB_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(b->dPairTab.as<char>(), b->aOff.data(), tab, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->dPairTab.as<char>() + tab, b->xOff.data(), tab, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->dPairTab.as<char>() + 2 * tab, b->yOff.data(), tab, cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     guard.b = nullptr;
@@ -472,7 +481,7 @@ extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *se
 extern "C" void cpb_batch_destroy(cpb_batch *b) {
     if (b == nullptr) return;
     cudaSetDevice(b->ctx->device);
-    DevBuf *bufs[] = { &b->strips, &b->symX, &b->symY, &b->dAnchors, &b->regions, &b->diags, &b->blocks, &b->totals, &b->lists, &b->counts,
+    DevBuf *bufs[] = { &b->strips, &b->symX, &b->symY, &b->dAnchors, &b->dPairTab, &b->splitFlags, &b->regions, &b->diags, &b->blocks, &b->totals, &b->lists, &b->counts,
                        &b->offsets, &b->masks, &b->tileSums, &b->pairCounts, &b->partials, &b->pairBlockOff, &b->perPair, &b->hmmTotal, &b->forwardOut, &b->out[0], &b->out[1],
                        &b->out[2], &b->ckRegions, &b->ckDiags, &b->ckSizes, &b->ckpt };
     for (DevBuf *d : bufs) d->release();
@@ -483,44 +492,14 @@ extern "C" void cpb_batch_destroy(cpb_batch *b) {
 /* ------------------------------------------------------------------------------------------------
  * region construction on the host
  * ---------------------------------------------------------------------------------------------- */
-/* cpb_split_points (model.c; getSplitPoints, impl/pairwiseAligner.c:1230-1257) over the int32 triples the batch keeps */
-static int64_t split_points32(const int32_t *anchors, int64_t nAnchors, int64_t lX, int64_t lY, int64_t splitBiggerThan, int raggedLeft,
-                              int raggedRight, int64_t *out4, int64_t cap) {
-    int64_t n = 0;
-    auto sink = [&](int64_t x1, int64_t y1, int64_t x2, int64_t y2) {
-        if (n < cap) {
-            out4[4 * n] = x1;
-            out4[4 * n + 1] = y1;
-            out4[4 * n + 2] = x2;
-            out4[4 * n + 3] = y2;
-        }
-        n++;
-    };
-    const int64_t half = (int64_t) sqrt((double) splitBiggerThan);
-    int64_t openX = 0, openY = 0, prevX = 0, prevY = 0; /* start of the region being grown; one past the previous anchor */
-    int lastGapSplit = 0;
-    for (int64_t i = 0; i <= nAnchors; i++) {
-        const int64_t nextX = i < nAnchors ? anchors[3 * i] : lX, nextY = i < nAnchors ? anchors[3 * i + 1] : lY;
-        const int64_t gapX = nextX - prevX, gapY = nextY - prevY;
-        lastGapSplit = 0;
-        if (gapX * gapY > splitBiggerThan) {
-            const int64_t hX = gapX / 2 > half ? half : gapX / 2, hY = gapY / 2 > half ? half : gapY / 2;
-            if (!(raggedLeft && i == 0)) sink(openX, openY, prevX + hX, prevY + hY); /* a ragged left end drops the region before the first anchor */
-            openX = nextX - hX;
-            openY = nextY - hY;
-            lastGapSplit = 1;
-        }
-        prevX = nextX + 1;
-        prevY = nextY + 1;
-    }
-    if (!lastGapSplit || !raggedRight) sink(openX, openY, lX, lY); /* a ragged right end drops the region after a trailing split */
-    return n;
-}
-
-static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
-    /* Pairs are independent: every host thread of a pool makes the split points and region records of a contiguous range of pairs
-     * (a scan over all anchors, ~1 ms per 300 k anchors per thread) with the offsets into the device arrays counted from the start
-     * of its range; the ranges' totals are then prefix-summed and every thread moves its records to their place in the batch's table. */
+/* Region records of every pair from the gaps k_split_flags marked (getSplitPoints, impl/pairwiseAligner.c:1230-1257; the model.c
+ * restatement cpb_split_points is what the tests compare with).  `flags` = the host copy of the bit array, nullptr if no pair is cut
+ * (or the mode never cuts: computeForwardProbability takes the whole matrix). */
+static int build_regions(cpb_batch *b, const CpbParams *p, int mode, const uint32_t *flags) {
+    /* Pairs are independent: every host thread of a pool makes the region records of a contiguous range of pairs with the offsets
+     * into the device arrays counted from the start of its range; the ranges' totals are then prefix-summed and every thread moves its
+     * records to their place in the batch's table.  A region's anchors are those between the two cuts that bound it, so nobody
+     * walks the anchors here. */
     const int64_t n = b->n;
     struct Part {
         std::vector<RegionDev> regs;
@@ -528,59 +507,28 @@ static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
     };
     const int64_t nThreads = std::max<int64_t>(1, std::min<int64_t>({ (int64_t) std::thread::hardware_concurrency(), (int64_t) 16, n / 256 }));
     std::vector<Part> parts((size_t) nThreads);
+    const int64_t half = (int64_t) sqrt((double) p->splitMatrixBiggerThanThis);
     auto work = [&](int64_t t) {
         const int64_t i0 = n * t / nThreads, i1 = n * (t + 1) / nThreads;
         Part &part = parts[(size_t) t];
         part.regs.reserve((size_t) (i1 - i0) + 16);
-        std::vector<int64_t> split;
         for (int64_t i = i0; i < i1; i++) {
             const int64_t lX = b->xOff[i + 1] - b->xOff[i], lY = b->yOff[i + 1] - b->yOff[i];
             const int64_t a0 = b->aOff[i], nA = b->aOff[i + 1] - a0;
             const int32_t *an = b->anchors + 3 * a0;
-            int64_t nReg = 1;
-            if (mode == CPB_MODE_FORWARD) {
-                split.assign({ 0, 0, lX, lY });
-            } else {
-                split.resize(4 * 4);
-                nReg = split_points32(an, nA, lX, lY, p->splitMatrixBiggerThanThis, b->rl[i], b->rr[i], split.data(), 4);
-                if (nReg > 4) {
-                    split.resize(4 * nReg);
-                    nReg = split_points32(an, nA, lX, lY, p->splitMatrixBiggerThanThis, b->rl[i], b->rr[i], split.data(), nReg);
-                }
-            }
-            int64_t j = 0;
-            for (int64_t r = 0; r < nReg; r++) {
-                const int64_t x1 = split[4 * r], y1 = split[4 * r + 1], x2 = split[4 * r + 2], y2 = split[4 * r + 3];
+            const size_t firstOfPair = part.regs.size();
+            auto emit = [&](int64_t x1, int64_t y1, int64_t x2, int64_t y2, int64_t j0, int64_t j1) {
                 RegionDev R;
                 memset(&R, 0, sizeof(R));
                 R.xBase = b->xOff[i] + x1;
                 R.yBase = b->yOff[i] + y1;
-                R.anchorBase = a0 + j;
-                int64_t cnt = 0;
-                if (nReg == 1 && nA > 0 && an[3 * (nA - 1)] + an[3 * (nA - 1) + 1] < x2 + y2) {
-                    /* the only region of the pair: x + y grows along the anchors (checked by cpb_batch_create), the last one lies before the
-                     * region's last diagonal, so they all do -- no need to walk them */
-                    cnt = nA;
-                    j = nA;
-                }
-                /* anchors of this region: up to the first one on or past the region's last diagonal (impl/pairwiseAligner.c:1296-1308) */
-                while (j < nA && an[3 * j] + an[3 * j + 1] < x2 + y2) {
-                    j++;
-                    cnt++;
-                }
-                R.nAnchors = (int32_t) cnt;
+                R.anchorBase = a0 + j0;
+                R.nAnchors = (int32_t) (j1 - j0); /* the anchors before the region's last diagonal (impl/pairwiseAligner.c:1296-1308): those up to the cut */
                 R.lX = (int32_t) (x2 - x1);
                 R.lY = (int32_t) (y2 - y1);
                 R.pair = (int32_t) i;
                 R.ox = (int32_t) x1;
                 R.oy = (int32_t) y1;
-                if (mode == CPB_MODE_FORWARD) {
-                    R.raggedL = b->rl[i];
-                    R.raggedR = b->rr[i];
-                } else {
-                    R.raggedL = b->rl[i] || r > 0;
-                    R.raggedR = b->rr[i] || r < nReg - 1;
-                }
                 /* consecutive traceback points are at least minDiags - (traceBack+1) diagonals apart (T moves to d - traceBack - 1) */
                 R.blockCap = (int32_t) (((int64_t) R.lX + R.lY) / (p->minDiagsBetweenTraceBack - p->traceBackDiagonals - 1) + 2);
                 R.diagBase = part.diags;
@@ -590,6 +538,42 @@ static int build_regions(cpb_batch *b, const CpbParams *p, int mode) {
                 part.diags += (int64_t) R.lX + R.lY + 3; /* lX+lY+1 diagonals and two sentinels */
                 part.blocks += R.blockCap;
                 part.regs.push_back(R);
+            };
+            int64_t openX = 0, openY = 0, openJ = 0; /* start of the region being grown, its first anchor */
+            bool lastGapSplit = false;
+            if (flags != nullptr && mode != CPB_MODE_FORWARD) {
+                /* the set bits of [bit0, bit0 + nA], in ascending order */
+                const int64_t bit0 = a0 + i, bit1 = bit0 + nA;
+                for (int64_t w = bit0 >> 5; w <= bit1 >> 5; w++) {
+                    uint32_t m = flags[w];
+                    if (w == bit0 >> 5) m &= 0xFFFFFFFFu << (bit0 & 31);
+                    if (w == bit1 >> 5 && (bit1 & 31) != 31) m &= (2u << (bit1 & 31)) - 1u;
+                    while (m != 0) {
+                        const int64_t g = (w << 5) + __builtin_ctz(m) - bit0;
+                        m &= m - 1;
+                        const int64_t prevX = g > 0 ? (int64_t) an[3 * (g - 1)] + 1 : 0, prevY = g > 0 ? (int64_t) an[3 * (g - 1) + 1] + 1 : 0;
+                        const int64_t nextX = g < nA ? (int64_t) an[3 * g] : lX, nextY = g < nA ? (int64_t) an[3 * g + 1] : lY;
+                        const int64_t gapX = nextX - prevX, gapY = nextY - prevY;
+                        const int64_t hX = gapX / 2 > half ? half : gapX / 2, hY = gapY / 2 > half ? half : gapY / 2;
+                        if (!(b->rl[i] && g == 0)) emit(openX, openY, prevX + hX, prevY + hY, openJ, g); /* a ragged left end drops the region before the first anchor */
+                        openX = nextX - hX;
+                        openY = nextY - hY;
+                        openJ = g;
+                        lastGapSplit = g == nA;
+                    }
+                }
+            }
+            if (!lastGapSplit || !b->rr[i]) emit(openX, openY, lX, lY, openJ, nA); /* a ragged right end drops the region after a trailing cut */
+            const size_t nOfPair = part.regs.size() - firstOfPair;
+            for (size_t r = 0; r < nOfPair; r++) {
+                RegionDev &R = part.regs[firstOfPair + r];
+                if (mode == CPB_MODE_FORWARD) {
+                    R.raggedL = b->rl[i];
+                    R.raggedR = b->rr[i];
+                } else {
+                    R.raggedL = b->rl[i] || r > 0;
+                    R.raggedR = b->rr[i] || r + 1 < nOfPair;
+                }
             }
         }
     };
@@ -803,7 +787,46 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     key.traceBack = p->traceBackDiagonals;
     key.budget = (int64_t) ctx->scratchBudget;
     auto make_plan = [&]() -> int {
-        int rc = build_regions(b, p, mode);
+        int rc = CPB_OK;
+        /* where the pairs are cut into regions: decided on the device, which has the anchors; the host gets one bit per gap */
+        const uint32_t *hostFlags = nullptr;
+        struct PinnedLoan { /* goes back to the context's pool when the plan is made, or on an error return */
+            PinnedPool *pool = nullptr;
+            void *p = nullptr;
+            ~PinnedLoan() {
+                if (p != nullptr) pool->give(p);
+            }
+        } loan;
+        std::vector<uint32_t> pageable;
+        if (mode != CPB_MODE_FORWARD && b->n > 0) {
+            const int64_t nBits = b->aOff[b->n] + b->n;
+            const size_t words = (size_t) ((nBits + 31) / 32 + 1), head = 4; /* word 0: pairs with a cut; the bits start at word 4 */
+            if ((rc = b->splitFlags.reserve((head + words) * sizeof(uint32_t))) != CPB_OK) return rc;
+            uint32_t *dFlags = b->splitFlags.as<uint32_t>();
+            CUDA_TRY(cudaMemsetAsync(dFlags, 0, (head + words) * sizeof(uint32_t), st));
+            const int64_t *tab = b->dPairTab.as<int64_t>();
+            k_split_flags<<<(unsigned) ((b->n * 32 + 255) / 256), 256, 0, st>>>(b->dAnchors.as<int32_t>(), tab, tab + (b->n + 1), tab + 2 * (b->n + 1), (int) b->n,
+                                                                              (long long) p->splitMatrixBiggerThanThis, dFlags + head, dFlags);
+            stx.kernelLaunches++;
+            uint32_t cutPairs = 0;
+            CUDA_TRY(cudaMemcpyAsync(&cutPairs, dFlags, sizeof(cutPairs), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaGetLastError());
+            if (cutPairs > 0) {
+                loan.pool = &ctx->pinned;
+                loan.p = ctx->pinned.take(words * sizeof(uint32_t));
+                uint32_t *dst = static_cast<uint32_t *>(loan.p);
+                if (dst == nullptr) {
+                    pageable.resize(words);
+                    dst = pageable.data();
+                }
+                CUDA_TRY(cudaMemcpyAsync(dst, dFlags + head, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                hostFlags = dst;
+            }
+        }
+        stamp("k_split_flags");
+        rc = build_regions(b, p, mode, hostFlags);
         if (rc != CPB_OK) return rc;
         stamp("build_regions");
         nReg = (int64_t) regs.size();

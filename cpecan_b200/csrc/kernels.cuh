@@ -905,6 +905,41 @@ __global__ void k_encode(uint8_t *s, int64_t n) {
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * k_split_flags : one warp per pair -- where getSplitPoints (impl/pairwiseAligner.c:1230-1257) cuts a pair into regions.
+ * Pair i has nA + 1 gaps: gap g lies between anchor g-1 (or the origin) and anchor g (or the end of both sequences).  Bit
+ * aOff[i] + i + g of `flags` is set iff the rectangle of gap g holds more than splitBiggerThan cells.  The host turns the flagged
+ * gaps into region records without walking the anchors itself (the anchors of 100 000 x 1 kb pairs are a gigabyte).
+ * ------------------------------------------------------------------------------------------- */
+__global__ void k_split_flags(const int32_t *anchors, const int64_t *aOff, const int64_t *xOff, const int64_t *yOff, int nPairs, long long splitBiggerThan,
+                              uint32_t *flags, unsigned int *nFlaggedPairs) {
+    const int pair = (int) (((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (pair >= nPairs) return;
+    const int64_t a0 = aOff[pair], nA = aOff[pair + 1] - a0;
+    const int64_t lX = xOff[pair + 1] - xOff[pair], lY = yOff[pair + 1] - yOff[pair];
+    const int32_t *an = anchors + 3 * a0;
+    const int64_t bit0 = a0 + pair;
+    bool any = false;
+    for (int64_t g0 = 0; g0 <= nA; g0 += 32) {
+        const int64_t g = g0 + lane;
+        bool f = false;
+        if (g <= nA) {
+            const int64_t prevX = g > 0 ? (int64_t) an[3 * (g - 1)] + 1 : 0, prevY = g > 0 ? (int64_t) an[3 * (g - 1) + 1] + 1 : 0;
+            const int64_t nextX = g < nA ? (int64_t) an[3 * g] : lX, nextY = g < nA ? (int64_t) an[3 * g + 1] : lY;
+            f = (nextX - prevX) * (nextY - prevY) > splitBiggerThan;
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, f);
+        if (m != 0 && lane == 0) {
+            const int64_t B = bit0 + g0;
+            const int sh = (int) (B & 31);
+            atomicOr(flags + (B >> 5), m << sh);
+            if (sh != 0 && (m >> (32 - sh)) != 0) atomicOr(flags + (B >> 5) + 1, m >> (32 - sh));
+            any = true;
+        }
+    }
+    if (lane == 0 && any) atomicAdd(nFlaggedPairs, 1u);
+}
+
+/* ---------------------------------------------------------------------------------------------
  * k_band : one warp per region -- the device-side band builder and traceback scheduler.
  *   band:     band_construct / band_constructDynamic, impl/pairwiseAligner.c:94-234.  The reference walks the diagonals
  *             with a moving (previous anchor, next anchor) pair; here every lane takes one diagonal, finds its anchor

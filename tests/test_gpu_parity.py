@@ -634,3 +634,31 @@ def test_plan_is_kept_between_runs_with_the_same_parameters(ctx, oracle, monkeyp
     b.run(five.cpb(), q, cp.MODE_ALIGNED_PAIRS)
     assert b.stats().planReused == 0
     b.close()
+
+
+def test_regions_from_device_split_flags(ctx, oracle):
+    """The pairs are cut into regions where k_split_flags marks a gap between anchors (getSplitPoints,
+    impl/pairwiseAligner.c:1230-1257): the number of regions must be what the host restatement counts, for every ragged-end
+    combination, cut threshold and anchor density -- including pairs without anchors, empty sequences and cuts at the first and
+    last gap -- and the aligned pairs those of the oracle's splitting run."""
+    rng = np.random.default_rng(4242)
+    cases = []
+    for k in range(120):
+        lX, lY = int(rng.integers(0, 90)), int(rng.integers(0, 90))
+        sX, sY = synth.random_sequence(rng, lX), synth.random_sequence(rng, lY)
+        a = synth.random_anchor_pairs(rng, lX, lY)
+        if k % 3 == 0 and len(a) > 2:
+            a = a[rng.random(len(a)) > 0.7]  # sparse anchors: wide gaps
+        if k % 7 == 0:
+            a = a[:0]
+        cases.append((sX, sY, a, bool(k & 1), bool(k & 2)))
+    spec = helpers.ModelSpec(cp.fiveState)
+    for split in (0, 1, 9, 64, 400, 10 ** 9):
+        p = cp.pairwiseAlignmentBandingParameters_construct()
+        p.splitMatrixBiggerThanThis = split
+        p.minDiagsBetweenTraceBack, p.traceBackDiagonals = 30, 10
+        want = sum(len(cp.getSplitPoints(c[2], len(c[0]), len(c[1]), split, c[3], c[4])) for c in cases)
+        b = run_batch(ctx, spec, p, cases, cp.MODE_ALIGNED_PAIRS)
+        assert b.stats().nRegions == want, "split %d: %d regions, the host restatement has %d" % (split, b.stats().nRegions, want)
+        b.close()
+        check_aligned_pairs(ctx, oracle, spec, p, cases[:40], "split %d" % split)
