@@ -176,6 +176,53 @@ struct PinnedPool {
     }
 };
 
+/* A host table that travels to and from the device every run (region and block records): page-locked memory from the context's
+ * pool, so that the copies are DMA transfers instead of the driver's staged pageable path (~3x slower for these 10-20 MB tables);
+ * ordinary heap memory if page-locked memory cannot be had.  resize() does not keep the contents. */
+template <class T> struct HostArray {
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    PinnedPool *pool = nullptr;
+    bool pinned = false;
+    HostArray() = default;
+    HostArray(const HostArray &) = delete;
+    HostArray &operator=(const HostArray &) = delete;
+    ~HostArray() { release(); }
+    void release() {
+        if (p != nullptr) {
+            if (pinned) pool->give(p);
+            else free(p);
+        }
+        p = nullptr;
+        n = cap = 0;
+    }
+    bool resize(size_t m) {
+        if (m > cap) {
+            PinnedPool *keep = pool;
+            release();
+            pool = keep;
+            const size_t want = m + m / 8 + 16;
+            p = pool != nullptr ? static_cast<T *>(pool->take(want * sizeof(T))) : nullptr;
+            pinned = p != nullptr;
+            if (p == nullptr) p = static_cast<T *>(malloc(want * sizeof(T)));
+            if (p == nullptr) return false;
+            cap = want;
+        }
+        n = m;
+        return true;
+    }
+    void clear() { n = 0; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+    T &back() { return p[n - 1]; }
+    T *begin() { return p; }
+    T *end() { return p + n; }
+};
+
 struct cpb_context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -325,8 +372,8 @@ struct cpb_batch {
     std::vector<int64_t> pairOff[3]; /* n+1 */
     int lastMode = -1, lastS = 0;
     CpbRunStats stats;
-    std::vector<RegionDev> hRegions;
-    std::vector<BlockRec> hBlocks; /* compact, region order */
+    HostArray<RegionDev> hRegions;
+    HostArray<BlockRec> hBlocks; /* compact, region order */
     /* the plan of the last run, kept for the next one with the same key (run_impl) */
     std::vector<Chunk> chunks;
     PlanKey planKey;
@@ -365,6 +412,8 @@ extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *se
     CUDA_TRY(cudaSetDevice(ctx->device));
     cpb_batch *b = new cpb_batch();
     b->ctx = ctx;
+    b->hRegions.pool = &ctx->pinned;
+    b->hBlocks.pool = &ctx->pinned;
     struct Guard { /* every early return below frees the batch, its device buffers and its page-locked anchor buffer */
         cpb_batch *b;
         ~Guard() {
@@ -372,7 +421,7 @@ extern "C" int cpb_batch_create(cpb_context *ctx, int64_t nPairs, const char *se
         }
     } guard{ b };
     {
-        DevBuf *all[] = { &b->strips, &b->symX, &b->symY, &b->dAnchors, &b->regions, &b->diags, &b->blocks, &b->totals, &b->lists, &b->counts, &b->offsets,
+        DevBuf *all[] = { &b->strips, &b->symX, &b->symY, &b->dAnchors, &b->dPairTab, &b->splitFlags, &b->regions, &b->diags, &b->blocks, &b->totals, &b->lists, &b->counts, &b->offsets,
                           &b->masks, &b->tileSums, &b->pairCounts, &b->partials, &b->pairBlockOff, &b->perPair, &b->hmmTotal, &b->forwardOut, &b->out[0],
                           &b->out[1], &b->out[2], &b->ckRegions, &b->ckDiags, &b->ckSizes, &b->ckpt };
         for (DevBuf *d : all) d->pool = &ctx->pool;
@@ -598,7 +647,10 @@ static int build_regions(cpb_batch *b, const CpbParams *p, int mode, const uint3
         blockBase += parts[(size_t) t].blocks;
         stripBase += parts[(size_t) t].strips;
     }
-    b->hRegions.resize((size_t) first[(size_t) nThreads]);
+    if (!b->hRegions.resize((size_t) first[(size_t) nThreads])) {
+        cpb_set_error("out of host memory for %lld region records", (long long) first[(size_t) nThreads]);
+        return CPB_ERR_MEMORY;
+    }
     run_pool([&](int64_t t) {
         RegionDev *out = b->hRegions.data() + first[(size_t) t];
         for (const RegionDev &R0 : parts[(size_t) t].regs) {
@@ -666,15 +718,19 @@ static int check_params(const CpbParams *p) {
  * work-fetch order only needs the big items early; an exact std::sort of a few hundred thousand items was the largest host stage. */
 template <class Cost> static void order_by_cost_descending(int32_t *idx, int64_t n, Cost cost) {
     if (n < 2) return;
+    std::vector<int64_t> c((size_t) n); /* the costs, fetched once: the records they come from are 40 to 144 bytes apart */
     int64_t largest = 1;
-    for (int64_t i = 0; i < n; i++) largest = std::max<int64_t>(largest, cost(idx[i]));
+    for (int64_t i = 0; i < n; i++) {
+        c[(size_t) i] = cost(idx[i]);
+        largest = std::max<int64_t>(largest, c[(size_t) i]);
+    }
     int shift = 0;
     while ((largest >> shift) >= 2048) shift++;
     std::vector<int64_t> start(2049, 0);
-    for (int64_t i = 0; i < n; i++) start[2047 - (cost(idx[i]) >> shift) + 1]++;
+    for (int64_t i = 0; i < n; i++) start[(size_t) (2047 - (c[(size_t) i] >> shift) + 1)]++;
     for (int k = 0; k < 2048; k++) start[k + 1] += start[k];
     std::vector<int32_t> out((size_t) n);
-    for (int64_t i = 0; i < n; i++) out[(size_t) start[2047 - (cost(idx[i]) >> shift)]++] = idx[i];
+    for (int64_t i = 0; i < n; i++) out[(size_t) start[(size_t) (2047 - (c[(size_t) i] >> shift))]++] = idx[i];
     memcpy(idx, out.data(), (size_t) n * sizeof(int32_t));
 }
 
@@ -771,8 +827,8 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     /* The plan of a run -- regions, bands, traceback schedule, chunks, work lists -- depends on the batch, the mode, the state count
      * and the banding parameters, not on the model's numbers: a batch that is run again with the same ones (every EM iteration of a
      * resident batch) keeps its plan, host tables and device tables alike.  $CPB_NO_PLAN_CACHE=1 plans every run anew. */
-    std::vector<RegionDev> &regs = b->hRegions;
-    std::vector<BlockRec> &hBlocks = b->hBlocks;
+    HostArray<RegionDev> &regs = b->hRegions;
+    HostArray<BlockRec> &hBlocks = b->hBlocks;
     std::vector<Chunk> &chunks = b->chunks;
     int64_t nReg = 0, nDiagRecs = 0, totalBlocks = 0;
     size_t scratchNeed = 0;
@@ -896,11 +952,20 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             stx.maxWidth = std::max(stx.maxWidth, regs[r].maxW);
         }
         stx.nBlocks = totalBlocks;
-        hBlocks.resize(totalBlocks);
+        if (!hBlocks.resize((size_t) totalBlocks)) {
+            cpb_set_error("out of host memory for %lld block records", (long long) totalBlocks);
+            return CPB_ERR_MEMORY;
+        }
         std::vector<int64_t> regionBlock0(nReg + 1, 0);
         if (totalBlocks > 0) {
-            std::vector<BlockRec> slots(blockSlots);
-            CUDA_TRY(cudaMemcpy(slots.data(), b->blocks.p, blockSlots * sizeof(BlockRec), cudaMemcpyDeviceToHost));
+            HostArray<BlockRec> slots; /* the slots as k_band filled them: blockCap per region, nBlocks of them used */
+            slots.pool = &ctx->pinned;
+            if (!slots.resize((size_t) blockSlots)) {
+                cpb_set_error("out of host memory for %lld block slots", (long long) blockSlots);
+                return CPB_ERR_MEMORY;
+            }
+            CUDA_TRY(cudaMemcpyAsync(slots.data(), b->blocks.p, blockSlots * sizeof(BlockRec), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
             int64_t k = 0;
             for (int64_t r = 0; r < nReg; r++) {
                 regionBlock0[r] = k;
@@ -979,16 +1044,39 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         stamp("scratch");
         /* launch lists: forward regions per class, backward blocks per class, all blocks in order */
         std::vector<int32_t> lists;
-        for (auto &c : chunks) {
-            c.allBlocksOff = (int64_t) lists.size();
-            for (int64_t k = c.block0; k < c.block1; k++) lists.push_back((int32_t) k);
-            /* strip engine: one list of regions and one of blocks, most expensive first (work is fetched dynamically) */
-            c.stripFwdOff = (int64_t) lists.size();
-            for (int64_t r = c.region0; r < c.region1; r++) lists.push_back((int32_t) r);
-            order_by_cost_descending(lists.data() + c.stripFwdOff, c.region1 - c.region0, [&](int32_t x) { return (int64_t) regs[x].cells; });
-            c.stripBwdOff = (int64_t) lists.size();
-            for (int64_t k = c.block0; k < c.block1; k++) lists.push_back((int32_t) k);
-            order_by_cost_descending(lists.data() + c.stripBwdOff, c.block1 - c.block0, [&](int32_t k) { return (int64_t) hBlocks[k].cells; });
+        {
+            int64_t total = 0;
+            for (auto &c : chunks) {
+                c.allBlocksOff = total;
+                c.stripFwdOff = c.allBlocksOff + (c.block1 - c.block0);
+                c.stripBwdOff = c.stripFwdOff + (c.region1 - c.region0);
+                total = c.stripBwdOff + (c.block1 - c.block0);
+            }
+            lists.resize((size_t) total);
+            /* strip engine: one list of regions and one of blocks per chunk, most expensive first (work is fetched dynamically); the
+             * block lists are ordered by a second thread while this one does the regions */
+            auto block_lists = [&]() {
+                for (auto &c : chunks) {
+                    int32_t *all = lists.data() + c.allBlocksOff, *bwd = lists.data() + c.stripBwdOff;
+                    for (int64_t k = c.block0; k < c.block1; k++) all[k - c.block0] = bwd[k - c.block0] = (int32_t) k;
+                    order_by_cost_descending(bwd, c.block1 - c.block0, [&](int32_t k) { return (int64_t) hBlocks[(size_t) k].cells; });
+                }
+            };
+            auto region_lists = [&]() {
+                for (auto &c : chunks) {
+                    int32_t *fwd = lists.data() + c.stripFwdOff;
+                    for (int64_t r = c.region0; r < c.region1; r++) fwd[r - c.region0] = (int32_t) r;
+                    order_by_cost_descending(fwd, c.region1 - c.region0, [&](int32_t x) { return (int64_t) regs[(size_t) x].cells; });
+                }
+            };
+            if (total > 100000) {
+                std::thread other(block_lists);
+                region_lists();
+                other.join();
+            } else {
+                block_lists();
+                region_lists();
+            }
         }
         if ((rc = b->lists.reserve(std::max<size_t>(lists.size(), 1) * sizeof(int32_t))) != CPB_OK) return rc;
         CUDA_TRY(cudaMemcpyAsync(b->lists.p, lists.data(), lists.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -1212,7 +1300,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
             if ((rc = b->ckpt.reserve(std::max<int64_t>(total, 1) * sizeof(double))) != CPB_OK) return rc;
             if ((rc = b->ckDiags.reserve(nDiagRecs * sizeof(DiagRec))) != CPB_OK) return rc;
             if ((rc = b->ckRegions.reserve(nReg * sizeof(RegionDev))) != CPB_OK) return rc;
-            std::vector<RegionDev> ckRegs(regs);
+            std::vector<RegionDev> ckRegs(regs.begin(), regs.end());
             for (auto &r : ckRegs) r.auxBase = 0; /* checkpoint offsets are absolute */
             CUDA_TRY(cudaMemcpyAsync(b->ckRegions.p, ckRegs.data(), nReg * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
             k_ckpt_diags<<<(unsigned) ((nDiagRecs + 255) / 256), 256, 0, st>>>(b->diags.as<DiagRec>(), b->ckDiags.as<DiagRec>(), nDiagRecs);
