@@ -1541,7 +1541,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     }
     if (mode == CPB_MODE_EXPECTATIONS) {
         size_t ev = tic(&stx.msPosterior);
-        k_reduce_total<<<1, 128, 0, st>>>(b->perPair.as<double>(), (int) b->n, hmmLen, b->hmmTotal.as<double>());
+        k_reduce_total<<<(unsigned) hmmLen, 256, 0, st>>>(b->perPair.as<double>(), (int) b->n, hmmLen, b->hmmTotal.as<double>());
         stx.kernelLaunches++;
         toc(ev);
     }

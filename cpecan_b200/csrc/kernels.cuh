@@ -351,6 +351,9 @@ template <int S> __device__ __forceinline__ void fill_tables(Tables<S> &t, const
 template <int S> __host__ __device__ constexpr int lower_from(int k) { return S == 5 ? (k == 0 ? 0 : (k == 1 ? 1 : (k == 2 ? 0 : 3))) : k; }
 template <int S> __host__ __device__ constexpr int lower_to(int k) { return S == 5 ? (k < 2 ? 1 : 3) : 1; }
 template <int S> __host__ __device__ constexpr int middle_from(int k) { return k; }
+/* states that occur as the source of a lower / an upper transition (k_expect fetches only those) */
+template <int S> __host__ __device__ constexpr bool uses_lower_from(int s) { return S == 5 ? (s == 0 || s == 1 || s == 3) : true; }
+template <int S> __host__ __device__ constexpr bool uses_upper_from(int s) { return S == 5 ? (s == 0 || s == 2 || s == 4) : true; }
 template <int S> __host__ __device__ constexpr int upper_from(int k) { return S == 5 ? (k == 0 ? 0 : (k == 1 ? 2 : (k == 2 ? 0 : 4))) : (k == 0 ? 0 : (k == 1 ? 2 : 1)); }
 template <int S> __host__ __device__ constexpr int upper_to(int k) { return S == 5 ? (k < 2 ? 2 : 4) : 2; }
 
@@ -771,14 +774,19 @@ __global__ void __launch_bounds__(32, S == 5 ? 20 : 16) k_expect(const DpArgs a,
         DiagRec mine = dg[max(dLow - 2 + min(lane, nd + 1), 0)]; /* lane r: diagonal dLow - 2 + r */
         const int c0 = (int) __shfl_sync(0xFFFFFFFFu, mine.coff, 2);
         const int c1 = (int) (__shfl_sync(0xFFFFFFFFu, mine.coff, nd + 1) + __shfl_sync(0xFFFFFFFFu, (uint32_t) mine.width, nd + 1));
+        /* first cell of the decade's 2nd .. 10th diagonal (beyond nd: never reached), fetched once per decade, not once per 32 cells */
+        int firstCell[9];
+#pragma unroll
+        for (int t = 1; t < 10; t++) {
+            const int ct = (int) __shfl_sync(0xFFFFFFFFu, mine.coff, min(t, nd - 1) + 2);
+            firstCell[t - 1] = t < nd ? ct : 0x7FFFFFFF;
+        }
         for (int base = c0; base < c1; base += 32) {
             const int c = base + lane;
             const bool valid = c < c1;
             int q = 0;
-            for (int t = 1; t < nd; t++) {
-                const int ct = (int) __shfl_sync(0xFFFFFFFFu, mine.coff, t + 2);
-                if (c >= ct) q = t;
-            }
+#pragma unroll
+            for (int t = 1; t < 10; t++) q = c >= firstCell[t - 1] ? t : q;
             DiagRec rec, rec1, rec2;
             rec.xmyL = __shfl_sync(0xFFFFFFFFu, mine.xmyL, q + 2);
             rec.width = __shfl_sync(0xFFFFFFFFu, mine.width, q + 2);
@@ -800,23 +808,34 @@ __global__ void __launch_bounds__(32, S == 5 ? 20 : 16) k_expect(const DpArgs a,
             const bool haveM = d >= 2 && !(K.T > 0 && d == K.T + 1); /* F[d-2] was freed at the block boundary (:855) */
             const int xmy = rec.xmyL + 2 * i;
             const int x = (d + xmy) >> 1, y = (d - xmy) >> 1;
-            const int cX = x > 0 ? sx[x - 1] : 4, cY = y > 0 ? sy[y - 1] : 4;
-            const int64_t cell = c;
-            double b[S];
-#pragma unroll
-            for (int s = 0; s < S; s++) b[s] = pb[(int64_t) s * a.planeStride + cell];
             const int iL = (xmy - 1 - rec1.xmyL) >> 1, iU = iL + 1; /* xmy-1 and xmy+1 on d-1 (same parity as rec1.xmyL) */
             const bool inL = xmy - 1 >= rec1.xmyL && iL < rec1.width;
             const bool inU = xmy + 1 >= rec1.xmyL && iU < rec1.width;
             const int iM = (xmy - rec2.xmyL) >> 1;
             const bool inM = haveM && xmy >= rec2.xmyL && iM < rec2.width;
+            /* Every load of the cell is issued before the first exponential: the B states of the cell and the F states of its three
+             * neighbours (a neighbour outside the band reads the cell itself -- a valid address whose value is not used).  Issued
+             * inside the three branches below, the loads of one neighbour waited for the exponentials of the one before; the kernel
+             * is bound by the latency of these loads (ncu: long scoreboard 4.2 stalled warps per issue). */
+            const int64_t cell = c;
+            const int64_t cellL = inL ? (int64_t) rec1.coff + iL : cell, cellU = inU ? (int64_t) rec1.coff + iU : cell, cellM = inM ? (int64_t) rec2.coff + iM : cell;
+            const int cX = x > 0 ? sx[x - 1] : 4, cY = y > 0 ? sy[y - 1] : 4;
+            double b[S], fL[S], fM[S], fU[S];
+#pragma unroll
+            for (int s = 0; s < S; s++) b[s] = pb[(int64_t) s * a.planeStride + cell];
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                fM[s] = pf[(int64_t) s * a.planeStride + cellM];
+                if (uses_lower_from<S>(s)) fL[s] = pf[(int64_t) s * a.planeStride + cellL];
+                if (uses_upper_from<S>(s)) fU[s] = pf[(int64_t) s * a.planeStride + cellU];
+            }
             emit = cX < 4 && cY < 4;
             eIdx = cX * 4 + cY;
             if (inL) {
 #pragma unroll
                 for (int k = 0; k < NL; k++) {
                     const int f = lower_from<S>(k), t = lower_to<S>(k);
-                    const double pr = exp(pf[(int64_t) f * a.planeStride + rec1.coff + iL] + b[t] + tab.tl[cX][k] + minusTotal);
+                    const double pr = exp(fL[f] + b[t] + tab.tl[cX][k] + minusTotal);
                     accT[k] += pr;
                     q2[t] += pr;
                 }
@@ -825,7 +844,7 @@ __global__ void __launch_bounds__(32, S == 5 ? 20 : 16) k_expect(const DpArgs a,
 #pragma unroll
                 for (int k = 0; k < NM; k++) {
                     const int f = middle_from<S>(k);
-                    const double pr = exp(pf[(int64_t) f * a.planeStride + rec2.coff + iM] + b[0] + tab.tm[cX * 5 + cY][k] + minusTotal);
+                    const double pr = exp(fM[f] + b[0] + tab.tm[cX * 5 + cY][k] + minusTotal);
                     accT[NL + k] += pr;
                     q2[0] += pr;
                 }
@@ -834,7 +853,7 @@ __global__ void __launch_bounds__(32, S == 5 ? 20 : 16) k_expect(const DpArgs a,
 #pragma unroll
                 for (int k = 0; k < NU; k++) {
                     const int f = upper_from<S>(k), t = upper_to<S>(k);
-                    const double pr = exp(pf[(int64_t) f * a.planeStride + rec1.coff + iU] + b[t] + tab.tu[cY][k] + minusTotal);
+                    const double pr = exp(fU[f] + b[t] + tab.tu[cY][k] + minusTotal);
                     accT[NL + NM + k] += pr;
                     q2[t] += pr;
                 }
@@ -885,13 +904,20 @@ __global__ void k_reduce_pairs(const double *partials, const int64_t *pairBlockO
     perPair[idx] += s;
 }
 
-/* total over pairs in pair order; one thread per entry (len <= 106), sequential => deterministic */
-__global__ void k_reduce_total(const double *perPair, int nPairs, int len, double *total) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= len) return;
+/* total over pairs: one CTA per entry (len <= 106); thread t adds pairs t, t + 256, ... in order, then a fixed tree over the 256
+ * partial sums => the same bits on every run of the same batch (a single sequential chain of 50 000 adds took 4.6 ms) */
+__global__ void __launch_bounds__(256) k_reduce_total(const double *perPair, int nPairs, int len, double *total) {
+    __shared__ double part[256];
+    const int e = blockIdx.x;
     double s = 0.0;
-    for (int p = 0; p < nPairs; p++) s += perPair[(int64_t) p * len + e];
-    total[e] = s;
+    for (int p = threadIdx.x; p < nPairs; p += 256) s += perPair[(int64_t) p * len + e];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int) threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[e] = part[0];
 }
 
 /* ---------------------------------------------------------------------------------------------
