@@ -547,9 +547,11 @@ __global__ void __launch_bounds__(32 * POST_WARPS) k_posterior(const DpArgs a, c
                 for (int o = 16; o > 0; o >>= 1) struck += __shfl_xor_sync(0xFFFFFFFFu, struck, o);
                 if (lane == 0) p.counts[(int64_t) l * p.nDecades + g] = cnt - struck;
             } else {
-                /* Kept cells are rare (about one per diagonal): every lane takes one 32-cell mask word of the decade, a warp scan gives
-                 * each word its place in the output, and the lane writes out its own word's few set bits.  The decade's records sit in
-                 * shared memory so that this per-lane loop needs no warp-wide operation. */
+                /* Kept cells are rare (about one per diagonal).  32 mask words of the decade at a time: every lane takes one word, a warp
+                 * scan numbers the set bits of the group, and then every lane takes one KEPT CELL -- it finds the word that holds its
+                 * cell by bisection over the scan and the bit inside it with __fns.  (A lane per word, each writing out its own word's
+                 * bits, left 28 lanes idle on narrow bands, where a decade is three or four words: 20 of 145 ms per 100 000 x 1 kb
+                 * pairs with cPecanRealign's band.)  The decade's records sit in shared memory for the per-lane diagonal search. */
                 int64_t run = p.offsets[(int64_t) l * p.nDecades + g];
                 __syncwarp();
                 if (lane < nd) {
@@ -560,7 +562,7 @@ __global__ void __launch_bounds__(32 * POST_WARPS) k_posterior(const DpArgs a, c
                 const int64_t nWords = (c1 - cA + 31) >> 5;
                 for (int64_t wb = 0; wb < nWords; wb += 32) {
                     const int64_t wi = wb + lane;
-                    unsigned m = wi < nWords ? masks[(cA >> 5) + wi] : 0u;
+                    const unsigned m = wi < nWords ? masks[(cA >> 5) + wi] : 0u;
                     const int cnt = __popc(m);
                     int incl = cnt;
 #pragma unroll
@@ -568,37 +570,49 @@ __global__ void __launch_bounds__(32 * POST_WARPS) k_posterior(const DpArgs a, c
                         const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
                         if (lane >= o) incl += t;
                     }
-                    int64_t pos = run + incl - cnt;
-                    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
-                    while (m != 0) {
-                        const int bit = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int64_t cell = cA + (wi << 5) + bit;
-                        /* the diagonal of the cell: the last of the decade's diagonals that starts at or before it */
-                        int k = 0;
-                        for (int q = 1; q < nd; q++) k = cell >= R.cellBase + sCoff[warp][q] ? q : k;
-                        const int d = dLow + k;
-                        const int x = ((d + sXmyL[warp][k]) >> 1) + (int) (cell - R.cellBase - sCoff[warp][k]), y = d - x;
-                        bool safe;
-                        const double lp = plane[cell] - total;
-                        const int pInt = posterior_weight(lp, p, safe);
-                        if (!safe) {
-                            const unsigned k = atomicAdd(p.fixupCount, 1u);
-                            if (k < (unsigned) p.fixupCap) {
-                                PintFixup f;
-                                f.lp = lp;
-                                f.pos = pos;
-                                f.list = l;
-                                f.pad_ = 0;
-                                p.fixups[k] = f;
-                            }
+                    const int kept = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    for (int t0 = 0; t0 < kept; t0 += 32) {
+                        const int t = t0 + lane; /* this lane's kept cell of the group, if t < kept */
+                        /* the first word whose inclusive count exceeds t */
+                        int w = 0;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const int probe = __shfl_sync(0xFFFFFFFFu, incl, w + o - 1);
+                            if (probe <= t) w += o;
                         }
-                        int32_t *o = p.out[l] + 3 * pos;
-                        o[0] = pInt;
-                        o[1] = x - 1 + R.ox;
-                        o[2] = y - 1 + R.oy;
-                        pos++;
+                        w = min(w, 31);
+                        const unsigned mw = __shfl_sync(0xFFFFFFFFu, m, w);
+                        const int before = __shfl_sync(0xFFFFFFFFu, incl, w) - __popc(mw);
+                        if (t < kept) {
+                            const int bit = (int) __fns(mw, 0, t - before + 1);
+                            const int64_t cell = cA + ((wb + w) << 5) + bit;
+                            /* the diagonal of the cell: the last of the decade's diagonals that starts at or before it */
+                            int k = 0;
+                            for (int q = 1; q < nd; q++) k = cell >= R.cellBase + sCoff[warp][q] ? q : k;
+                            const int d = dLow + k;
+                            const int x = ((d + sXmyL[warp][k]) >> 1) + (int) (cell - R.cellBase - sCoff[warp][k]), y = d - x;
+                            const int64_t pos = run + t;
+                            bool safe;
+                            const double lp = plane[cell] - total;
+                            const int pInt = posterior_weight(lp, p, safe);
+                            if (!safe) {
+                                const unsigned k = atomicAdd(p.fixupCount, 1u);
+                                if (k < (unsigned) p.fixupCap) {
+                                    PintFixup f;
+                                    f.lp = lp;
+                                    f.pos = pos;
+                                    f.list = l;
+                                    f.pad_ = 0;
+                                    p.fixups[k] = f;
+                                }
+                            }
+                            int32_t *o = p.out[l] + 3 * pos;
+                            o[0] = pInt;
+                            o[1] = x - 1 + R.ox;
+                            o[2] = y - 1 + R.oy;
+                        }
                     }
+                    run += kept;
                 }
             }
         }
