@@ -238,7 +238,7 @@ struct cpb_context {
 };
 
 static const int kStripWPC = 4; /* warps per CTA of the strip kernels */
-static const int kBwdWideBand = 1500; /* widest diagonal (cells) from which the backward kernel runs in its 4-CTAs-per-SM build */
+static const int kBwdWideBand = 1500; /* widest diagonal (cells) from which the backward kernel runs in its 3-CTAs-per-SM (168-register) build */
 static const int64_t kSymPad = 64; /* bytes of 'n' before and after the symbol arrays */
 
 static int configure_kernels() {
@@ -1139,7 +1139,7 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     /* strip engine: persistent grid of independent warps, boundary rings, work counters */
     typedef void (*StripKernel)(const DpArgs, const CpbModel, const StripArgs);
     StripKernel kFwdStrip = nullptr, kFwdTeam = nullptr, kFwdBlocks = nullptr, kBwdStrip = nullptr;
-    /* the backward kernel exists compiled for 6 and for 4 resident CTAs per SM: see strip_kernels.cuh ($CPB_BWD_WIDE=0/1 forces one) */
+    /* the backward kernel exists compiled for 6 and for 3 resident CTAs per SM: see strip_kernels.cuh ($CPB_BWD_WIDE=0/1 forces one) */
     bool bwdWide = stx.maxWidth > kBwdWideBand;
     if (getenv("CPB_BWD_WIDE") != nullptr) bwdWide = atoi(getenv("CPB_BWD_WIDE")) != 0;
     StripKernel kCkStrip = k_forward_strip<S, 0, kStripWPC, FWD_REGIONS>, kCkTeam = k_forward_strip<S, 0, kStripWPC, FWD_TEAMS>; /* first pass of two */
@@ -1147,25 +1147,25 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
     case CPB_MODE_FORWARD:
         kFwdStrip = k_forward_strip<S, 0, kStripWPC, FWD_REGIONS>;
         kFwdTeam = k_forward_strip<S, 0, kStripWPC, FWD_TEAMS>;
-        kBwdStrip = bwdWide ? k_backward_strip<S, 0, true, kStripWPC, 4> : k_backward_strip<S, 0, true, kStripWPC, CPB_BWD_MIN_BLOCKS>;
+        kBwdStrip = bwdWide ? k_backward_strip<S, 0, true, kStripWPC, CPB_BWD_WIDE_MIN_BLOCKS> : k_backward_strip<S, 0, true, kStripWPC, CPB_BWD_MIN_BLOCKS>;
         break;
     case CPB_MODE_ALIGNED_PAIRS:
         kFwdStrip = k_forward_strip<S, 1, kStripWPC, FWD_REGIONS>;
         kFwdTeam = k_forward_strip<S, 1, kStripWPC, FWD_TEAMS>;
         kFwdBlocks = k_forward_strip<S, 1, kStripWPC, FWD_BLOCKS>;
-        kBwdStrip = bwdWide ? k_backward_strip<S, 1, true, kStripWPC, 4> : k_backward_strip<S, 1, true, kStripWPC, CPB_BWD_MIN_BLOCKS>;
+        kBwdStrip = bwdWide ? k_backward_strip<S, 1, true, kStripWPC, CPB_BWD_WIDE_MIN_BLOCKS> : k_backward_strip<S, 1, true, kStripWPC, CPB_BWD_MIN_BLOCKS>;
         break;
     case CPB_MODE_ALIGNED_PAIRS_INDELS:
         kFwdStrip = k_forward_strip<S, 3, kStripWPC, FWD_REGIONS>;
         kFwdTeam = k_forward_strip<S, 3, kStripWPC, FWD_TEAMS>;
         kFwdBlocks = k_forward_strip<S, 3, kStripWPC, FWD_BLOCKS>;
-        kBwdStrip = bwdWide ? k_backward_strip<S, 3, true, kStripWPC, 4> : k_backward_strip<S, 3, true, kStripWPC, CPB_BWD_MIN_BLOCKS>;
+        kBwdStrip = bwdWide ? k_backward_strip<S, 3, true, kStripWPC, CPB_BWD_WIDE_MIN_BLOCKS> : k_backward_strip<S, 3, true, kStripWPC, CPB_BWD_MIN_BLOCKS>;
         break;
     default:
         kFwdStrip = k_forward_strip<S, S, kStripWPC, FWD_REGIONS>;
         kFwdTeam = k_forward_strip<S, S, kStripWPC, FWD_TEAMS>;
         kFwdBlocks = k_forward_strip<S, S, kStripWPC, FWD_BLOCKS>;
-        kBwdStrip = bwdWide ? k_backward_strip<S, S, false, kStripWPC, 4> : k_backward_strip<S, S, false, kStripWPC, CPB_BWD_MIN_BLOCKS>;
+        kBwdStrip = bwdWide ? k_backward_strip<S, S, false, kStripWPC, CPB_BWD_WIDE_MIN_BLOCKS> : k_backward_strip<S, S, false, kStripWPC, CPB_BWD_MIN_BLOCKS>;
         break;
     }
     /* narrow bands: groups of 8 or 16 lanes per region / block (narrow_kernels.cuh) */

@@ -303,6 +303,9 @@ __device__ __forceinline__ double log_add(double x, double y, const LaTable la) 
 #ifndef CPB_BWD_MIN_BLOCKS
 #define CPB_BWD_MIN_BLOCKS 6 /* backward gains 8 % from 24 resident warps per SM (80 registers); forward loses 5 %: it keeps 128 registers */
 #endif
+#ifndef CPB_BWD_WIDE_MIN_BLOCKS
+#define CPB_BWD_WIDE_MIN_BLOCKS 3 /* very wide bands (engine.cu kBwdWideBand): 168 registers, no spills; 500 x 100 kb: 644 ms at 6 CTAs/SM, 582 at 5, 540 at 4, 504 at 3, 636 at 2 */
+#endif
 
 /* ---------------------------------------------------------------------------------------------
  * per-CTA tables: eP + tP for every (symbol, transition)

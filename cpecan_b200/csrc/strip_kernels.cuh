@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(32 * WPC, CPB_FWD_MIN_BLOCKS) k_forward_strip(
 /* ---------------------------------------------------------------------------------------------
  * k_backward_strip<S, NP, ZSUM, WPC, MINB> : one warp per traceback block, strips in descending row order.
  * MINB: resident CTAs per SM it is compiled for (the engine picks 6 -- 80 registers -- for ordinary bands, where the 24 warps per SM
- * are worth 8 %, and 4 -- 128 registers -- for very wide ones, where they cost 15 %).
+ * are worth 8 %, and 3 -- 168 registers, nothing spilled -- for very wide ones, where the 80-register build is 28 % slower).
  * ZSUM: the planes written are F + B per state (what the posterior scan needs); otherwise raw B (expectations).
  * ------------------------------------------------------------------------------------------- */
 template <int S> struct BwdShare; /* states of row x+1 that row x needs: M (for the middle step) and the gap-X states */
