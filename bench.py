@@ -386,12 +386,16 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "pairs_per_s": pairs_all * e2e_steps / float(tw[0])},
-            "roofline": {"bound": "fp64", "kernel": "k_backward_strip<5,1,true,4>", "achieved": bwd["achieved"], "peak": fp64_peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp64", "kernel": "k_backward_strip<5,1,true,4,6>", "achieved": bwd["achieved"], "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": bwd["frac"],
                          "traffic": DRAM_BYTES_BACKWARD * cells / n_launch,
                          "note": "non-fused FP64 operations (the reference's arithmetic forbids FMA contraction); peak = 148 SMs x 64 FP64 lanes x "
                                  "sm_max_mhz of MEASURED_PEAKS.json; traffic = ncu dram__bytes_read+write of one launch (bytes per cell x cells per launch)",
                          "peak_source": peak_src, "launches_per_step": n_launch,
+                         # what this instruction mix reaches with the band logic taken away (tools/ubench_step.cu on one B200, committed in
+                         # profiles/r2_variants.txt): the forward step alone, every lane busy on every step
+                         "bare_step_ceiling": {"forward_g_cells_per_s": 96.0, "at": "4 CTAs/SM, 110 registers", "saturates_at": 108.0,
+                                               "source": "profiles/r2_variants.txt (tools/ubench_step.cu), a measurement of round 2, not of this run"},
                          "k_backward_strip": bwd, "k_forward_strip": fwd,
                          "forward_plus_backward": {"achieved": both_tf, "frac": both_tf / fp64_peak, "ops_per_cell": OPS_FORWARD + OPS_BACKWARD,
                                                    # round 1 counted 170 FP64 instructions per cell (with the directed-rounding add of the
