@@ -53,6 +53,10 @@ extern "C" const char *cpb_version(void) { return "cpecan_b200 0.1 (sm_100a)"; }
 /* Device allocations released by one batch are kept for the next (cudaMalloc / cudaFree of multi-GB buffers costs
  * hundreds of milliseconds per batch otherwise).  Best fit within 2x; everything is returned to the driver when the
  * context is destroyed or an allocation fails. */
+/* Counts the calls that change how much device memory the driver has free (cudaMalloc / cudaFree made here): while it stands still, a
+ * context's last answer from cudaMemGetInfo -- which costs ~12 ms once a few hundred buffers are live -- is still good. */
+static std::atomic<uint64_t> g_allocEpoch{ 1 };
+
 struct DevPool {
     struct Item {
         void *p;
@@ -73,6 +77,7 @@ struct DevPool {
     void give(void *p, size_t cap) { items.push_back({ p, cap }); }
     void drain() {
         for (auto &it : items) cudaFree(it.p);
+        if (!items.empty()) g_allocEpoch++;
         items.clear();
     }
 };
@@ -86,6 +91,7 @@ struct DevBuf {
         if (bytes <= cap) return CPB_OK;
         release();
         if (pool != nullptr && (p = pool->take(bytes, &cap)) != nullptr) return CPB_OK;
+        g_allocEpoch++;
         cudaError_t e = cudaMalloc(&p, bytes);
         if (e != cudaSuccess && pool != nullptr) {
             (void) cudaGetLastError();
@@ -103,8 +109,12 @@ struct DevBuf {
     }
     void release() {
         if (p) {
-            if (pool != nullptr) pool->give(p, cap);
-            else cudaFree(p);
+            if (pool != nullptr) {
+                pool->give(p, cap);
+            } else {
+                cudaFree(p);
+                g_allocEpoch++;
+            }
         }
         p = nullptr;
         cap = 0;
@@ -228,6 +238,8 @@ struct cpb_context {
     cudaStream_t stream = nullptr;
     bool ownStream = false;
     size_t scratchBudget = 0;
+    size_t freePlusScratch = 0;  /* cudaMemGetInfo's free bytes + the scratch buffer's, as of allocation epoch freeEpoch (0: never asked) */
+    uint64_t freeEpoch = 0;
     DevBuf scratch;
     DevBuf boundary, counters, negRecord, progress; /* strip engine: per-warp-slot boundary rings, work-fetch counters, one LOG_ZERO ring record */
     DevBuf fixups;                                  /* posterior write pass: one counter (first 16 bytes), then PintFixup records */
@@ -981,66 +993,79 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         stamp("block table");
         /* chunk planning */
         const int64_t bytesPerCell = (int64_t) sizeof(double) * 2 * nPlanes;
-        size_t budget = ctx->scratchBudget;
-        if (budget == 0) {
-            /* 70 % of what is free; a run that fits the scratch buffer already there does not need to ask the driver (cudaMemGetInfo
-             * costs tens of milliseconds once a few hundred buffers are live) */
-            size_t wholeRun = 0;
-            for (int64_t r = 0; r < nReg; r++) wholeRun += (size_t) ((regs[r].cells + 36) * bytesPerCell + (regs[r].auxDoubles + 6) * 8);
-            if (wholeRun + 256 <= ctx->scratch.cap) {
-                budget = ctx->scratch.cap;
-            } else {
-                size_t freeB = 0, totalB = 0;
-                CUDA_TRY(cudaMemGetInfo(&freeB, &totalB));
-                budget = (size_t) ((double) (freeB + ctx->scratch.cap) * 0.70);
+        for (int attempt = 0;; attempt++) {
+            bool budgetFromCache = false;
+            size_t budget = ctx->scratchBudget;
+            if (budget == 0) {
+                /* 70 % of what is free; a run that fits the scratch buffer already there does not need to ask the driver (cudaMemGetInfo
+                 * costs tens of milliseconds once a few hundred buffers are live) */
+                size_t wholeRun = 0;
+                for (int64_t r = 0; r < nReg; r++) wholeRun += (size_t) ((regs[r].cells + 36) * bytesPerCell + (regs[r].auxDoubles + 6) * 8);
+                if (wholeRun + 256 <= ctx->scratch.cap) {
+                    budget = ctx->scratch.cap;
+                } else {
+                    budgetFromCache = ctx->freeEpoch == g_allocEpoch.load();
+                    if (!budgetFromCache) {
+                        size_t freeB = 0, totalB = 0;
+                        CUDA_TRY(cudaMemGetInfo(&freeB, &totalB));
+                        ctx->freePlusScratch = freeB + ctx->scratch.cap;
+                        ctx->freeEpoch = g_allocEpoch.load();
+                    }
+                    budget = (size_t) ((double) ctx->freePlusScratch * 0.70);
+                }
             }
-        }
-        chunks.clear();
-        {
-            int64_t r = 0;
-            while (r < nReg) {
-                Chunk c;
-                memset(&c, 0, sizeof(c));
-                c.region0 = r;
-                int64_t cells = 0, aux = 0, words = 0;
+            chunks.clear();
+            {
+                int64_t r = 0;
                 while (r < nReg) {
-                    const int64_t nc = cells + regs[r].cells + 32, na = aux + regs[r].auxDoubles + 4;
-                    if (r > c.region0 && (size_t) (nc * bytesPerCell + na * 8) > budget) break;
-                    regs[r].cellBase = cells;
-                    regs[r].auxBase = aux;
-                    regs[r].maskBase = words;
-                    cells = (nc + 3) & ~int64_t(3);
-                    aux = (na + 1) & ~int64_t(1);
-                    words += (regs[r].cells >> 5) + regs[r].lX + regs[r].lY + 4;
-                    r++;
+                    Chunk c;
+                    memset(&c, 0, sizeof(c));
+                    c.region0 = r;
+                    int64_t cells = 0, aux = 0, words = 0;
+                    while (r < nReg) {
+                        const int64_t nc = cells + regs[r].cells + 32, na = aux + regs[r].auxDoubles + 4;
+                        if (r > c.region0 && (size_t) (nc * bytesPerCell + na * 8) > budget) break;
+                        regs[r].cellBase = cells;
+                        regs[r].auxBase = aux;
+                        regs[r].maskBase = words;
+                        cells = (nc + 3) & ~int64_t(3);
+                        aux = (na + 1) & ~int64_t(1);
+                        words += (regs[r].cells >> 5) + regs[r].lX + regs[r].lY + 4;
+                        r++;
+                    }
+                    c.region1 = r;
+                    c.cells = cells;
+                    c.aux = aux;
+                    c.maskWords = words; /* provisional; final value below once the decades are counted */
+                    c.stride = (cells + 31) & ~int64_t(31);
+                    c.block0 = regionBlock0[c.region0];
+                    c.block1 = regionBlock0[c.region1];
+                    c.pair0 = regs[c.region0].pair;
+                    c.pair1 = regs[c.region1 - 1].pair;
+                    /* decades: ceil(owned diagonals / 10) per block, numbered consecutively inside the chunk */
+                    int64_t dec = 0;
+                    for (int64_t k = c.block0; k < c.block1; k++) {
+                        hBlocks[k].decadeBase = dec;
+                        dec += (hBlocks[k].from - hBlocks[k].T + 9) / 10;
+                    }
+                    c.decades = dec;
+                    c.maskWords = (c.cells >> 5) + dec + 2; /* k_posterior: word of chunk cell C in decade g is (C >> 5) + g */
+                    chunks.push_back(c);
                 }
-                c.region1 = r;
-                c.cells = cells;
-                c.aux = aux;
-                c.maskWords = words; /* provisional; final value below once the decades are counted */
-                c.stride = (cells + 31) & ~int64_t(31);
-                c.block0 = regionBlock0[c.region0];
-                c.block1 = regionBlock0[c.region1];
-                c.pair0 = regs[c.region0].pair;
-                c.pair1 = regs[c.region1 - 1].pair;
-                /* decades: ceil(owned diagonals / 10) per block, numbered consecutively inside the chunk */
-                int64_t dec = 0;
-                for (int64_t k = c.block0; k < c.block1; k++) {
-                    hBlocks[k].decadeBase = dec;
-                    dec += (hBlocks[k].from - hBlocks[k].T + 9) / 10;
-                }
-                c.decades = dec;
-                c.maskWords = (c.cells >> 5) + dec + 2; /* k_posterior: word of chunk cell C in decade g is (C >> 5) + g */
-                chunks.push_back(c);
             }
-        }
-        stx.nChunks = (int64_t) chunks.size();
-        stamp("chunk planning");
-        if (totalBlocks > 0) CUDA_TRY(cudaMemcpyAsync(b->blocks.p, hBlocks.data(), totalBlocks * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
-        scratchNeed = 0;
-        for (auto &c : chunks) scratchNeed = std::max(scratchNeed, (size_t) (c.stride * bytesPerCell + c.aux * 8 + 256));
-        if ((rc = ctx->scratch.reserve(std::max<size_t>(scratchNeed, 256))) != CPB_OK) return rc;
+            stx.nChunks = (int64_t) chunks.size();
+            stamp("chunk planning");
+            if (totalBlocks > 0) CUDA_TRY(cudaMemcpyAsync(b->blocks.p, hBlocks.data(), totalBlocks * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
+            scratchNeed = 0;
+            for (auto &c : chunks) scratchNeed = std::max(scratchNeed, (size_t) (c.stride * bytesPerCell + c.aux * 8 + 256));
+            rc = ctx->scratch.reserve(std::max<size_t>(scratchNeed, 256));
+            if (rc == CPB_OK) break;
+            /* the budget may rest on an answer of cudaMemGetInfo from before somebody else in this process took device memory: ask again, once */
+            if (attempt > 0 || !budgetFromCache) return rc;
+            (void) cudaGetLastError();
+            ctx->freeEpoch = 0;
 
+        }
         stamp("scratch");
         /* launch lists: forward regions per class, backward blocks per class, all blocks in order */
         std::vector<int32_t> lists;
@@ -1085,7 +1110,13 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         stamp("lists");
         return CPB_OK;
     };
-    if (b->planValid && memcmp(&key, &b->planKey, sizeof(key)) == 0 && getenv("CPB_NO_PLAN_CACHE") == nullptr) {
+    bool reuse = b->planValid && memcmp(&key, &b->planKey, sizeof(key)) == 0 && getenv("CPB_NO_PLAN_CACHE") == nullptr;
+    if (reuse && ctx->scratch.reserve(std::max<size_t>(b->planScratch, 256)) != CPB_OK) {
+        /* the context's scratch has served another batch since and the chunks of the kept plan no longer fit what is free: plan anew */
+        (void) cudaGetLastError();
+        reuse = false;
+    }
+    if (reuse) {
         nReg = (int64_t) regs.size();
         nDiagRecs = regs.back().diagBase + regs.back().lX + regs.back().lY + 3;
         totalBlocks = (int64_t) hBlocks.size();
@@ -1097,7 +1128,6 @@ static int run_impl(cpb_batch *b, const CpbModel *m, const CpbParams *p, int mod
         stx.nBlocks = b->planStats.nBlocks;
         stx.nChunks = b->planStats.nChunks;
         stx.planReused = 1;
-        if ((rc = ctx->scratch.reserve(std::max<size_t>(scratchNeed, 256))) != CPB_OK) return rc; /* the context's scratch may have served another batch since */
         stamp("plan reused");
     } else {
         b->planValid = false;
