@@ -662,3 +662,28 @@ def test_regions_from_device_split_flags(ctx, oracle):
         assert b.stats().nRegions == want, "split %d: %d regions, the host restatement has %d" % (split, b.stats().nRegions, want)
         b.close()
         check_aligned_pairs(ctx, oracle, spec, p, cases[:40], "split %d" % split)
+
+
+@pytest.mark.parametrize("team", [2, 4, 16])
+def test_forward_teams_are_bit_identical(ctx, oracle, monkeypatch, team):
+    """A region's strips dealt to a team of warps and pipelined through the rings (FWD_TEAMS; the engine's choice for few, long
+    regions) against one warp per region: forced here on short, ragged, split and empty problems -- teams larger than a region has
+    strips, strips that are empty, several regions per team one after the other -- for aligned pairs, expectations and the forward
+    probability."""
+    monkeypatch.setenv("CPB_TEAM", str(team))
+    rng = np.random.default_rng(600 + team)
+    cases = small_cases(rng, 20, max_len=400, ragged=True)
+    p = cp.pairwiseAlignmentBandingParameters_construct()
+    p.minDiagsBetweenTraceBack, p.traceBackDiagonals, p.splitMatrixBiggerThanThis = 90, 30, 60 * 60
+    for type_ in (cp.fiveState, cp.threeState):
+        spec = helpers.ModelSpec(type_)
+        check_aligned_pairs(ctx, oracle, spec, p, cases, "team %d" % team)
+        b = run_batch(ctx, spec, p, cases, cp.MODE_FORWARD)
+        got = b.fetch_forward()
+        b.close()
+        monkeypatch.delenv("CPB_TEAM")
+        b = run_batch(ctx, spec, p, cases, cp.MODE_FORWARD)
+        want = b.fetch_forward()
+        b.close()
+        monkeypatch.setenv("CPB_TEAM", str(team))
+        assert np.array_equal(got, want, equal_nan=True), "forward probabilities differ with teams of %d" % team
