@@ -20,6 +20,7 @@
  * This is host code on purpose: it is a CALLER of the hot path (the reference's own is a CPU subprocess), it works on one pair at
  * a time in O(l) memory, and the batch entry points run it on a host thread per problem.
  */
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -30,19 +31,13 @@ typedef struct {
     int32_t x, y, len; /* an exact match of `len` bases starting at (x, y) */
 } Seed;
 
-static inline int base_code(char ch, int maskLower) {
-    switch (ch) {
-    case 'A': return 0;
-    case 'C': return 1;
-    case 'G': return 2;
-    case 'T': return 3;
-    case 'a': return maskLower ? -1 : 0;
-    case 'c': return maskLower ? -1 : 1;
-    case 'g': return maskLower ? -1 : 2;
-    case 't': return maskLower ? -1 : 3;
-    default: return -1;
-    }
-}
+/* a, c, g, t -> 0..3, anything else -1; lower case counts as "anything else" where the soft mask is honoured.  A table, not a switch:
+ * on sequence data a switch is four unpredictable branches per base. */
+static const signed char kCode[2][256] = {
+    { ['A'] = 1, ['C'] = 2, ['G'] = 3, ['T'] = 4, ['a'] = 1, ['c'] = 2, ['g'] = 3, ['t'] = 4 },
+    { ['A'] = 1, ['C'] = 2, ['G'] = 3, ['T'] = 4 },
+};
+static inline int base_code(char ch, int maskLower) { return kCode[maskLower != 0][(unsigned char) ch] - 1; }
 
 static inline int same_base(char p, char q) {
     const int u = base_code(p, 0);
@@ -67,73 +62,99 @@ static int word_length(int64_t lX, int64_t lY) {
     return k;
 }
 
-/* exact k-mer matches (x, y) with the k-mer unique in Y, in ascending x; consecutive matches of one diagonal are merged */
+/* exact k-mer matches (x, y) with the k-mer unique in Y, in ascending x; consecutive matches of one diagonal are merged.
+ * The index of Y is an open-addressing table of 16-byte entries (the k-mer and the position + 1 of its first occurrence, negated once
+ * it occurs again) -- one cache line per probe -- and both passes work through the sequence 32 positions at a time: roll the
+ * window over the block, ask for the 32 table lines, then probe them (the table of a 100 kb sequence is 4 MB: every probe is a
+ * cache miss, and the next one cannot be issued before the window has moved on unless the addresses are computed ahead). */
+typedef struct {
+    uint64_t key;
+    int32_t slot;
+    int32_t pad_;
+} IndexEntry;
+enum { SEED_BLOCK = 32 };
+
+/* rolls the k-mer window over positions [i0, i1) of s; for every position that ends a whole word: its word, its home slot (also
+ * prefetched) and its index in the block.  Returns how many there are. */
+static inline int roll_block(const char *s, int64_t i0, int64_t i1, int k, int maskLower, uint64_t wordMask, uint64_t capMask, const IndexEntry *table,
+                             uint64_t *w, int *valid, uint64_t *words, uint64_t *homes, int *at) {
+    int m = 0;
+    for (int64_t i = i0; i < i1; i++) {
+        const int c = base_code(s[i], maskLower);
+        if (c < 0) {
+            *valid = 0;
+            continue;
+        }
+        *w = ((*w << 2) | (uint64_t) c) & wordMask;
+        if (++*valid < k) continue;
+        words[m] = *w;
+        homes[m] = mix(*w) & capMask;
+        at[m] = (int) (i - i0);
+        __builtin_prefetch(table + homes[m]);
+        m++;
+    }
+    return m;
+}
+
 static Seed *find_seeds(const char *sX, const char *sY, int64_t lX, int64_t lY, int k, int maskLower, int64_t *nOut) {
     *nOut = 0;
     if (lX < k || lY < k) return NULL;
     int64_t cap = 16;
     while (cap < 2 * lY) cap <<= 1;
-    /* open addressing; slot = position + 1 of the k-mer's first occurrence in Y, negated once it occurs again */
-    int32_t *slot = calloc((size_t) cap, sizeof(int32_t));
-    uint64_t *keys = cpecan_malloc((size_t) cap * sizeof(uint64_t));
-    if (slot == NULL) st_errAbort("cpecan: out of memory indexing %lld bases", (long long) lY);
-    const uint64_t wordMask = k < 32 ? (((uint64_t) 1 << (2 * k)) - 1) : ~(uint64_t) 0;
+    IndexEntry *table = calloc((size_t) cap, sizeof(IndexEntry));
+    if (table == NULL) st_errAbort("cpecan: out of memory indexing %lld bases", (long long) lY);
+    const uint64_t wordMask = k < 32 ? (((uint64_t) 1 << (2 * k)) - 1) : ~(uint64_t) 0, capMask = (uint64_t) (cap - 1);
+    uint64_t words[SEED_BLOCK], homes[SEED_BLOCK];
+    int at[SEED_BLOCK];
     uint64_t w = 0;
     int valid = 0;
-    for (int64_t i = 0; i < lY; i++) {
-        const int c = base_code(sY[i], maskLower);
-        if (c < 0) {
-            valid = 0;
-            continue;
-        }
-        w = ((w << 2) | (uint64_t) c) & wordMask;
-        if (++valid < k) continue;
-        uint64_t h = mix(w) & (uint64_t) (cap - 1);
-        for (;;) {
-            if (slot[h] == 0) {
-                slot[h] = (int32_t) (i - k + 2);
-                keys[h] = w;
-                break;
+    for (int64_t i0 = 0; i0 < lY; i0 += SEED_BLOCK) {
+        const int64_t i1 = i0 + SEED_BLOCK < lY ? i0 + SEED_BLOCK : lY;
+        const int m = roll_block(sY, i0, i1, k, maskLower, wordMask, capMask, table, &w, &valid, words, homes, at);
+        for (int j = 0; j < m; j++) {
+            uint64_t h = homes[j];
+            for (;;) {
+                if (table[h].slot == 0) {
+                    table[h].slot = (int32_t) (i0 + at[j] - k + 2);
+                    table[h].key = words[j];
+                    break;
+                }
+                if (table[h].key == words[j]) {
+                    if (table[h].slot > 0) table[h].slot = -table[h].slot;
+                    break;
+                }
+                h = (h + 1) & capMask;
             }
-            if (keys[h] == w) {
-                if (slot[h] > 0) slot[h] = -slot[h];
-                break;
-            }
-            h = (h + 1) & (uint64_t) (cap - 1);
         }
     }
     int64_t n = 0, room = 1024;
     Seed *seeds = cpecan_malloc((size_t) room * sizeof(Seed));
     w = 0;
     valid = 0;
-    for (int64_t i = 0; i < lX; i++) {
-        const int c = base_code(sX[i], maskLower);
-        if (c < 0) {
-            valid = 0;
-            continue;
+    for (int64_t i0 = 0; i0 < lX; i0 += SEED_BLOCK) {
+        const int64_t i1 = i0 + SEED_BLOCK < lX ? i0 + SEED_BLOCK : lX;
+        const int m = roll_block(sX, i0, i1, k, maskLower, wordMask, capMask, table, &w, &valid, words, homes, at);
+        for (int j = 0; j < m; j++) {
+            uint64_t h = homes[j];
+            while (table[h].slot != 0 && table[h].key != words[j]) h = (h + 1) & capMask;
+            if (table[h].slot <= 0) continue;
+            const int32_t x = (int32_t) (i0 + at[j] - k + 1), y = table[h].slot - 1;
+            if (n > 0 && seeds[n - 1].x + seeds[n - 1].len - k + 1 == x && seeds[n - 1].y + seeds[n - 1].len - k + 1 == y) {
+                seeds[n - 1].len++; /* the previous match shifted by one: one longer exact run */
+                continue;
+            }
+            if (n == room) {
+                room *= 2;
+                seeds = realloc(seeds, (size_t) room * sizeof(Seed));
+                if (seeds == NULL) st_errAbort("cpecan: out of memory");
+            }
+            seeds[n].x = x;
+            seeds[n].y = y;
+            seeds[n].len = k;
+            n++;
         }
-        w = ((w << 2) | (uint64_t) c) & wordMask;
-        if (++valid < k) continue;
-        uint64_t h = mix(w) & (uint64_t) (cap - 1);
-        while (slot[h] != 0 && keys[h] != w) h = (h + 1) & (uint64_t) (cap - 1);
-        if (slot[h] <= 0) continue;
-        const int32_t x = (int32_t) (i - k + 1), y = slot[h] - 1;
-        if (n > 0 && seeds[n - 1].x + seeds[n - 1].len - k + 1 == x && seeds[n - 1].y + seeds[n - 1].len - k + 1 == y) {
-            seeds[n - 1].len++; /* the previous match shifted by one: one longer exact run */
-            continue;
-        }
-        if (n == room) {
-            room *= 2;
-            seeds = realloc(seeds, (size_t) room * sizeof(Seed));
-            if (seeds == NULL) st_errAbort("cpecan: out of memory");
-        }
-        seeds[n].x = x;
-        seeds[n].y = y;
-        seeds[n].len = k;
-        n++;
     }
-    free(slot);
-    free(keys);
+    free(table);
     *nOut = n;
     return seeds;
 }
@@ -200,16 +221,48 @@ static int64_t chain_seeds(Seed *seeds, int64_t n, int64_t lY, Seed **chainOut) 
     return m;
 }
 
-static int sort_by_x_plus_y(const void *a, const void *b) {
-    const int64_t k = stIntTuple_get((stIntTuple *) a, 0) + stIntTuple_get((stIntTuple *) a, 1);
-    const int64_t l = stIntTuple_get((stIntTuple *) b, 0) + stIntTuple_get((stIntTuple *) b, 1);
-    return k > l ? 1 : (k < l ? -1 : 0);
+/* ---- anchors as flat (x, y, expansion) int32 triples: the three functions below hand stLists to their callers, but between themselves
+ * they work on arrays (a tuple per anchor, three times over, was half the time of anchoring a 100 kb pair) ---- */
+typedef struct {
+    int32_t *v; /* 3 per anchor */
+    int64_t n, cap;
+} Triples;
+
+static void triples_push(Triples *t, int64_t x, int64_t y, int64_t e) {
+    if (t->n == t->cap) {
+        t->cap = t->cap ? 2 * t->cap : 1024;
+        t->v = realloc(t->v, (size_t) t->cap * 3 * sizeof(int32_t));
+        if (t->v == NULL) st_errAbort("cpecan: out of memory");
+    }
+    t->v[3 * t->n] = (int32_t) x;
+    t->v[3 * t->n + 1] = (int32_t) y;
+    t->v[3 * t->n + 2] = (int32_t) e;
+    t->n++;
 }
 
-stList *getBlastPairs(const char *sX, const char *sY, int64_t lX, int64_t lY, int64_t trim, int64_t diagonalExpansion, bool repeatMask) {
-    stList *pairs = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
-    if (lX == 0 || lY == 0) return pairs;
+static int by_x_plus_y(const void *a, const void *b) {
+    const int32_t *p = a, *q = b;
+    const int64_t k = (int64_t) p[0] + p[1], l = (int64_t) q[0] + q[1];
+    return k > l ? 1 : (k < l ? -1 : 0);
+}
+static int by_elements(const void *a, const void *b) { /* stIntTuple_cmpFn on tuples of three */
+    const int32_t *p = a, *q = b;
+    for (int i = 0; i < 3; i++) {
+        if (p[i] != q[i]) return p[i] < q[i] ? -1 : 1;
+    }
+    return 0;
+}
+/* sorts unless the triples are in order already (a chain's anchors are: x and y both ascend) */
+static void triples_sort(Triples *t, int (*cmp)(const void *, const void *)) {
+    int64_t i = 1;
+    while (i < t->n && cmp(t->v + 3 * (i - 1), t->v + 3 * i) <= 0) i++;
+    if (i < t->n) qsort(t->v, (size_t) t->n, 3 * sizeof(int32_t), cmp);
+}
+
+static void blast_pairs(const char *sX, const char *sY, int64_t lX, int64_t lY, int64_t trim, int64_t diagonalExpansion, bool repeatMask, Triples *pairs) {
+    if (lX == 0 || lY == 0) return;
     if (lX > 0x7FFFFFF0 || lY > 0x7FFFFFF0) st_errAbort("getBlastPairs: sequences of %lld and %lld bases are too long", (long long) lX, (long long) lY);
+    if (diagonalExpansion < 0 || diagonalExpansion > 0x7FFFFFF0) st_errAbort("getBlastPairs: diagonal expansion %lld out of range", (long long) diagonalExpansion);
     const int k = word_length(lX, lY);
     int64_t n = 0;
     Seed *seeds = find_seeds(sX, sY, lX, lY, k, repeatMask, &n);
@@ -232,81 +285,97 @@ stList *getBlastPairs(const char *sX, const char *sY, int64_t lX, int64_t lY, in
         }
         /* a lone word that joined nothing is as likely a chance match inside a gap as a piece of the alignment: it anchors nothing */
         if (j - i > 1 || x1 - x0 >= 2 * k) {
-            for (int64_t l = trim; l < x1 - x0 - trim; l++) stList_append(pairs, stIntTuple_construct3(x0 + l, y0 + l, diagonalExpansion));
+            for (int64_t l = trim; l < x1 - x0 - trim; l++) triples_push(pairs, x0 + l, y0 + l, diagonalExpansion);
         }
         i = j;
     }
     free(chain);
-    stList_sort(pairs, sort_by_x_plus_y); /* as the reference does (:1063); the chain is already in this order */
-    return pairs;
+    triples_sort(pairs, by_x_plus_y); /* as the reference does (:1063); the chain is in this order already */
 }
 
-/* impl/pairwiseAligner.c:1095-1135: of pairs sorted by (x, y), keep those that no later pair undercuts in x or y (backward sweep) and
- * that exceed every earlier pair in both (forward sweep) */
-stList *filterToRemoveOverlap(stList *sortedOverlappingPairs) {
-    const int64_t n = stList_length(sortedOverlappingPairs);
-    stList *out = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+stList *getBlastPairs(const char *sX, const char *sY, int64_t lX, int64_t lY, int64_t trim, int64_t diagonalExpansion, bool repeatMask) {
+    Triples pairs = { NULL, 0, 0 };
+    blast_pairs(sX, sY, lX, lY, trim, diagonalExpansion, repeatMask, &pairs);
+    stList *list = cpecan_tripleList_construct(pairs.v, pairs.n);
+    free(pairs.v);
+    return list;
+}
+
+/* impl/pairwiseAligner.c:1095-1135 on triples sorted by (x, y, expansion): keep those that no later one undercuts in x or y (backward
+ * sweep) and that exceed every earlier one in both (forward sweep).  The reference keeps the survivors of the backward sweep in a
+ * sorted SET of tuples: a triple equal (in all elements) to a surviving one counts as surviving too. */
+static void filter_overlap(const int32_t *in, int64_t n, int64_t dx, int64_t dy, Triples *out) {
     char *alive = cpecan_malloc((size_t) n + 1);
     int64_t pX = INT64_MAX, pY = INT64_MAX;
     for (int64_t i = n - 1; i >= 0; i--) {
-        stIntTuple *pair = stList_get(sortedOverlappingPairs, i);
-        const int64_t x = stIntTuple_get(pair, 0), y = stIntTuple_get(pair, 1);
+        const int64_t x = in[3 * i], y = in[3 * i + 1];
         alive[i] = x < pX && y < pY;
         pX = x < pX ? x : pX;
         pY = y < pY ? y : pY;
     }
-    /* the reference keeps the survivors of the backward sweep in a sorted SET of tuples: a pair equal (in all elements) to a
-     * surviving one counts as surviving too */
     pX = INT64_MIN;
     pY = INT64_MIN;
     for (int64_t i = 0; i < n; i++) {
-        stIntTuple *pair = stList_get(sortedOverlappingPairs, i);
-        const int64_t x = stIntTuple_get(pair, 0), y = stIntTuple_get(pair, 1);
+        const int64_t x = in[3 * i], y = in[3 * i + 1];
         int survives = alive[i];
-        for (int64_t j = i + 1; !survives && j < n && stIntTuple_equalsFn(pair, stList_get(sortedOverlappingPairs, j)); j++) survives = alive[j];
-        for (int64_t j = i - 1; !survives && j >= 0 && stIntTuple_equalsFn(pair, stList_get(sortedOverlappingPairs, j)); j--) survives = alive[j];
-        if (x > pX && y > pY && survives) stList_append(out, stIntTuple_construct3(x, y, stIntTuple_get(pair, 2)));
+        for (int64_t j = i + 1; !survives && j < n && by_elements(in + 3 * i, in + 3 * j) == 0; j++) survives = alive[j];
+        for (int64_t j = i - 1; !survives && j >= 0 && by_elements(in + 3 * i, in + 3 * j) == 0; j--) survives = alive[j];
+        if (x > pX && y > pY && survives) triples_push(out, x + dx, y + dy, in[3 * i + 2]);
         pX = x > pX ? x : pX;
         pY = y > pY ? y : pY;
     }
     free(alive);
-    return out;
+}
+
+stList *filterToRemoveOverlap(stList *sortedOverlappingPairs) {
+    const int64_t n = stList_length(sortedOverlappingPairs);
+    Triples in = { NULL, 0, 0 }, out = { NULL, 0, 0 };
+    for (int64_t i = 0; i < n; i++) {
+        stIntTuple *pair = stList_get(sortedOverlappingPairs, i);
+        const int64_t x = stIntTuple_get(pair, 0), y = stIntTuple_get(pair, 1), e = stIntTuple_get(pair, 2);
+        if (x < INT32_MIN || x > INT32_MAX || y < INT32_MIN || y > INT32_MAX || e < INT32_MIN || e > INT32_MAX) {
+            st_errAbort("filterToRemoveOverlap: (%lld, %lld, %lld) is outside the 32-bit range", (long long) x, (long long) y, (long long) e);
+        }
+        triples_push(&in, x, y, e);
+    }
+    filter_overlap(in.v, in.n, 0, 0, &out);
+    stList *list = cpecan_tripleList_construct(out.v, out.n);
+    free(in.v);
+    free(out.v);
+    return list;
 }
 
 /* anchors of the sub-matrix [pX, x) x [pY, y) if it is still bigger than anchorMatrixBiggerThanThis (:1137-1160) */
-static void anchor_gap(const char *sX, const char *sY, int64_t pX, int64_t pY, int64_t x, int64_t y, PairwiseAlignmentParameters *p, stList *combined) {
+static void anchor_gap(const char *sX, const char *sY, int64_t pX, int64_t pY, int64_t x, int64_t y, PairwiseAlignmentParameters *p, Triples *combined) {
     const int64_t lX2 = x - pX, lY2 = y - pY;
     if (lX2 <= 0 || lY2 <= 0) return;
     const int64_t matrixSize = lX2 * lY2;
     if (matrixSize <= p->anchorMatrixBiggerThanThis) return;
-    stList *unfiltered = getBlastPairs(sX + pX, sY + pY, lX2, lY2, p->constraintDiagonalTrim, p->diagonalExpansion, matrixSize > p->repeatMaskMatrixBiggerThanThis);
-    stList_sort(unfiltered, stIntTuple_cmpFn);
-    stList *bottom = filterToRemoveOverlap(unfiltered);
-    stList_destruct(unfiltered);
-    for (int64_t i = 0; i < stList_length(bottom); i++) {
-        stIntTuple *t = stList_get(bottom, i);
-        stList_append(combined, stIntTuple_construct3(stIntTuple_get(t, 0) + pX, stIntTuple_get(t, 1) + pY, stIntTuple_get(t, 2)));
-    }
-    stList_destruct(bottom);
+    Triples unfiltered = { NULL, 0, 0 };
+    blast_pairs(sX + pX, sY + pY, lX2, lY2, p->constraintDiagonalTrim, p->diagonalExpansion, matrixSize > p->repeatMaskMatrixBiggerThanThis, &unfiltered);
+    triples_sort(&unfiltered, by_elements);
+    filter_overlap(unfiltered.v, unfiltered.n, pX, pY, combined);
+    free(unfiltered.v);
 }
 
 stList *getBlastPairsForPairwiseAlignmentParameters(const char *sX, const char *sY, const int64_t lX, const int64_t lY, PairwiseAlignmentParameters *p) {
     if (lX * lY <= p->anchorMatrixBiggerThanThis) return stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
-    stList *unfiltered = getBlastPairs(sX, sY, lX, lY, p->constraintDiagonalTrim, p->diagonalExpansion, 1);
-    stList_sort(unfiltered, stIntTuple_cmpFn);
-    stList *top = filterToRemoveOverlap(unfiltered);
-    stList_destruct(unfiltered);
-    stList *combined = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    Triples unfiltered = { NULL, 0, 0 }, top = { NULL, 0, 0 }, combined = { NULL, 0, 0 };
+    blast_pairs(sX, sY, lX, lY, p->constraintDiagonalTrim, p->diagonalExpansion, 1, &unfiltered);
+    triples_sort(&unfiltered, by_elements);
+    filter_overlap(unfiltered.v, unfiltered.n, 0, 0, &top);
+    free(unfiltered.v);
     int64_t pX = 0, pY = 0;
-    for (int64_t i = 0; i < stList_length(top); i++) {
-        stIntTuple *anchor = stList_get(top, i);
-        const int64_t x = stIntTuple_get(anchor, 0), y = stIntTuple_get(anchor, 1);
-        anchor_gap(sX, sY, pX, pY, x, y, p, combined);
-        stList_append(combined, stIntTuple_construct3(x, y, stIntTuple_get(anchor, 2)));
+    for (int64_t i = 0; i < top.n; i++) {
+        const int64_t x = top.v[3 * i], y = top.v[3 * i + 1];
+        anchor_gap(sX, sY, pX, pY, x, y, p, &combined);
+        triples_push(&combined, x, y, top.v[3 * i + 2]);
         pX = x + 1;
         pY = y + 1;
     }
-    anchor_gap(sX, sY, pX, pY, lX, lY, p, combined);
-    stList_destruct(top);
-    return combined;
+    anchor_gap(sX, sY, pX, pY, lX, lY, p, &combined);
+    free(top.v);
+    stList *list = cpecan_tripleList_construct(combined.v, combined.n);
+    free(combined.v);
+    return list;
 }
