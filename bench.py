@@ -194,6 +194,60 @@ def capi_arm(cp, device, stream, model, params, packed, n, barrier):
             "api": "getAlignedPairsUsingAnchorsBatch (include/cpecan/pairwiseAligner.h), stList / stIntTuple in and out"}
 
 
+def cli_arm(n, length=1000):
+    """cPecanRealign itself, the program of the reference that north_star names: FASTA and cigars in, realigned cigars out, with its
+    own defaults (band of +-4 around the input alignment's matching columns, split at gaps of more than 10 cells).  The input
+    alignments are the anchor columns of synthetic evolved pairs; the process is started twice and the second run is timed, start to
+    exit -- CUDA context creation, parsing, one device pass per --batchBases, maximal-expected-accuracy alignment, output."""
+    from cpecan_b200 import synth
+
+    exe = os.path.join(ROOT, "cpecan_b200", "lib", "cPecanRealign")
+    if not os.path.exists(exe):
+        return {"value": None, "note": "cpecan_b200/lib/cPecanRealign is not built"}
+    packed = synth.evolved_pairs(n, length, seed=0xC1, trim=0, expansion=4)
+    fa, cig = "/tmp/cpecan_cli_%d.fa" % os.getpid(), "/tmp/cpecan_cli_%d.cigar" % os.getpid()
+    try:
+        with open(fa, "w") as f, open(cig, "w") as g:
+            for i in range(n):
+                sx, sy, a = synth.unpack(packed, i)
+                f.write(">x%d\n%s\n>y%d\n%s\n" % (i, sx.decode(), i, sy.decode()))
+                xs, ys = a[:, 0], a[:, 1]
+                if xs.size == 0:
+                    continue
+                # the input alignment: the anchor columns, the equally long stretches between them as mismatched columns of the same
+                # match operation (what an aligner emits for substitutions), the rest as a deletion and / or an insertion
+                gx, gy = np.diff(xs) - 1, np.diff(ys) - 1
+                ops, cur = [], int(xs[0])
+                for k in np.nonzero(gx != gy)[0]:
+                    both = int(min(gx[k], gy[k]))
+                    ops.append(("M", int(xs[k]) - cur + 1 + both))
+                    if gx[k] > both:
+                        ops.append(("D", int(gx[k]) - both))
+                    if gy[k] > both:
+                        ops.append(("I", int(gy[k]) - both))
+                    cur = int(xs[k + 1])
+                ops.append(("M", int(xs[-1]) - cur + 1))
+                g.write("cigar: y%d %d %d + x%d %d %d + 1.0%s\n" % (i, int(ys[0]), int(ys[-1]) + 1, i, int(xs[0]), int(xs[-1]) + 1,
+                                                                  "".join(" %s %d" % o for o in ops)))
+        wall, lines = None, 0
+        for _ in range(2):
+            t0 = time.perf_counter()
+            with open(cig) as g:
+                out = subprocess.run([exe, fa], stdin=g, capture_output=True, text=True, timeout=900)
+            wall = time.perf_counter() - t0
+            if out.returncode != 0:
+                return {"value": None, "note": "cPecanRealign failed: %s" % out.stderr.strip()[-300:]}
+            lines = sum(1 for l in out.stdout.splitlines() if l.startswith("cigar:"))
+        return {"value": n / wall, "unit": "pairs/s", "pairs": n, "cigars_out": lines, "s_process": wall,
+                "program": "cPecanRealign seqs.fa < alignments.cigar (its own defaults), whole process incl. CUDA context creation"}
+    except Exception as ex:
+        return {"value": None, "note": "cPecanRealign arm failed: %s" % ex}
+    finally:
+        for path in (fa, cig):
+            if os.path.exists(path):
+                os.remove(path)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -354,10 +408,11 @@ def main():
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
     e2e_value = cells_all * e2e_steps / float(tw[0]) / 1e9
 
-    e2e_capi = None
+    e2e_capi = e2e_cli = None
     if rank == 0 and world == 1 and not args.skip_e2e:
         ctx.close()  # the C API arm runs in its own process: give it the whole GPU (this context holds 70 % of HBM as scratch)
         e2e_capi = capi_arm(cp, local_rank, stream, model, params, packed, min(args.pairs, args.capi_pairs), barrier)
+        e2e_cli = cli_arm(min(args.pairs, args.capi_pairs))
     if rank == 0:
         hbm_peak, sm_max, peak_src = read_peaks()
         # The dominant kernel is the backward wavefront (one launch per chunk), then the forward one.  Both are bound by the FP64 pipe --
@@ -404,6 +459,8 @@ def main():
         }
         if e2e_capi is not None:
             line["e2e_capi"] = e2e_capi
+        if e2e_cli is not None:
+            line["e2e_cli"] = e2e_cli
         # CPU baseline on a bounded sample of the same workload
         try:
             if args.skip_cpu:

@@ -12,6 +12,7 @@
 #include <getopt.h>
 
 #include "cpecan/multipleAligner.h"
+#include "host_internal.h"
 #include "realignJobs.h"
 
 static void usage(void) {
@@ -92,15 +93,14 @@ static stList *score_anchor_pairs(stList *anchorPairs, stList *alignedPairs) {
 
 static void add_op(struct List *ops, int64_t type, int64_t length) { listAppend(ops, constructAlignmentOperation(type, length, 0)); }
 
-/* xy: (x, y) tuples sorted ascending */
+/* xy: n (x, y) pairs sorted ascending */
 static struct PairwiseAlignment *pairs_to_alignment(const char *name1, const char *name2, double score, int64_t length1, int64_t length2,
-                                                    stList *xy) {
+                                                    const int64_t *xy, int64_t n) {
     struct List *ops = constructEmptyList(0, (void (*)(void *)) destructAlignmentOperation);
     int64_t pX = -1, pY = -1, run = 0;
-    const int64_t n = stList_length(xy);
     for (int64_t i = 0; i <= n; i++) { /* a closing pair at (length1, length2) produces the trailing indels */
-        const int64_t x = i < n ? stIntTuple_get(stList_get(xy, i), 0) : length1;
-        const int64_t y = i < n ? stIntTuple_get(stList_get(xy, i), 1) : length2;
+        const int64_t x = i < n ? xy[2 * i] : length1;
+        const int64_t y = i < n ? xy[2 * i + 1] : length2;
         if (x - pX > 0 && y - pY > 0) { /* pairs that do not advance both sequences are dropped */
             if (x - pX > 1) {
                 if (run > 0) add_op(ops, PAIRWISE_MATCH, run);
@@ -119,6 +119,12 @@ static struct PairwiseAlignment *pairs_to_alignment(const char *name1, const cha
     }
     if (run > 1) add_op(ops, PAIRWISE_MATCH, run - 1); /* the closing pair itself is not a column */
     return constructPairwiseAlignment(name1, 0, length1, 1, name2, 0, length2, 1, score, ops);
+}
+
+static int by_x_then_y(const void *a, const void *b) {
+    const int64_t *p = a, *q = b;
+    if (p[0] != q[0]) return p[0] < q[0] ? -1 : 1;
+    return p[1] < q[1] ? -1 : (p[1] > q[1] ? 1 : 0);
 }
 
 /* ---- splitting at long indel runs (cPecanRealign.c:94-218) ---- */
@@ -204,14 +210,19 @@ static void job_finish(Job *j, stList *alignedPairs, const Options *o, const Pai
         write_posterior_probs(o->posteriorProbsFile, alignedPairs, j->shift1, j->flip1, pA->end1 - pA->start1, j->shift2, j->flip2, pA->end2 - pA->start2);
     }
     /* (weight, x, y) -> (x, y), ascending */
-    stList *xy = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
-    for (int64_t i = 0; i < stList_length(alignedPairs); i++) {
+    const int64_t nPairs = stList_length(alignedPairs);
+    int64_t *xy = xmalloc((size_t) (nPairs > 0 ? nPairs : 1) * 2 * sizeof(int64_t));
+    bool ascending = true;
+    for (int64_t i = 0; i < nPairs; i++) {
         stIntTuple *t = stList_get(alignedPairs, i);
-        stList_append(xy, stIntTuple_construct2(stIntTuple_get(t, 1), stIntTuple_get(t, 2)));
+        xy[2 * i] = stIntTuple_get(t, 1);
+        xy[2 * i + 1] = stIntTuple_get(t, 2);
+        ascending = ascending && (i == 0 || by_x_then_y(xy + 2 * (i - 1), xy + 2 * i) <= 0);
     }
     stList_destruct(alignedPairs);
-    stList_sort(xy, stIntTuple_cmpFn);
-    struct PairwiseAlignment *rPA = pairs_to_alignment(pA->contig1, pA->contig2, pA->score, pA->end1, pA->end2, xy);
+    if (!ascending) qsort(xy, (size_t) nPairs, 2 * sizeof(int64_t), by_x_then_y);
+    struct PairwiseAlignment *rPA = pairs_to_alignment(pA->contig1, pA->contig2, pA->score, pA->end1, pA->end2, xy, nPairs);
+    free(xy);
     rebase(&rPA->start1, &rPA->end1, &rPA->strand1, j->shift1, j->flip1);
     rebase(&rPA->start2, &rPA->end2, &rPA->strand2, j->shift2, j->flip2);
     checkPairwiseAlignment(rPA);
@@ -222,8 +233,32 @@ static void job_finish(Job *j, stList *alignedPairs, const Options *o, const Pai
     } else {
         cigarWrite(out, rPA, 0);
     }
-    stList_destruct(xy);
     destructPairwiseAlignment(rPA);
+}
+
+/* the host work on either side of a device pass, over a range of the batch's alignments (cpecan_parallel_for) */
+typedef struct {
+    Job *jobs;
+    stList **pairs;
+    char **text;
+    const PairwiseAlignmentParameters *p;
+    const Options *o;
+} HostPass;
+
+static void prepare_range(int64_t first, int64_t last, void *arg) {
+    HostPass *h = arg;
+    for (int64_t i = first; i < last; i++) job_prepare(&h->jobs[i], h->jobs[i].pA, h->p);
+}
+
+static void finish_range(int64_t first, int64_t last, void *arg) {
+    HostPass *h = arg;
+    for (int64_t i = first; i < last; i++) {
+        size_t size = 0;
+        FILE *f = open_memstream(&h->text[i], &size);
+        if (f == NULL) st_errAbort("cPecanRealign: out of memory");
+        job_finish(&h->jobs[i], h->pairs[i], h->o, h->p, f);
+        fclose(f);
+    }
 }
 
 int main(int argc, char *argv[]) {
@@ -338,11 +373,21 @@ int main(int argc, char *argv[]) {
                 jobs = realloc(jobs, (size_t) capJobs * sizeof(Job));
                 if (jobs == NULL) st_errAbort("cPecanRealign: out of memory");
             }
-            job_prepare(&jobs[n], pA, p);
-            bases += pA->end1 + pA->end2;
+            jobs[n].pA = pA; /* prepared below, all alignments of the batch on the host threads together */
+            bases += llabs((long long) (pA->end1 - pA->start1)) + llabs((long long) (pA->end2 - pA->start2));
             n++;
         }
         if (n == 0) break;
+        int64_t *work = xmalloc((size_t) (n + 1) * sizeof(int64_t)); /* prefix sums of the alignments' bases: how the host threads share them */
+        work[0] = 0;
+        for (int64_t i = 0; i < n; i++) {
+            const struct PairwiseAlignment *q = jobs[i].pA;
+            work[i + 1] = work[i] + llabs((long long) (q->end1 - q->start1)) + llabs((long long) (q->end2 - q->start2)) + 1;
+        }
+        {
+            HostPass pass = { jobs, NULL, NULL, p, NULL };
+            cpecan_parallel_for(n, work, prepare_range, &pass);
+        }
         const char **sX = xmalloc((size_t) n * sizeof(char *)), **sY = xmalloc((size_t) n * sizeof(char *));
         stList **anchors = xmalloc((size_t) n * sizeof(stList *));
         bool *ragged = xmalloc((size_t) n * sizeof(bool));
@@ -360,10 +405,24 @@ int main(int argc, char *argv[]) {
             o.reweightedOnDevice = !o.rescoreOriginalAlignment && o.allPosteriorProbsFile == NULL;
             stList **pairs = o.reweightedOnDevice ? getReweightedAlignedPairsUsingAnchorsBatch(sM, n, sX, sY, anchors, p, ragged, ragged, p->gapGamma)
                                                   : getAlignedPairsUsingAnchorsBatch(sM, n, sX, sY, anchors, p, ragged, ragged);
-            for (int64_t i = 0; i < n; i++) job_finish(&jobs[i], pairs[i], &o, p, stdout);
+            if (o.posteriorProbsFile != NULL || o.allPosteriorProbsFile != NULL) {
+                for (int64_t i = 0; i < n; i++) job_finish(&jobs[i], pairs[i], &o, p, stdout); /* they append to one file, in input order */
+            } else {
+                /* everything after the device pass is per alignment: on the host threads, each alignment's cigars into a buffer of
+                 * its own, the buffers to the standard output in input order */
+                char **text = xmalloc((size_t) n * sizeof(char *));
+                HostPass pass = { jobs, pairs, text, p, &o };
+                cpecan_parallel_for(n, work, finish_range, &pass);
+                for (int64_t i = 0; i < n; i++) {
+                    fputs(text[i], stdout);
+                    free(text[i]);
+                }
+                free(text);
+            }
             free(pairs);
         }
         for (int64_t i = 0; i < n; i++) job_release(&jobs[i]);
+        free(work);
         free(sX);
         free(sY);
         free(anchors);

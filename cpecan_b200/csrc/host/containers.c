@@ -3,6 +3,7 @@
  * (include/cpecan/sonLibLite.h).  Left out of the link when building against a real sonLib.
  */
 #ifndef CPECAN_USE_SONLIB
+#define _GNU_SOURCE /* qsort_r */
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -129,12 +130,12 @@ void stList_reverse(stList *l) {
     }
 }
 
-static int (*g_cmp)(const void *, const void *);
-static int cmp_indirect(const void *a, const void *b) { return g_cmp(*(void *const *) a, *(void *const *) b); }
+static int cmp_indirect(const void *a, const void *b, void *cmpFn) {
+    return ((int (*)(const void *, const void *)) cmpFn)(*(void *const *) a, *(void *const *) b);
+}
 
 void stList_sort(stList *l, int (*cmpFn)(const void *a, const void *b)) {
-    g_cmp = cmpFn; /* cPecan's callers are single threaded */
-    qsort(l->items, (size_t) l->length, sizeof(void *), cmp_indirect);
+    qsort_r(l->items, (size_t) l->length, sizeof(void *), cmp_indirect, (void *) cmpFn); /* no global: lists are sorted on several host threads */
 }
 
 static stIntTuple *tuple_new(int64_t n) {

@@ -15,6 +15,8 @@
  */
 #include <ctype.h>
 #include <inttypes.h>
+#include <stdbool.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -29,17 +31,43 @@ static stList *new_tuple_list(void) { return stList_construct3(0, (void (*)(void
 
 stList *convertPairwiseForwardStrandAlignmentToAnchorPairs(struct PairwiseAlignment *pA, int64_t trim, int64_t diagonalExpansion) {
     if (!pA->strand1 || !pA->strand2) st_errAbort("anchor pairs need a forward-strand alignment (%s / %s)", pA->contig1, pA->contig2);
-    stList *anchors = new_tuple_list();
-    int64_t x = pA->start1, y = pA->start2;
+    /* count first: the tuples of the list then come from one slab (cpecan_tripleList_construct) instead of one allocation per column,
+     * which is what a thousand columns per alignment times tens of thousands of alignments spent their time in */
+    int64_t n = 0, x = pA->start1, y = pA->start2;
     for (int64_t i = 0; i < pA->operationList->length; i++) {
         const struct AlignmentOperation *op = pA->operationList->list[i];
-        if (op->opType == PAIRWISE_MATCH) {
-            for (int64_t l = trim; l < op->length - trim; l++) stList_append(anchors, stIntTuple_construct3(x + l, y + l, diagonalExpansion));
-        }
+        if (op->opType == PAIRWISE_MATCH && op->length > 2 * trim) n += op->length - 2 * trim;
         if (op->opType != PAIRWISE_INDEL_Y) x += op->length;
         if (op->opType != PAIRWISE_INDEL_X) y += op->length;
     }
     if (x != pA->end1 || y != pA->end2) st_errAbort("cigar operations of %s / %s do not end at the alignment's end coordinates", pA->contig1, pA->contig2);
+    const bool narrow = pA->start1 >= 0 && pA->start2 >= 0 && x <= INT32_MAX && y <= INT32_MAX && diagonalExpansion >= INT32_MIN && diagonalExpansion <= INT32_MAX;
+    stList *anchors = narrow ? NULL : new_tuple_list();
+    int32_t *flat = narrow ? cpecan_malloc((size_t) (n > 0 ? n : 1) * 3 * sizeof(int32_t)) : NULL;
+    int64_t at = 0;
+    x = pA->start1;
+    y = pA->start2;
+    for (int64_t i = 0; i < pA->operationList->length; i++) {
+        const struct AlignmentOperation *op = pA->operationList->list[i];
+        if (op->opType == PAIRWISE_MATCH) {
+            for (int64_t l = trim; l < op->length - trim; l++) {
+                if (narrow) {
+                    flat[3 * at] = (int32_t) (x + l);
+                    flat[3 * at + 1] = (int32_t) (y + l);
+                    flat[3 * at + 2] = (int32_t) diagonalExpansion;
+                    at++;
+                } else {
+                    stList_append(anchors, stIntTuple_construct3(x + l, y + l, diagonalExpansion));
+                }
+            }
+        }
+        if (op->opType != PAIRWISE_INDEL_Y) x += op->length;
+        if (op->opType != PAIRWISE_INDEL_X) y += op->length;
+    }
+    if (narrow) {
+        anchors = cpecan_tripleList_construct(flat, at);
+        free(flat);
+    }
     return anchors;
 }
 
@@ -188,9 +216,30 @@ stList *filterPairwiseAlignmentToMakePairsOrdered(stList *alignedPairs, const ch
         }
         i = j;
     }
-    stList *out = new_tuple_list();
-    for (int64_t k = best; k >= 0; k = c[k].prev) stList_append(out, stIntTuple_construct3(c[k].w, c[k].x, c[k].y));
-    stList_reverse(out);
+    /* the chain, first pair first; its tuples from one slab when the coordinates allow (they do for anything the device aligned) */
+    int64_t len = 0;
+    bool narrow = true;
+    for (int64_t k = best; k >= 0; k = c[k].prev) {
+        len++;
+        narrow = narrow && c[k].x >= INT32_MIN && c[k].x <= INT32_MAX && c[k].y <= INT32_MAX && c[k].w >= INT32_MIN && c[k].w <= INT32_MAX;
+    }
+    stList *out;
+    if (narrow) {
+        int32_t *flat = cpecan_malloc((size_t) (len > 0 ? len : 1) * 3 * sizeof(int32_t));
+        int64_t at = len;
+        for (int64_t k = best; k >= 0; k = c[k].prev) {
+            at--;
+            flat[3 * at] = (int32_t) c[k].w;
+            flat[3 * at + 1] = (int32_t) c[k].x;
+            flat[3 * at + 2] = (int32_t) c[k].y;
+        }
+        out = cpecan_tripleList_construct(flat, len);
+        free(flat);
+    } else {
+        out = new_tuple_list();
+        for (int64_t k = best; k >= 0; k = c[k].prev) stList_append(out, stIntTuple_construct3(c[k].w, c[k].x, c[k].y));
+        stList_reverse(out);
+    }
     free(tree);
     free(c);
     stList_destruct(alignedPairs);
