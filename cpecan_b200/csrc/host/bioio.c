@@ -144,22 +144,10 @@ void checkPairwiseAlignment(struct PairwiseAlignment *pA) {
 
 /* next line of the stream without its newline, in a buffer the caller owns and reuses; NULL at end of file */
 static char *read_line(FILE *f, char **buf, size_t *cap) {
-    size_t n = 0;
-    int c;
-    while ((c = fgetc(f)) != EOF) {
-        if (n + 2 > *cap) {
-            *cap = *cap ? *cap * 2 : 256;
-            *buf = realloc(*buf, *cap);
-            if (*buf == NULL) st_errAbort("cpecan: out of memory reading a line");
-        }
-        if (c == '\n') break;
-        (*buf)[n++] = (char) c;
-    }
-    if (c == EOF && n == 0) return NULL;
-    if (*buf == NULL) {
-        *cap = 16;
-        *buf = cpecan_malloc(*cap);
-    }
+    const ssize_t got = getline(buf, cap, f); /* a character at a time through fgetc was a third of cPecanRealign's start-up on a 40 MB FASTA file */
+    if (got < 0) return NULL;
+    size_t n = (size_t) got;
+    if (n > 0 && (*buf)[n - 1] == '\n') n--;
     if (n > 0 && (*buf)[n - 1] == '\r') n--;
     (*buf)[n] = '\0';
     return *buf;
