@@ -10,6 +10,7 @@
  * engine's message.
  */
 #include <getopt.h>
+#include <time.h>
 
 #include "cpecan/multipleAligner.h"
 #include "host_internal.h"
@@ -261,7 +262,24 @@ static void finish_range(int64_t first, int64_t last, void *arg) {
     }
 }
 
+/* $CPECAN_HOST_TIMING: wall-clock time of the program's stages on stderr */
+static double g_stageClock;
+static bool g_stageTiming;
+static double stage_now(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
+static void stage(const char *what) {
+    if (!g_stageTiming) return;
+    const double t = stage_now();
+    fprintf(stderr, "[cPecanRealign] %-44s %8.1f ms\n", what, 1e3 * (t - g_stageClock));
+    g_stageClock = t;
+}
+
 int main(int argc, char *argv[]) {
+    g_stageTiming = getenv("CPECAN_HOST_TIMING") != NULL;
+    g_stageClock = stage_now();
     PairwiseAlignmentParameters *p = pairwiseAlignmentBandingParameters_construct();
     p->constraintDiagonalTrim = 0; /* the CLI's own defaults (cPecanRealign.c:359-361) */
     p->splitMatrixBiggerThanThis = 10;
@@ -355,6 +373,7 @@ int main(int argc, char *argv[]) {
         return 1;
     }
     read_sequence_files(argc, argv, optind);
+    stage("options, model, sequence files");
 
     /* read a batch of cigars, one device pass, finish and write them in order; repeat */
     Job *jobs = NULL;
@@ -378,6 +397,7 @@ int main(int argc, char *argv[]) {
             n++;
         }
         if (n == 0) break;
+        stage("cigars of the batch read");
         int64_t *work = xmalloc((size_t) (n + 1) * sizeof(int64_t)); /* prefix sums of the alignments' bases: how the host threads share them */
         work[0] = 0;
         for (int64_t i = 0; i < n; i++) {
@@ -397,6 +417,7 @@ int main(int argc, char *argv[]) {
             anchors[i] = jobs[i].filtered;
             ragged[i] = 1; /* both ends of a local alignment are ragged (cPecanRealign.c:532, :537) */
         }
+        stage("sub-sequences and anchors (host threads)");
         log_info("Device pass over %" PRIi64 " alignments, %" PRIi64 " bases\n", n, bases);
         if (hmmExpectations != NULL) {
             getExpectationsUsingAnchorsBatch(sM, hmmExpectations, n, sX, sY, anchors, p, ragged, ragged);
@@ -405,6 +426,7 @@ int main(int argc, char *argv[]) {
             o.reweightedOnDevice = !o.rescoreOriginalAlignment && o.allPosteriorProbsFile == NULL;
             stList **pairs = o.reweightedOnDevice ? getReweightedAlignedPairsUsingAnchorsBatch(sM, n, sX, sY, anchors, p, ragged, ragged, p->gapGamma)
                                                   : getAlignedPairsUsingAnchorsBatch(sM, n, sX, sY, anchors, p, ragged, ragged);
+            stage("batch call (device pass + lists)");
             if (o.posteriorProbsFile != NULL || o.allPosteriorProbsFile != NULL) {
                 for (int64_t i = 0; i < n; i++) job_finish(&jobs[i], pairs[i], &o, p, stdout); /* they append to one file, in input order */
             } else {
@@ -420,6 +442,7 @@ int main(int argc, char *argv[]) {
                 free(text);
             }
             free(pairs);
+            stage("chains, cigars out (host threads)");
         }
         for (int64_t i = 0; i < n; i++) job_release(&jobs[i]);
         free(work);
@@ -442,6 +465,7 @@ int main(int argc, char *argv[]) {
     stateMachine_destruct(sM);
     pairwiseAlignmentBandingParameters_destruct(p);
     cpecan_shutdown();
+    stage("release");
     log_info("Finished realigning pairwise alignments, exiting.\n");
     return 0;
 }
