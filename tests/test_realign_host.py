@@ -338,6 +338,10 @@ int main(int argc, char **argv) {
     assert out[3] == "cigar: seq2 30 10 - seq1 100 125 + 0.000000 M 10 I 5 M 5 D 10"
     assert out[4:7] == ["seq [one first record] 8 ACGTACGT", "seq [two] 0 ", "seq [three\tx] 8 NNNNacgt"]
     assert out[7] == "rc YacgtNACGT"
+    # the same files with DOS line ends read the same
+    (tmp_path / "dos.cig").write_bytes(CIGARS.replace("\n", "\r\n").encode())
+    (tmp_path / "dos.fa").write_bytes(b">one first record\r\nACGT\r\nAC GT\r\n\r\n>two\r\n>three\tx\r\nNNNN\r\nacgt")
+    assert subprocess.check_output([str(exe), str(tmp_path / "dos.cig"), str(tmp_path / "dos.fa")], text=True).splitlines() == out
 
 
 LIB_DIR = os.path.dirname(HOST_SO)
